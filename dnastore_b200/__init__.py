@@ -1,0 +1,28 @@
+"""dnastore_b200 -- B200-native batched Viterbi decoder for ihh/dnastore's hot path.
+
+The product is the C-ABI shared library ``libdnastore_b200.so`` (CUDA sm_100a
+kernels + C++ host, see ``include/dnastore_b200.h``).  This package is only the
+thin ctypes binding tests and ``bench.py`` call it through; it contains no
+compute and NO CPU fallback: importing it without the built library raises, and
+creating a decoder without a CUDA device raises.
+"""
+from ._capi import (  # noqa: F401
+    DnabError,
+    Machine,
+    ErrorFlags,
+    Compiled,
+    Decoder,
+    Tables,
+    lib,
+    lib_path,
+    pack_reads,
+    READ_OK,
+    READ_NO_DECODING,
+    READ_OVERFLOW,
+    READ_TRACEBACK_FAILED,
+)
+
+__all__ = [
+    "DnabError", "Machine", "ErrorFlags", "Compiled", "Decoder", "Tables", "lib", "lib_path", "pack_reads",
+    "READ_OK", "READ_NO_DECODING", "READ_OVERFLOW", "READ_TRACEBACK_FAILED",
+]

@@ -1,0 +1,336 @@
+"""ctypes binding of include/dnastore_b200.h (one class per opaque handle).
+
+Names mirror the reference's: ``Machine.from_file`` / ``Machine.compose`` /
+``Machine.to_json`` (reference src/trans.h:83-126), ``ErrorFlags`` = the CLI's
+error-model flags (reference t/dnastore.cpp:69-75), ``Decoder.decode_fasta`` =
+``decodeFastSeqs`` (reference src/viterbi.h:108).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libdnastore_b200.so")
+
+if not os.path.exists(lib_path):
+    raise ImportError(
+        f"{lib_path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C dnastore_b200/csrc`). There is no Python/CPU fallback."
+    )
+lib = C.CDLL(lib_path)
+
+READ_OK, READ_NO_DECODING, READ_OVERFLOW, READ_TRACEBACK_FAILED = 0, 1, 2, 3
+
+
+class DnabError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dnab error {code}: {msg}")
+        self.code = code
+
+
+class Tables(C.Structure):
+    """struct dnab_tables (include/dnab_tables.h)."""
+    _fields_ = [
+        ("n_states", C.c_uint32), ("k", C.c_uint32), ("local", C.c_uint32), ("n_emit", C.c_uint32), ("n_null", C.c_uint32),
+        ("emit_off", C.POINTER(C.c_uint32)), ("emit_src", C.POINTER(C.c_uint32)), ("emit_score", C.POINTER(C.c_double)),
+        ("emit_base", C.POINTER(C.c_uint8)), ("emit_in", C.POINTER(C.c_uint8)),
+        ("null_off", C.POINTER(C.c_uint32)), ("null_src", C.POINTER(C.c_uint32)), ("null_score", C.POINTER(C.c_double)),
+        ("null_in", C.POINTER(C.c_uint8)),
+        ("ctx", C.POINTER(C.c_uint8)), ("mdl", C.POINTER(C.c_uint8)),
+        ("noGap", C.c_double), ("delOpen", C.c_double), ("delExtend", C.c_double), ("delEnd", C.c_double), ("tanDup", C.c_double),
+        ("sub", C.c_double * 16),
+        ("len", C.POINTER(C.c_double)),
+    ]
+
+
+class ErrorFlags(C.Structure):
+    """struct dnab_error_flags: the CLI's error-model flags with the reference's defaults."""
+    _fields_ = [("length", C.c_int32), ("global_", C.c_int32), ("sub_prob", C.c_double), ("iv_ratio", C.c_double),
+                ("dup_prob", C.c_double), ("del_open", C.c_double), ("del_ext", C.c_double)]
+
+    def __init__(self, length=12, global_=False, sub_prob=.01, iv_ratio=10., dup_prob=.001, del_open=.001, del_ext=.01):
+        super().__init__(int(length), int(bool(global_)), sub_prob, iv_ratio, dup_prob, del_open, del_ext)
+
+
+class DecoderInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("n_states", "k", "local", "cluster_size", "states_per_cta", "threads_per_cta",
+                                          "smem_bytes_per_cta", "t_in_smem", "n_clusters", "sm_count")]
+
+
+class DecoderStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("fill_launches", C.c_uint64), ("traceback_launches", C.c_uint64),
+                ("reads", C.c_uint64), ("cells", C.c_uint64), ("last_fill_ms", C.c_double), ("last_traceback_ms", C.c_double)]
+
+
+def _sig(name, restype, *argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+_vp = C.c_void_p
+_sig("dnab_last_error", C.c_char_p)
+_sig("dnab_version", C.c_char_p)
+_sig("dnab_free", None, _vp)
+_sig("dnab_machine_load", _vp, C.c_char_p)
+_sig("dnab_machine_from_json", _vp, C.c_char_p)
+_sig("dnab_machine_compose", _vp, _vp, _vp)
+_sig("dnab_machine_to_json", _vp, _vp)
+_sig("dnab_machine_n_states", C.c_uint32, _vp)
+_sig("dnab_machine_max_left_context", C.c_uint32, _vp)
+_sig("dnab_machine_input_alphabet", C.c_int, _vp, C.c_int, C.c_char_p, C.c_size_t)
+_sig("dnab_machine_free", None, _vp)
+_sig("dnab_error_flags_default", None, C.POINTER(ErrorFlags))
+_sig("dnab_compile", _vp, _vp, C.POINTER(ErrorFlags))
+_sig("dnab_compile_with_error_file", _vp, _vp, C.c_char_p)
+_sig("dnab_compiled_tables", C.POINTER(Tables), _vp)
+_sig("dnab_compiled_free", None, _vp)
+_sig("dnab_decoder_create", _vp, C.POINTER(Tables), C.c_int)
+_sig("dnab_decoder_destroy", None, _vp)
+_sig("dnab_decoder_get_info", C.c_int, _vp, C.POINTER(DecoderInfo))
+_sig("dnab_decoder_configure", C.c_int, _vp, C.c_uint32, C.c_uint32, C.c_uint32)
+_sig("dnab_decoder_get_stats", C.c_int, _vp, C.POINTER(DecoderStats))
+_sig("dnab_packed_size", C.c_size_t, _vp, C.c_int64)
+_sig("dnab_pack_reads", C.c_int, C.c_char_p, _vp, C.c_int64, _vp, _vp, _vp)
+_sig("dnab_viterbi_batch", C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp)
+_sig("dnab_viterbi_batch_device", C.c_int, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp)
+_sig("dnab_viterbi_cells", C.c_int, _vp, _vp, C.c_int32, _vp, _vp)
+_sig("dnab_decode_fasta", _vp, _vp, C.c_char_p)
+_sig("dnab_decoded_count", C.c_int64, _vp)
+_sig("dnab_decoded_name", C.c_char_p, _vp, C.c_int64)
+_sig("dnab_decoded_seq", C.c_char_p, _vp, C.c_int64)
+_sig("dnab_decoded_loglike", C.c_double, _vp, C.c_int64)
+_sig("dnab_decoded_status", C.c_int32, _vp, C.c_int64)
+_sig("dnab_decoded_free", None, _vp)
+
+
+def _err(code=-1):
+    return DnabError(code, lib.dnab_last_error().decode(errors="replace"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+class Machine:
+    """dnastore transducer handle (reference src/trans.h:83-126)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise _err()
+        self._h = handle
+
+    @classmethod
+    def from_file(cls, path):
+        return cls(lib.dnab_machine_load(os.fspath(path).encode()))
+
+    @classmethod
+    def from_json(cls, text):
+        return cls(lib.dnab_machine_from_json(text.encode()))
+
+    @classmethod
+    def compose(cls, first, second):
+        """Machine::compose(first, second): first's output feeds second's input."""
+        return cls(lib.dnab_machine_compose(first._h, second._h))
+
+    @classmethod
+    def load_composed(cls, base, composes=()):
+        """--load-machine BASE --compose-machine C1 --compose-machine C2 ...:
+        applied right to left, so the first listed is outermost (reference t/dnastore.cpp:159-165)."""
+        m = cls.from_file(base)
+        for c in reversed(list(composes)):
+            m = cls.compose(cls.from_file(c), m)
+        return m
+
+    def to_json(self):
+        p = lib.dnab_machine_to_json(self._h)
+        if not p:
+            raise _err()
+        try:
+            return C.string_at(p).decode()
+        finally:
+            lib.dnab_free(p)
+
+    @property
+    def n_states(self):
+        return lib.dnab_machine_n_states(self._h)
+
+    @property
+    def max_left_context(self):
+        return lib.dnab_machine_max_left_context(self._h)
+
+    def input_alphabet(self, flags=2 | 8 | 16):
+        buf = C.create_string_buffer(256)
+        rc = lib.dnab_machine_input_alphabet(self._h, flags, buf, 256)
+        if rc:
+            raise _err(rc)
+        return buf.value.decode()
+
+    def compile(self, flags=None, error_file=None):
+        return Compiled(self, flags, error_file)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.dnab_machine_free(self._h)
+            self._h = None
+
+
+class Compiled:
+    """Flat tables in host memory (include/dnab_tables.h)."""
+
+    def __init__(self, machine, flags=None, error_file=None):
+        self._machine = machine
+        if error_file is not None:
+            h = lib.dnab_compile_with_error_file(machine._h, os.fspath(error_file).encode())
+        else:
+            self.flags = flags if flags is not None else ErrorFlags()
+            h = lib.dnab_compile(machine._h, C.byref(self.flags))
+        if not h:
+            raise _err()
+        self._h = h
+        self.tables = lib.dnab_compiled_tables(h)
+
+    @property
+    def t(self):
+        return self.tables.contents
+
+    def arrays(self):
+        """numpy views of the tables (for tests)."""
+        t = self.t
+        n, k = t.n_states, t.k
+
+        def arr(p, count, dt):
+            if count == 0:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(p, shape=(count,)).astype(dt, copy=True)
+
+        return dict(
+            n_states=n, k=k, local=t.local,
+            emit_off=arr(t.emit_off, n + 1, np.uint32), emit_src=arr(t.emit_src, t.n_emit, np.uint32),
+            emit_score=arr(t.emit_score, t.n_emit, np.float64), emit_base=arr(t.emit_base, t.n_emit, np.uint8),
+            emit_in=arr(t.emit_in, t.n_emit, np.uint8),
+            null_off=arr(t.null_off, n + 1, np.uint32), null_src=arr(t.null_src, t.n_null, np.uint32),
+            null_score=arr(t.null_score, t.n_null, np.float64), null_in=arr(t.null_in, t.n_null, np.uint8),
+            ctx=arr(t.ctx, n * k, np.uint8), mdl=arr(t.mdl, n, np.uint8),
+            noGap=t.noGap, delOpen=t.delOpen, delExtend=t.delExtend, delEnd=t.delEnd, tanDup=t.tanDup,
+            sub=np.array(list(t.sub)), len=arr(t.len, k, np.float64),
+        )
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.dnab_compiled_free(self._h)
+            self._h = None
+
+
+def pack_reads(reads):
+    """ASCII reads -> (packed uint8, byte_off int64, read_len int32): 2 bits per base."""
+    n = len(reads)
+    joined = "".join(reads).encode()
+    base_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in reads], out=base_off[1:])
+    read_len = np.diff(base_off).astype(np.int32)
+    packed = np.zeros(lib.dnab_packed_size(_ptr(read_len), n), dtype=np.uint8)
+    byte_off = np.zeros(n, dtype=np.int64)
+    rc = lib.dnab_pack_reads(joined, _ptr(base_off), n, _ptr(packed), _ptr(byte_off), _ptr(read_len))
+    if rc:
+        raise _err(rc)
+    return packed, byte_off, read_len
+
+
+class Decoder:
+    """Tables resident on one GPU + the CUDA kernels. Raises without a CUDA device."""
+
+    def __init__(self, compiled, device=0):
+        self._compiled = compiled
+        h = lib.dnab_decoder_create(compiled.tables, int(device))
+        if not h:
+            raise _err(-2)
+        self._h = h
+        self.device = int(device)
+
+    def configure(self, cluster_size=0, threads_per_cta=0, t_in_smem_mode=0):
+        rc = lib.dnab_decoder_configure(self._h, cluster_size, threads_per_cta, t_in_smem_mode)
+        if rc:
+            raise _err(rc)
+
+    def info(self):
+        i = DecoderInfo()
+        rc = lib.dnab_decoder_get_info(self._h, C.byref(i))
+        if rc:
+            raise _err(rc)
+        return {n: getattr(i, n) for n, _ in DecoderInfo._fields_}
+
+    def stats(self):
+        s = DecoderStats()
+        lib.dnab_decoder_get_stats(self._h, C.byref(s))
+        return {n: getattr(s, n) for n, _ in DecoderStats._fields_}
+
+    def viterbi(self, reads, want_path=False, decoded_stride=None, path_stride=None):
+        """Decode ASCII reads through host buffers. Returns dict(loglike, decoded, status[, path])."""
+        packed, byte_off, read_len = pack_reads(reads)
+        return self.viterbi_packed(packed, byte_off, read_len, want_path, decoded_stride, path_stride)
+
+    def viterbi_packed(self, packed, byte_off, read_len, want_path=False, decoded_stride=None, path_stride=None):
+        n = len(read_len)
+        max_len = int(read_len.max()) if n else 0
+        stride = int(decoded_stride or (8 * max_len + 1024))
+        loglike = np.zeros(n, dtype=np.float64)
+        decoded = np.zeros((n, stride), dtype=np.uint8)
+        dec_len = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        path = path_len = None
+        pstride = 0
+        if want_path:
+            pstride = int(path_stride or (16 * max_len + 4096))
+            path = np.zeros((n, pstride, 3), dtype=np.int32)
+            path_len = np.zeros(n, dtype=np.int32)
+        rc = lib.dnab_viterbi_batch(self._h, n, _ptr(packed), _ptr(byte_off), _ptr(read_len), _ptr(loglike), _ptr(decoded),
+                                    stride, _ptr(dec_len), _ptr(status), _ptr(path) if want_path else None, pstride,
+                                    _ptr(path_len) if want_path else None)
+        if rc:
+            raise _err(rc)
+        out = dict(loglike=loglike, status=status,
+                   decoded=[bytes(decoded[r, :dec_len[r]]).decode("latin1") for r in range(n)])
+        if want_path:
+            out["path"] = [path[r, :min(path_len[r], pstride)].copy() for r in range(n)]
+            out["path_len"] = path_len
+        return out
+
+    def viterbi_cells(self, read):
+        """One read; returns (loglike, cells[(L+1), n_states, k+2]) in the reference's layout."""
+        packed, byte_off, read_len = pack_reads([read])
+        t = self._compiled.t
+        L = int(read_len[0])
+        cells = np.zeros((L + 1, t.n_states, t.k + 2), dtype=np.float64)
+        ll = C.c_double(0)
+        rc = lib.dnab_viterbi_cells(self._h, _ptr(packed), L, C.byref(ll), _ptr(cells))
+        if rc:
+            raise _err(rc)
+        return ll.value, cells
+
+    def viterbi_device(self, n_reads, max_read_len, d_packed, d_byte_off, d_read_len, d_loglike, d_decoded, decoded_stride,
+                       d_decoded_len, d_status, stream=0):
+        """All arguments are raw device pointers (ints), e.g. torch tensors' .data_ptr()."""
+        rc = lib.dnab_viterbi_batch_device(self._h, n_reads, max_read_len, d_packed, d_byte_off, d_read_len, d_loglike,
+                                           d_decoded, decoded_stride, d_decoded_len, d_status, stream)
+        if rc:
+            raise _err(rc)
+
+    def decode_fasta(self, path):
+        """decodeFastSeqs: [(name, decoded string, loglike, status)] in input order."""
+        s = lib.dnab_decode_fasta(self._h, os.fspath(path).encode())
+        if not s:
+            raise _err()
+        try:
+            return [(lib.dnab_decoded_name(s, i).decode(), lib.dnab_decoded_seq(s, i).decode("latin1"),
+                     lib.dnab_decoded_loglike(s, i), lib.dnab_decoded_status(s, i))
+                    for i in range(lib.dnab_decoded_count(s))]
+        finally:
+            lib.dnab_decoded_free(s)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.dnab_decoder_destroy(self._h)
+            self._h = None

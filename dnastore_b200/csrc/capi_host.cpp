@@ -1,0 +1,214 @@
+// Host half of the C ABI (include/dnastore_b200.h): machines, error model, table
+// compilation, read packing and the decodeFastSeqs drop-in.  Exceptions from the
+// C++ host classes are turned into error codes here; none crosses the boundary.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dnastore_b200.h"
+#include "capi_error.h"
+#include "host/fasta.h"
+#include "host/machine.h"
+#include "host/tables.h"
+
+namespace dnab {
+static thread_local std::string g_lastError;
+void setLastError(const std::string& msg) { g_lastError = msg; }
+}  // namespace dnab
+
+using namespace dnab;
+
+struct dnab_machine {
+  Machine m;
+};
+struct dnab_compiled {
+  CompiledTables c;
+};
+struct dnab_decoded_set {
+  std::vector<std::string> names, seqs;
+  std::vector<double> loglike;
+  std::vector<int32_t> status;
+};
+
+template <class F>
+static auto guarded(F&& f, decltype(f()) onError) -> decltype(f()) {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    setLastError(e.what());
+  } catch (...) {
+    setLastError("unknown error");
+  }
+  return onError;
+}
+
+extern "C" {
+
+const char* dnab_last_error(void) { return g_lastError.c_str(); }
+const char* dnab_version(void) { return "dnastore_b200 0.1 (sm_100a)"; }
+void dnab_free(void* p) { std::free(p); }
+
+dnab_machine* dnab_machine_load(const char* json_path) {
+  return guarded([&]() { return new dnab_machine{Machine::fromFile(json_path)}; }, (dnab_machine*)nullptr);
+}
+dnab_machine* dnab_machine_from_json(const char* json_text) {
+  return guarded([&]() { return new dnab_machine{Machine::fromJSONText(json_text)}; }, (dnab_machine*)nullptr);
+}
+dnab_machine* dnab_machine_compose(const dnab_machine* first, const dnab_machine* second) {
+  if (!first || !second) {
+    setLastError("dnab_machine_compose: null machine");
+    return nullptr;
+  }
+  return guarded([&]() { return new dnab_machine{Machine::compose(first->m, second->m)}; }, (dnab_machine*)nullptr);
+}
+char* dnab_machine_to_json(const dnab_machine* m) {
+  if (!m) return nullptr;
+  return guarded(
+      [&]() {
+        const std::string s = m->m.toJSON();
+        char* out = (char*)std::malloc(s.size() + 1);
+        if (!out) throw std::bad_alloc();
+        std::memcpy(out, s.c_str(), s.size() + 1);
+        return out;
+      },
+      (char*)nullptr);
+}
+uint32_t dnab_machine_n_states(const dnab_machine* m) { return m ? (uint32_t)m->m.nStates() : 0; }
+uint32_t dnab_machine_max_left_context(const dnab_machine* m) { return m ? (uint32_t)m->m.maxLeftContext() : 0; }
+int dnab_machine_input_alphabet(const dnab_machine* m, int flags, char* out, size_t cap) {
+  if (!m || !out || !cap) return DNAB_EINVAL;
+  const std::string a = m->m.inputAlphabet(flags);
+  if (a.size() + 1 > cap) {
+    setLastError("dnab_machine_input_alphabet: buffer too small");
+    return DNAB_EINVAL;
+  }
+  std::memcpy(out, a.c_str(), a.size() + 1);
+  return DNAB_OK;
+}
+void dnab_machine_free(dnab_machine* m) { delete m; }
+
+void dnab_error_flags_default(dnab_error_flags* f) {
+  if (!f) return;
+  f->length = 12;
+  f->global = 0;
+  f->sub_prob = .01;
+  f->iv_ratio = 10;
+  f->dup_prob = .001;
+  f->del_open = .001;
+  f->del_ext = .01;
+}
+
+static dnab_compiled* compileWith(const dnab_machine* m, const MutatorParams& params) {
+  auto* c = new dnab_compiled();
+  try {
+    compileTables(m->m, params, c->c);
+  } catch (...) {
+    delete c;
+    throw;
+  }
+  return c;
+}
+
+dnab_compiled* dnab_compile(const dnab_machine* m, const dnab_error_flags* f) {
+  if (!m || !f) {
+    setLastError("dnab_compile: null argument");
+    return nullptr;
+  }
+  return guarded(
+      [&]() {
+        return compileWith(m, MutatorParams::fromFlags(f->length, f->sub_prob, f->iv_ratio, f->dup_prob, f->del_open,
+                                                       f->del_ext, f->global != 0));
+      },
+      (dnab_compiled*)nullptr);
+}
+dnab_compiled* dnab_compile_with_error_file(const dnab_machine* m, const char* error_json_path) {
+  if (!m || !error_json_path) {
+    setLastError("dnab_compile_with_error_file: null argument");
+    return nullptr;
+  }
+  return guarded([&]() { return compileWith(m, MutatorParams::fromFile(error_json_path)); }, (dnab_compiled*)nullptr);
+}
+const dnab_tables* dnab_compiled_tables(const dnab_compiled* c) { return c ? &c->c.t : nullptr; }
+void dnab_compiled_free(dnab_compiled* c) { delete c; }
+
+size_t dnab_packed_size(const int32_t* read_len, int64_t n_reads) { return packedSize(read_len, n_reads); }
+
+int dnab_pack_reads(const char* bases, const int64_t* base_off, int64_t n_reads, uint8_t* packed, int64_t* read_byte_off,
+                    int32_t* read_len) {
+  char bad = 0;
+  const int64_t r = packReads(bases, base_off, n_reads, packed, read_byte_off, read_len, &bad);
+  if (r >= 0) {
+    setLastError(std::string("Unknown symbol ") + bad + " in sequence " + std::to_string(r) + " (alphabet is ACGT)");
+    return DNAB_EFORMAT;
+  }
+  return DNAB_OK;
+}
+
+dnab_decoded_set* dnab_decode_fasta(dnab_decoder* d, const char* fasta_path) {
+  if (!d || !fasta_path) {
+    setLastError("dnab_decode_fasta: null argument");
+    return nullptr;
+  }
+  return guarded(
+      [&]() -> dnab_decoded_set* {
+        const std::vector<FastSeq> reads = readFastSeqs(fasta_path);
+        const int64_t n = (int64_t)reads.size();
+        auto* out = new dnab_decoded_set();
+        if (n == 0) return out;
+        std::string bases;
+        std::vector<int64_t> baseOff(n + 1, 0);
+        for (int64_t r = 0; r < n; ++r) {
+          bases += reads[r].seq;
+          baseOff[r + 1] = (int64_t)bases.size();
+        }
+        std::vector<int32_t> len(n);
+        for (int64_t r = 0; r < n; ++r) len[r] = (int32_t)reads[r].seq.size();
+        std::vector<uint8_t> packed(packedSize(len.data(), n));
+        std::vector<int64_t> byteOff(n);
+        char bad = 0;
+        const int64_t badRead = packReads(bases.data(), baseOff.data(), n, packed.data(), byteOff.data(), len.data(), &bad);
+        if (badRead >= 0) {
+          delete out;
+          throw std::runtime_error(std::string("Unknown symbol ") + bad + " in sequence " + reads[badRead].name +
+                                   " (alphabet is ACGT)");
+        }
+        int32_t maxLen = 0;
+        for (int32_t l : len) maxLen = std::max(maxLen, l);
+        int32_t stride = 8 * maxLen + 1024;
+        std::vector<double> ll(n);
+        std::vector<int32_t> decLen(n), status(n);
+        std::vector<char> dec;
+        for (int attempt = 0; attempt < 4; ++attempt) {
+          dec.assign((size_t)n * stride, 0);
+          const int rc = dnab_viterbi_batch(d, n, packed.data(), byteOff.data(), len.data(), ll.data(), dec.data(), stride,
+                                            decLen.data(), status.data(), nullptr, 0, nullptr);
+          if (rc != DNAB_OK) {
+            delete out;
+            throw std::runtime_error(dnab_last_error());
+          }
+          bool overflow = false;
+          for (int32_t s : status) overflow |= (s == DNAB_READ_OVERFLOW);
+          if (!overflow) break;
+          stride *= 8;
+        }
+        out->loglike = ll;
+        out->status = status;
+        for (int64_t r = 0; r < n; ++r) {
+          out->names.push_back(reads[r].name);
+          out->seqs.emplace_back(dec.data() + (size_t)r * stride, (size_t)decLen[r]);
+        }
+        return out;
+      },
+      (dnab_decoded_set*)nullptr);
+}
+int64_t dnab_decoded_count(const dnab_decoded_set* s) { return s ? (int64_t)s->seqs.size() : 0; }
+const char* dnab_decoded_name(const dnab_decoded_set* s, int64_t i) { return s->names[i].c_str(); }
+const char* dnab_decoded_seq(const dnab_decoded_set* s, int64_t i) { return s->seqs[i].c_str(); }
+double dnab_decoded_loglike(const dnab_decoded_set* s, int64_t i) { return s->loglike[i]; }
+int32_t dnab_decoded_status(const dnab_decoded_set* s, int64_t i) { return s->status[i]; }
+void dnab_decoded_free(dnab_decoded_set* s) { delete s; }
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+// dnastore-b200: command-line front end that keeps dnastore's flags for the Viterbi
+// path and calls the GPU decoder through the C ABI (include/dnastore_b200.h).
+//
+// Flag names, defaults and meaning follow the reference's main
+// (reference t/dnastore.cpp:41-82,115-130,150-176,217-223):
+//   -l/--length N (12)            k-mer length; sets maxDupLen = N/2
+//   -L/--load-machine FILE        machine JSON (plain or .gz)
+//   -C/--compose-machine FILE     repeatable; first listed = outermost
+//   -S/--save-machine FILE|-      write the (composed) machine JSON
+//   -V/--decode-viterbi FASTA     batched Viterbi decode on the GPU
+//   -r/--raw                      print bare decoded strings, one per line
+//   --error-sub-prob (.01) --error-iv-ratio (10) --error-dup-prob (.001)
+//   --error-del-open (.001) --error-del-ext (.01) --error-global  -F/--error-file
+//   -v/--verbose N                accepted (0 = quiet); >=2 prints decoder info to stderr
+//   --device N                    CUDA ordinal (new)
+// Machine construction (-l without -L), the exact codec (-e/-d/-E/-D/-b/-B) and error
+// model fitting are outside this build's scope and are reported as such.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../include/dnastore_b200.h"
+
+static void die(const std::string& msg, int code = 1) {
+  std::cerr << msg << std::endl;
+  std::exit(code);
+}
+
+int main(int argc, char** argv) {
+  dnab_error_flags ef;
+  dnab_error_flags_default(&ef);
+  std::string loadMachine, saveMachine, viterbiFile, errorFile;
+  std::vector<std::string> composes;
+  bool raw = false;
+  int verbose = 2, device = 0;
+
+  auto longName = [](const std::string& a, std::string& name, std::string& val, bool& hasVal) {
+    name = a.substr(2);
+    const size_t eq = name.find('=');
+    hasVal = eq != std::string::npos;
+    if (hasVal) {
+      val = name.substr(eq + 1);
+      name = name.substr(0, eq);
+    }
+  };
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i], name, val;
+    bool hasVal = false;
+    if (a.size() > 2 && a[0] == '-' && a[1] == '-')
+      longName(a, name, val, hasVal);
+    else if (a.size() >= 2 && a[0] == '-') {
+      static const struct { char s; const char* l; } shorts[] = {
+          {'l', "length"}, {'L', "load-machine"}, {'C', "compose-machine"}, {'S', "save-machine"},
+          {'V', "decode-viterbi"}, {'r', "raw"}, {'F', "error-file"}, {'v', "verbose"}, {'h', "help"},
+          {'d', "decode-file"}, {'e', "encode-file"}, {'E', "encode-string"}, {'D', "decode-string"},
+          {'b', "encode-bits"}, {'B', "decode-bits"}, {'f', "fit-error"}};
+      for (const auto& s : shorts)
+        if (s.s == a[1]) name = s.l;
+      if (name.empty()) die("unrecognised option '" + a + "'");
+      if (a.size() > 2) {
+        val = a.substr(2);
+        hasVal = true;
+      }
+    } else
+      die("too many positional options have been specified on the command line");
+    auto need = [&]() -> std::string {
+      if (hasVal) return val;
+      if (i + 1 >= argc) die("the required argument for option '--" + name + "' is missing");
+      return argv[++i];
+    };
+    if (name == "help") {
+      std::cout << "dnastore-b200: GPU Viterbi decoder behind dnastore's -V path; see the header of cli_main.cpp\n";
+      return 1;
+    } else if (name == "length") ef.length = std::atoi(need().c_str());
+    else if (name == "load-machine") loadMachine = need();
+    else if (name == "compose-machine") composes.push_back(need());
+    else if (name == "save-machine") saveMachine = need();
+    else if (name == "decode-viterbi") viterbiFile = need();
+    else if (name == "raw") raw = true;
+    else if (name == "error-sub-prob") ef.sub_prob = std::atof(need().c_str());
+    else if (name == "error-iv-ratio") ef.iv_ratio = std::atof(need().c_str());
+    else if (name == "error-dup-prob") ef.dup_prob = std::atof(need().c_str());
+    else if (name == "error-del-open") ef.del_open = std::atof(need().c_str());
+    else if (name == "error-del-ext") ef.del_ext = std::atof(need().c_str());
+    else if (name == "error-global") ef.global = 1;
+    else if (name == "error-file") errorFile = need();
+    else if (name == "verbose") verbose = std::atoi(need().c_str());
+    else if (name == "device") device = std::atoi(need().c_str());
+    else if (name == "nocolor") {}
+    else if (name == "log") (void)need();
+    else
+      die("option '--" + name + "' is outside the scope of dnastore-b200 (Viterbi decoding path only)", 2);
+  }
+  if (ef.length > 31) die("Maximum context is 31 bases");
+  if (loadMachine.empty()) die("dnastore-b200 needs --load-machine (machine construction is out of scope; "
+                               "machines are reproducible only as JSON)", 2);
+
+  dnab_machine* machine = dnab_machine_load(loadMachine.c_str());
+  if (!machine) die(dnab_last_error());
+  // compose arguments are applied right to left, so the first listed is outermost
+  for (auto it = composes.rbegin(); it != composes.rend(); ++it) {
+    dnab_machine* outer = dnab_machine_load(it->c_str());
+    if (!outer) die(dnab_last_error());
+    dnab_machine* composed = dnab_machine_compose(outer, machine);
+    if (!composed) die(dnab_last_error());
+    dnab_machine_free(outer);
+    dnab_machine_free(machine);
+    machine = composed;
+  }
+
+  if (!saveMachine.empty()) {
+    char* text = dnab_machine_to_json(machine);
+    if (!text) die(dnab_last_error());
+    if (saveMachine == "-")
+      std::fputs(text, stdout);
+    else {
+      FILE* f = std::fopen(saveMachine.c_str(), "w");
+      if (!f) die("cannot write " + saveMachine);
+      std::fputs(text, f);
+      std::fclose(f);
+    }
+    dnab_free(text);
+  }
+
+  if (!viterbiFile.empty()) {
+    dnab_compiled* compiled = errorFile.empty() ? dnab_compile(machine, &ef)
+                                                : dnab_compile_with_error_file(machine, errorFile.c_str());
+    if (!compiled) {
+      // a null cycle is reported and the reference still exits 0 (t/dnastore.cpp:245-250)
+      const std::string msg = dnab_last_error();
+      std::cerr << msg << std::endl;
+      return msg.find("cyclic") != std::string::npos ? 0 : 1;
+    }
+    dnab_decoder* dec = dnab_decoder_create(dnab_compiled_tables(compiled), device);
+    if (!dec) die(dnab_last_error(), 3);
+    if (verbose >= 3) {
+      dnab_decoder_info info;
+      if (dnab_decoder_get_info(dec, &info) == DNAB_OK)
+        std::cerr << "decoder: " << info.n_states << " states, k=" << info.k << ", cluster of " << info.cluster_size
+                  << " CTAs x " << info.threads_per_cta << " threads, " << info.states_per_cta << " states/CTA, "
+                  << info.smem_bytes_per_cta << " B smem, " << info.n_clusters << " reads in flight" << std::endl;
+    }
+    dnab_decoded_set* out = dnab_decode_fasta(dec, viterbiFile.c_str());
+    if (!out) die(dnab_last_error(), 3);
+    const int64_t n = dnab_decoded_count(out);
+    for (int64_t i = 0; i < n; ++i) {
+      if (dnab_decoded_status(out, i) == DNAB_READ_NO_DECODING) std::cerr << "No valid Viterbi decoding found" << std::endl;
+      const std::string seq = dnab_decoded_seq(out, i);
+      if (raw)
+        std::cout << seq << "\n";
+      else {
+        std::cout << '>' << dnab_decoded_name(out, i) << "\n";
+        for (size_t p = 0; p < seq.size(); p += 50) std::cout << seq.substr(p, 50) << "\n";
+      }
+    }
+    dnab_decoded_free(out);
+    dnab_decoder_destroy(dec);
+    dnab_compiled_free(compiled);
+  }
+  dnab_machine_free(machine);
+  return 0;
+}

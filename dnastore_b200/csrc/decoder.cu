@@ -1,0 +1,512 @@
+// Decoder handle: the flat tables resident on one B200 plus the launch logic.
+// Implements the decoder half of include/dnastore_b200.h.  There is no CPU
+// fallback anywhere in this file: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dnastore_b200.h"
+#include "capi_error.h"
+#include "viterbi_kernels.h"
+
+namespace dnab {
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t err__ = (expr);                                                               \
+    if (err__ != cudaSuccess) {                                                               \
+      setLastError(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " #expr);   \
+      return DNAB_ECUDA;                                                                      \
+    }                                                                                         \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t ensure(size_t count) {
+    if (count <= n) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& v) {
+    cudaError_t e = ensure(std::max<size_t>(v.size(), 1));
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+};
+
+struct LaunchPlan {
+  uint32_t C = 0, M = 0, threads = 0, tInSmem = 0, smemBytes = 0, nClusters = 0;
+  int32_t maxLen = -1;
+};
+
+}  // namespace dnab
+
+using namespace dnab;
+
+struct dnab_decoder {
+  int device = 0;
+  int smCount = 0;
+  size_t smemOptin = 0;
+  // host copy of the tables (owned)
+  uint32_t nStates = 0, k = 0, local = 0;
+  std::vector<uint32_t> emitOff, emitSrc, nullOff, nullSrc;
+  std::vector<uint8_t> emitSym, emitBase, nullSym, ctx, mdl;
+  std::vector<uint8_t> symChar;
+  std::vector<double> symScore;
+  double sub[16], len[kMaxK], noGap, delOpen, delExtend, delEnd, tanDup;
+  // user overrides
+  uint32_t wantC = 0, wantThreads = 0, wantTMode = 0;  // tMode: 0 auto, 1 smem, 2 global
+  // device-resident structures for the current plan
+  LaunchPlan plan;
+  DevTables dev{};
+  DevBuf<uint2> dStateRec;
+  DevBuf<uint32_t> dInEdges, dOutOff, dOutEdges, dOrigId;
+  DevBuf<uint8_t> dSymChar;
+  // scratch
+  DevBuf<uint8_t> dPred;
+  DevBuf<double> dTScratch, dPartVal, dCells;
+  DevBuf<uint32_t> dStart, dPartOrig, dPartG;
+  // staging for the host-buffer path
+  DevBuf<uint8_t> dPacked;
+  DevBuf<int64_t> dByteOff;
+  DevBuf<int32_t> dReadLen, dDecodedLen, dStatus, dPath, dPathLen;
+  DevBuf<double> dLoglike;
+  DevBuf<char> dDecoded;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  dnab_decoder_stats stats{};
+  size_t predBudgetBytes = 0;
+};
+
+namespace dnab {
+
+static int buildPlan(dnab_decoder* d, int32_t maxLen) {
+  if (d->plan.maxLen >= maxLen && d->plan.C) return DNAB_OK;
+  const uint32_t N = d->nStates, k = d->k;
+  const int32_t planLen = std::max(maxLen, 1024);
+  LaunchPlan best;
+  const uint32_t cands[] = {1, 2, 4, 8, 16};
+  for (uint32_t C : cands) {
+    if (d->wantC && C != d->wantC) continue;
+    const uint32_t M = (N + C - 1) / C;
+    if (M >= (1u << 20)) continue;
+    for (uint32_t tIn = 1; tIn + 1 > 0; --tIn) {  // 1 then 0
+      if (d->wantTMode == 1 && !tIn) break;
+      if (d->wantTMode == 2 && tIn) continue;
+      if (k == 0 && !tIn) break;
+      const uint32_t smem = fillSmemBytes(M, k, tIn, (uint32_t)planLen);
+      if (smem <= d->smemOptin) {
+        best.C = C;
+        best.M = M;
+        best.tInSmem = tIn;
+        best.smemBytes = smem;
+        break;
+      }
+      if (!tIn) break;
+    }
+    if (best.C) break;
+  }
+  if (!best.C) {
+    setLastError("machine does not fit: " + std::to_string(N) + " states need more shared memory than a 16-CTA cluster has");
+    return DNAB_EINVAL;
+  }
+  uint32_t threads = d->wantThreads ? d->wantThreads : std::min<uint32_t>(1024, std::max<uint32_t>(128, (best.M + 31) / 32 * 32));
+  threads = std::min<uint32_t>(1024, (threads + 31) / 32 * 32);
+  best.threads = threads;
+  best.maxLen = planLen;
+
+  // ---- device tables for this partition -------------------------------------------------
+  const uint32_t C = best.C, M = best.M, Np = C * M;
+  auto rankOf = [M](uint32_t g) { return g / M; };
+  auto localOf = [M](uint32_t g) { return g % M; };
+  std::vector<uint2> stateRec(Np);
+  std::vector<uint32_t> inEdges, origId(Np, 0xFFFFFFFFu);
+  std::vector<std::vector<uint32_t>> outs(Np);
+  inEdges.reserve(d->emitSrc.size() + d->nullSrc.size());
+  for (uint32_t g = 0; g < Np; ++g) {
+    uint2 rec{(uint32_t)inEdges.size(), 0};
+    if (g < N) {
+      origId[g] = g;  // identity permutation
+      const uint32_t nE = d->emitOff[g + 1] - d->emitOff[g], nN = d->nullOff[g + 1] - d->nullOff[g];
+      if (nE > 126 || 2 * nE + nN > 254 || nE + nN + 2 > 254) {
+        setLastError("state " + std::to_string(g) + " has too many incoming transitions for 1-byte predecessor records");
+        return DNAB_EINVAL;
+      }
+      for (uint32_t e = d->emitOff[g]; e < d->emitOff[g + 1]; ++e) {
+        const uint32_t s = d->emitSrc[e];
+        inEdges.push_back(packEdge(localOf(s), rankOf(s), d->emitSym[e], d->emitBase[e]));
+        outs[s].push_back(g);
+      }
+      for (uint32_t e = d->nullOff[g]; e < d->nullOff[g + 1]; ++e) {
+        const uint32_t s = d->nullSrc[e];
+        inEdges.push_back(packEdge(localOf(s), rankOf(s), d->nullSym[e], 0));
+        outs[s].push_back(g);
+      }
+      uint32_t y = nE | (nN << 8) | ((uint32_t)d->mdl[g] << 16);
+      for (uint32_t i = 0; i < d->mdl[g]; ++i) y |= (uint32_t)(d->ctx[(size_t)g * k + i] & 3u) << (20 + 2 * i);
+      rec.y = y;
+    }
+    stateRec[g] = rec;
+  }
+  std::vector<uint32_t> outOff(Np + 1, 0), outEdges;
+  for (uint32_t g = 0; g < Np; ++g) {
+    auto& o = outs[g];
+    std::sort(o.begin(), o.end());
+    o.erase(std::unique(o.begin(), o.end()), o.end());
+    for (uint32_t dest : o) outEdges.push_back(localOf(dest) | (rankOf(dest) << 20));
+    outOff[g + 1] = (uint32_t)outEdges.size();
+  }
+  CUDA_TRY(d->dStateRec.upload(stateRec));
+  CUDA_TRY(d->dInEdges.upload(inEdges));
+  CUDA_TRY(d->dOutOff.upload(outOff));
+  CUDA_TRY(d->dOutEdges.upload(outEdges));
+  CUDA_TRY(d->dOrigId.upload(origId));
+  CUDA_TRY(d->dSymChar.upload(d->symChar));
+
+  DevTables& t = d->dev;
+  t.nStates = N;
+  t.M = M;
+  t.C = C;
+  t.k = k;
+  t.local = d->local;
+  t.nSyms = (uint32_t)d->symChar.size();
+  t.startG = 0;
+  t.endG = N - 1;
+  t.tInSmem = best.tInSmem;
+  t.stateRec = d->dStateRec.p;
+  t.inEdges = d->dInEdges.p;
+  t.outOff = d->dOutOff.p;
+  t.outEdges = d->dOutEdges.p;
+  t.origId = d->dOrigId.p;
+  t.symChar = d->dSymChar.p;
+  for (int i = 0; i < kMaxSyms; ++i) t.symScore[i] = i < (int)d->symScore.size() ? d->symScore[i] : 0.;
+  std::memcpy(t.sub, d->sub, sizeof t.sub);
+  std::memcpy(t.len, d->len, sizeof t.len);
+  t.noGap = d->noGap;
+  t.delOpen = d->delOpen;
+  t.delExtend = d->delExtend;
+  t.delEnd = d->delEnd;
+  t.tanDup = d->tanDup;
+
+  int nClusters = 0;
+  CUDA_TRY(queryMaxClusters(t, best.threads, best.smemBytes, &nClusters));
+  if (nClusters < 1) {
+    setLastError("no cluster of size " + std::to_string(C) + " can be resident on this device");
+    return DNAB_ECUDA;
+  }
+  best.nClusters = (uint32_t)nClusters;
+  if (!best.tInSmem) CUDA_TRY(d->dTScratch.ensure((size_t)nClusters * C * k * M));
+  d->plan = best;
+  return DNAB_OK;
+}
+
+static size_t predBytesPerRead(const dnab_decoder* d, int32_t maxLen) {
+  return (size_t)(maxLen + 1) * (d->k + 2) * (size_t)d->plan.C * d->plan.M;
+}
+
+// fill + traceback over device-resident inputs/outputs, chunked so that the
+// predecessor records of one chunk fit the scratch budget
+static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint8_t* dPacked, const int64_t* dByteOff,
+                     const int32_t* dReadLen, double* dLoglike, char* dDecoded, int32_t decodedStride,
+                     int32_t* dDecodedLen, int32_t* dStatus, int32_t* dPath, int32_t pathStride, int32_t* dPathLen,
+                     double* dCells, cudaStream_t stream, bool timeIt) {
+  if (nReads <= 0) return DNAB_OK;
+  CUDA_TRY(cudaSetDevice(d->device));
+  int rc = buildPlan(d, maxLen);
+  if (rc != DNAB_OK) return rc;
+  const size_t perRead = predBytesPerRead(d, maxLen);
+  int64_t chunk = (int64_t)std::max<size_t>(1, d->predBudgetBytes / perRead);
+  chunk = std::min<int64_t>(chunk, nReads);
+  CUDA_TRY(d->dPred.ensure((size_t)chunk * perRead));
+  CUDA_TRY(d->dStart.ensure((size_t)chunk));
+  if (d->local) {
+    CUDA_TRY(d->dPartVal.ensure((size_t)chunk * d->plan.C));
+    CUDA_TRY(d->dPartOrig.ensure((size_t)chunk * d->plan.C));
+    CUDA_TRY(d->dPartG.ensure((size_t)chunk * d->plan.C));
+  }
+  for (int64_t at = 0; at < nReads; at += chunk) {
+    const int64_t n = std::min(chunk, nReads - at);
+    FillArgs fa{};
+    fa.nReads = n;
+    fa.maxLen = maxLen;
+    fa.packed = dPacked;
+    fa.byteOff = dByteOff + at;
+    fa.readLen = dReadLen + at;
+    fa.pred = d->dPred.p;
+    fa.tScratch = d->dTScratch.p;
+    fa.loglike = dLoglike + at;
+    fa.startState = d->dStart.p;
+    fa.partVal = d->dPartVal.p;
+    fa.partOrig = d->dPartOrig.p;
+    fa.partG = d->dPartG.p;
+    fa.cells = at == 0 ? dCells : nullptr;
+    const uint32_t nClusters = (uint32_t)std::min<int64_t>(d->plan.nClusters, n);
+    if (timeIt) CUDA_TRY(cudaEventRecord(d->ev0, stream));
+    CUDA_TRY(launchFill(d->dev, fa, nClusters, d->plan.threads, d->plan.smemBytes, stream));
+    if (timeIt) CUDA_TRY(cudaEventRecord(d->ev1, stream));
+    TracebackArgs ta{};
+    ta.nReads = n;
+    ta.maxLen = maxLen;
+    ta.readLen = dReadLen + at;
+    ta.pred = d->dPred.p;
+    ta.loglike = dLoglike + at;
+    ta.startState = d->dStart.p;
+    ta.partVal = d->dPartVal.p;
+    ta.partOrig = d->dPartOrig.p;
+    ta.partG = d->dPartG.p;
+    ta.decoded = dDecoded + (size_t)at * decodedStride;
+    ta.decodedStride = decodedStride;
+    ta.decodedLen = dDecodedLen + at;
+    ta.status = dStatus + at;
+    ta.path = dPath ? dPath + (size_t)at * 3 * pathStride : nullptr;
+    ta.pathStride = pathStride;
+    ta.pathLen = dPathLen ? dPathLen + at : nullptr;
+    CUDA_TRY(launchTraceback(d->dev, ta, stream));
+    if (timeIt) CUDA_TRY(cudaEventRecord(d->ev2, stream));
+    d->stats.kernel_launches += 2;
+    d->stats.fill_launches += 1;
+    d->stats.traceback_launches += 1;
+  }
+  d->stats.reads += (uint64_t)nReads;
+  return DNAB_OK;
+}
+
+}  // namespace dnab
+
+extern "C" {
+
+dnab_decoder* dnab_decoder_create(const dnab_tables* t, int device) {
+  if (!t || !t->n_states) {
+    setLastError("dnab_decoder_create: empty tables");
+    return nullptr;
+  }
+  int nDev = 0;
+  cudaError_t err = cudaGetDeviceCount(&nDev);
+  if (err != cudaSuccess || nDev == 0 || device < 0 || device >= nDev) {
+    setLastError(std::string("dnab_decoder_create: no usable CUDA device (") +
+                 (err != cudaSuccess ? cudaGetErrorString(err) : "device ordinal out of range") +
+                 "); this library has no CPU fallback");
+    return nullptr;
+  }
+  if (t->k > (uint32_t)kMaxK) {
+    setLastError("duplication depth k=" + std::to_string(t->k) + " exceeds the supported maximum " + std::to_string(kMaxK));
+    return nullptr;
+  }
+  auto* d = new dnab_decoder();
+  d->device = device;
+  cudaSetDevice(device);
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major < 10) {
+    setLastError(std::string("device ") + prop.name + " is not a Blackwell (sm_100a) GPU");
+    delete d;
+    return nullptr;
+  }
+  d->smCount = prop.multiProcessorCount;
+  d->smemOptin = prop.sharedMemPerBlockOptin;
+  size_t freeB = 0, totalB = 0;
+  cudaMemGetInfo(&freeB, &totalB);
+  d->predBudgetBytes = std::min<size_t>(freeB / 2, (size_t)48 << 30);
+  cudaEventCreate(&d->ev0);
+  cudaEventCreate(&d->ev1);
+  cudaEventCreate(&d->ev2);
+
+  const uint32_t N = t->n_states, k = t->k;
+  d->nStates = N;
+  d->k = k;
+  d->local = t->local;
+  d->emitOff.assign(t->emit_off, t->emit_off + N + 1);
+  d->nullOff.assign(t->null_off, t->null_off + N + 1);
+  d->emitSrc.assign(t->emit_src, t->emit_src + t->n_emit);
+  d->nullSrc.assign(t->null_src, t->null_src + t->n_null);
+  d->emitBase.assign(t->emit_base, t->emit_base + t->n_emit);
+  d->mdl.assign(t->mdl, t->mdl + N);
+  d->ctx.assign(t->ctx, t->ctx + (size_t)N * k);
+  // input symbols -> small ids; every transition carrying the same symbol has the same score
+  std::map<uint8_t, uint32_t> symId;
+  d->symChar.push_back(0);
+  d->symScore.push_back(0.);
+  symId[0] = 0;
+  auto idOf = [&](uint8_t ch, double score, bool& ok) -> uint8_t {
+    auto it = symId.find(ch);
+    if (it == symId.end()) {
+      if (d->symChar.size() >= (size_t)kMaxSyms) {
+        ok = false;
+        return 0;
+      }
+      it = symId.emplace(ch, (uint32_t)d->symChar.size()).first;
+      d->symChar.push_back(ch);
+      d->symScore.push_back(score);
+    }
+    if (std::memcmp(&d->symScore[it->second], &score, sizeof(double)) != 0) ok = false;
+    return (uint8_t)it->second;
+  };
+  bool ok = true;
+  d->emitSym.resize(t->n_emit);
+  d->nullSym.resize(t->n_null);
+  for (uint32_t e = 0; e < t->n_emit && ok; ++e) d->emitSym[e] = idOf(t->emit_in[e], t->emit_score[e], ok);
+  for (uint32_t e = 0; e < t->n_null && ok; ++e) d->nullSym[e] = idOf(t->null_in[e], t->null_score[e], ok);
+  if (!ok) {
+    setLastError("transition scores are not a function of the input symbol (or more than 31 symbols)");
+    dnab_decoder_destroy(d);
+    return nullptr;
+  }
+  std::memcpy(d->sub, t->sub, sizeof d->sub);
+  for (int i = 0; i < kMaxK; ++i) d->len[i] = (uint32_t)i < k ? t->len[i] : 0.;
+  d->noGap = t->noGap;
+  d->delOpen = t->delOpen;
+  d->delExtend = t->delExtend;
+  d->delEnd = t->delEnd;
+  d->tanDup = t->tanDup;
+  return d;
+}
+
+void dnab_decoder_destroy(dnab_decoder* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  if (d->ev0) cudaEventDestroy(d->ev0);
+  if (d->ev1) cudaEventDestroy(d->ev1);
+  if (d->ev2) cudaEventDestroy(d->ev2);
+  delete d;
+}
+
+int dnab_decoder_configure(dnab_decoder* d, uint32_t cluster_size, uint32_t threads_per_cta, uint32_t t_in_smem_mode) {
+  if (!d) return DNAB_EINVAL;
+  d->wantC = cluster_size;
+  d->wantThreads = threads_per_cta;
+  d->wantTMode = t_in_smem_mode;
+  d->plan = LaunchPlan();
+  return DNAB_OK;
+}
+
+int dnab_decoder_get_info(const dnab_decoder* dc, dnab_decoder_info* info) {
+  if (!dc || !info) return DNAB_EINVAL;
+  auto* d = const_cast<dnab_decoder*>(dc);
+  cudaSetDevice(d->device);
+  int rc = buildPlan(d, 1);
+  if (rc != DNAB_OK) return rc;
+  info->n_states = d->nStates;
+  info->k = d->k;
+  info->local = d->local;
+  info->cluster_size = d->plan.C;
+  info->states_per_cta = d->plan.M;
+  info->threads_per_cta = d->plan.threads;
+  info->smem_bytes_per_cta = d->plan.smemBytes;
+  info->t_in_smem = d->plan.tInSmem;
+  info->n_clusters = d->plan.nClusters;
+  info->sm_count = (uint32_t)d->smCount;
+  return DNAB_OK;
+}
+
+int dnab_decoder_get_stats(const dnab_decoder* d, dnab_decoder_stats* s) {
+  if (!d || !s) return DNAB_EINVAL;
+  *s = d->stats;
+  return DNAB_OK;
+}
+
+int dnab_viterbi_batch_device(dnab_decoder* d, int64_t n_reads, int32_t max_read_len, const uint8_t* d_packed,
+                              const int64_t* d_read_byte_off, const int32_t* d_read_len, double* d_loglike,
+                              char* d_decoded, int32_t decoded_stride, int32_t* d_decoded_len, int32_t* d_status,
+                              void* cuda_stream) {
+  if (!d || n_reads < 0 || max_read_len < 0 || decoded_stride <= 0) {
+    setLastError("dnab_viterbi_batch_device: bad argument");
+    return DNAB_EINVAL;
+  }
+  return runDevice(d, n_reads, max_read_len, d_packed, d_read_byte_off, d_read_len, d_loglike, d_decoded, decoded_stride,
+                   d_decoded_len, d_status, nullptr, 0, nullptr, nullptr, (cudaStream_t)cuda_stream, false);
+}
+
+static int viterbiHost(dnab_decoder* d, int64_t n, const uint8_t* packed, const int64_t* byteOff, const int32_t* readLen,
+                       double* loglike, char* decoded, int32_t decodedStride, int32_t* decodedLen, int32_t* status,
+                       int32_t* path, int32_t pathStride, int32_t* pathLen, double* cells) {
+  if (!d || n < 0 || decodedStride <= 0) {
+    setLastError("dnab_viterbi_batch: bad argument");
+    return DNAB_EINVAL;
+  }
+  if (n == 0) return DNAB_OK;
+  CUDA_TRY(cudaSetDevice(d->device));
+  int32_t maxLen = 0;
+  size_t packedBytes = 0;
+  uint64_t cellsTotal = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    maxLen = std::max(maxLen, readLen[r]);
+    packedBytes = std::max<size_t>(packedBytes, (size_t)byteOff[r] + ((((size_t)readLen[r] + 3) / 4 + 15) & ~(size_t)15));
+    cellsTotal += (uint64_t)d->nStates * (uint64_t)(readLen[r] + 1) * (d->k + 2);
+  }
+  packedBytes = std::max<size_t>(packedBytes, 16);
+  CUDA_TRY(d->dPacked.ensure(packedBytes));
+  CUDA_TRY(d->dByteOff.ensure((size_t)n));
+  CUDA_TRY(d->dReadLen.ensure((size_t)n));
+  CUDA_TRY(d->dLoglike.ensure((size_t)n));
+  CUDA_TRY(d->dDecoded.ensure((size_t)n * decodedStride));
+  CUDA_TRY(d->dDecodedLen.ensure((size_t)n));
+  CUDA_TRY(d->dStatus.ensure((size_t)n));
+  if (path) {
+    CUDA_TRY(d->dPath.ensure((size_t)n * 3 * pathStride));
+    CUDA_TRY(d->dPathLen.ensure((size_t)n));
+  }
+  size_t cellCount = 0;
+  if (cells) {
+    cellCount = (size_t)(readLen[0] + 1) * d->nStates * (d->k + 2);
+    CUDA_TRY(d->dCells.ensure(cellCount));
+  }
+  cudaStream_t stream = nullptr;
+  CUDA_TRY(cudaMemcpyAsync(d->dPacked.p, packed, packedBytes, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(d->dByteOff.p, byteOff, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(d->dReadLen.p, readLen, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  int rc = runDevice(d, n, maxLen, d->dPacked.p, d->dByteOff.p, d->dReadLen.p, d->dLoglike.p, d->dDecoded.p, decodedStride,
+                     d->dDecodedLen.p, d->dStatus.p, path ? d->dPath.p : nullptr, pathStride,
+                     path ? d->dPathLen.p : nullptr, cells ? d->dCells.p : nullptr, stream, true);
+  if (rc != DNAB_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(loglike, d->dLoglike.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaMemcpyAsync(decoded, d->dDecoded.p, (size_t)n * decodedStride, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaMemcpyAsync(decodedLen, d->dDecodedLen.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaMemcpyAsync(status, d->dStatus.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  if (path) {
+    CUDA_TRY(cudaMemcpyAsync(path, d->dPath.p, (size_t)n * 3 * pathStride * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(pathLen, d->dPathLen.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  }
+  if (cells) CUDA_TRY(cudaMemcpyAsync(cells, d->dCells.p, cellCount * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, d->ev0, d->ev1) == cudaSuccess) d->stats.last_fill_ms = ms;
+  if (cudaEventElapsedTime(&ms, d->ev1, d->ev2) == cudaSuccess) d->stats.last_traceback_ms = ms;
+  d->stats.cells += cellsTotal;
+  if (cells && d->local) {
+    // the reference overwrites S(end,L) with the column maximum in local mode (src/viterbi.cpp:171-173)
+    const size_t endCell = ((size_t)readLen[0] * d->nStates + (d->nStates - 1)) * (d->k + 2);
+    cells[endCell] = loglike[0];
+  }
+  return DNAB_OK;
+}
+
+int dnab_viterbi_batch(dnab_decoder* d, int64_t n_reads, const uint8_t* packed, const int64_t* read_byte_off,
+                       const int32_t* read_len, double* loglike, char* decoded, int32_t decoded_stride,
+                       int32_t* decoded_len, int32_t* status, int32_t* path, int32_t path_stride, int32_t* path_len) {
+  return viterbiHost(d, n_reads, packed, read_byte_off, read_len, loglike, decoded, decoded_stride, decoded_len, status,
+                     path, path_stride, path_len, nullptr);
+}
+
+int dnab_viterbi_cells(dnab_decoder* d, const uint8_t* packed, int32_t read_len, double* loglike, double* cells) {
+  const int64_t off = 0;
+  std::vector<char> dec(8 * (size_t)read_len + 1024);
+  int32_t decLen = 0, status = 0;
+  return viterbiHost(d, 1, packed, &off, &read_len, loglike, dec.data(), (int32_t)dec.size(), &decLen, &status, nullptr,
+                     0, nullptr, cells);
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+/* dnastore_b200.h -- C ABI of the B200-native batched Viterbi decoder for dnastore's
+ * hot path.  extern "C", plain pointers and sizes, integer return codes, no
+ * exceptions across the boundary, no torch types.  One decoder handle per device;
+ * a handle may be used from one host thread at a time.
+ *
+ * The reference (ihh/dnastore) has no plugin/FFI interface; the seam this library
+ * replaces is (all paths relative to the reference tree):
+ *   src/viterbi.h:108       decodeFastSeqs(filename, machine, mutatorParams)
+ *   src/viterbi.h:94-102    ViterbiMatrix(machine, inputModel, params, fastSeq),
+ *                           traceback(), loglike(), sCell/dCell/tCell
+ *   src/viterbi.h:18-40     MachineScores  (flattened into dnab_tables)
+ *   src/mutator.h:9-41      MutatorParams / MutatorScores
+ *   src/trans.h:83-126      Machine: fromFile, compose, writeJSON, inputAlphabet
+ *   t/dnastore.cpp:41-82    the CLI flags that feed them
+ * INTEGRATION.md shows the few lines a maintainer would add to the reference to
+ * call these entry points instead of its per-read CPU loop.
+ *
+ * Error convention: functions returning a pointer return NULL on failure, functions
+ * returning int return 0 on success and a negative DNAB_E* code on failure; in both
+ * cases dnab_last_error() (thread-local) describes what went wrong.
+ */
+#ifndef DNASTORE_B200_H
+#define DNASTORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "dnab_tables.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DNAB_OK 0
+#define DNAB_EINVAL (-1)      /* bad argument / unsupported machine */
+#define DNAB_ECUDA (-2)       /* CUDA runtime error, or no usable device */
+#define DNAB_EIO (-3)         /* file not found / unreadable */
+#define DNAB_ECYCLIC (-4)     /* null-transition cycle: reference throws std::domain_error (src/trans.cpp:631-632) */
+#define DNAB_EFORMAT (-5)     /* malformed machine / error-model JSON, non-ACGT read */
+
+/* per-read status written by dnab_viterbi_batch */
+#define DNAB_READ_OK 0
+#define DNAB_READ_NO_DECODING 1  /* loglike == -inf: reference warns "No valid Viterbi decoding found" and yields "" (src/viterbi.cpp:198-201) */
+#define DNAB_READ_OVERFLOW 2     /* decoded string or path did not fit the caller's buffer */
+#define DNAB_READ_TRACEBACK_FAILED 3 /* a predecessor record was missing (cannot happen for a finite loglike) */
+
+const char* dnab_last_error(void);
+const char* dnab_version(void);
+void dnab_free(void* p); /* frees strings/buffers this library returned */
+
+/* ------------------------------------------------------------------------
+ * Machine: dnastore's transducer and its JSON format (src/trans.h:83-126).
+ * ---------------------------------------------------------------------- */
+typedef struct dnab_machine dnab_machine;
+
+dnab_machine* dnab_machine_load(const char* json_path);             /* Machine::fromFile, src/trans.cpp:477-482 */
+dnab_machine* dnab_machine_from_json(const char* json_text);        /* Machine::fromJSON, src/trans.cpp:471-475 */
+/* Machine::compose(first, second), src/trans.cpp:505-602: first's output feeds second's input. */
+dnab_machine* dnab_machine_compose(const dnab_machine* first, const dnab_machine* second);
+char* dnab_machine_to_json(const dnab_machine* m);                  /* Machine::writeJSON, src/trans.cpp:402-429; dnab_free() it */
+uint32_t dnab_machine_n_states(const dnab_machine* m);
+uint32_t dnab_machine_max_left_context(const dnab_machine* m);      /* src/trans.cpp:252-257 */
+/* Machine::inputAlphabet(flags) (src/trans.cpp:280-292); flags as in src/trans.h:42-48. Writes a NUL-terminated string. */
+int dnab_machine_input_alphabet(const dnab_machine* m, int flags, char* out, size_t cap);
+void dnab_machine_free(dnab_machine* m);
+
+/* ------------------------------------------------------------------------
+ * Error model: the CLI's flags (t/dnastore.cpp:69-75,119-129).
+ * ---------------------------------------------------------------------- */
+typedef struct dnab_error_flags {
+  int32_t length;      /* -l/--length (default 12): maxDupLen = length/2 */
+  int32_t global;      /* --error-global: 1 = global alignment, 0 = local (CLI default) */
+  double sub_prob;     /* --error-sub-prob  (.01) */
+  double iv_ratio;     /* --error-iv-ratio  (10) */
+  double dup_prob;     /* --error-dup-prob  (.001) */
+  double del_open;     /* --error-del-open  (.001) */
+  double del_ext;      /* --error-del-ext   (.01) */
+} dnab_error_flags;
+
+void dnab_error_flags_default(dnab_error_flags* f);
+
+/* ------------------------------------------------------------------------
+ * Compile: Machine + error model -> flat tables (host memory).
+ * Replaces the per-read MachineScores/MutatorScores/InputModel construction
+ * (src/viterbi.cpp:6-14,23-60,309-310; src/mutator.cpp:56-75).
+ * ---------------------------------------------------------------------- */
+typedef struct dnab_compiled dnab_compiled;
+
+dnab_compiled* dnab_compile(const dnab_machine* m, const dnab_error_flags* flags);
+/* Same, with the error model read from an --error-file JSON (src/mutator.cpp:18-30). */
+dnab_compiled* dnab_compile_with_error_file(const dnab_machine* m, const char* error_json_path);
+const dnab_tables* dnab_compiled_tables(const dnab_compiled* c);
+void dnab_compiled_free(dnab_compiled* c);
+
+/* ------------------------------------------------------------------------
+ * Decoder: the tables resident on one GPU + the CUDA kernels.
+ * ---------------------------------------------------------------------- */
+typedef struct dnab_decoder dnab_decoder;
+
+/* Uploads the tables to `device` (CUDA ordinal) and derives the device-side
+ * structures (state partition over the thread-block cluster, packed edge words,
+ * outgoing lists).  Fails with DNAB_ECUDA when there is no CUDA device: there is
+ * NO CPU fallback. */
+dnab_decoder* dnab_decoder_create(const dnab_tables* t, int device);
+void dnab_decoder_destroy(dnab_decoder* d);
+
+typedef struct dnab_decoder_info {
+  uint32_t n_states, k, local;
+  uint32_t cluster_size;     /* CTAs cooperating on one read */
+  uint32_t states_per_cta;   /* slice of the state space owned by one CTA */
+  uint32_t threads_per_cta;
+  uint32_t smem_bytes_per_cta;
+  uint32_t t_in_smem;        /* 1: duplication (T) columns live in shared memory, 0: in global scratch */
+  uint32_t n_clusters;       /* clusters resident at once = reads in flight */
+  uint32_t sm_count;
+} dnab_decoder_info;
+int dnab_decoder_get_info(const dnab_decoder* d, dnab_decoder_info* info);
+
+/* Tuning overrides (0 = automatic); must be set before the first batch. */
+int dnab_decoder_configure(dnab_decoder* d, uint32_t cluster_size, uint32_t threads_per_cta, uint32_t t_in_smem_mode);
+
+/* Reads are packed 2 bits per base, A,C,G,T = 0..3 (src/kmer.h:11-13, src/fastseq.cpp:9-15),
+ * base i of a read in bits 2*(i%4).. of byte i/4; read r starts at byte
+ * read_byte_off[r] (a multiple of 16) and has read_len[r] bases. */
+size_t dnab_packed_size(const int32_t* read_len, int64_t n_reads);  /* bytes needed incl. 16-byte alignment */
+/* Packs ASCII reads (concatenated in `bases`, read r = bases[base_off[r] .. base_off[r+1])).
+ * Case-insensitive; a non-ACGT character is an error (DNAB_EFORMAT), as in the reference
+ * (src/fastseq.cpp:25-39, which terminates the process). */
+int dnab_pack_reads(const char* bases, const int64_t* base_off, int64_t n_reads, uint8_t* packed, int64_t* read_byte_off,
+                    int32_t* read_len);
+
+/* Batched Viterbi decode with HOST buffers: copies the packed reads to the device,
+ * runs fill + traceback there, copies results back (this is the `e2e` path).
+ *   loglike[n]          ViterbiMatrix::loglike() (src/viterbi.h:102), fp64, bit-exact
+ *   decoded             n * decoded_stride bytes; read r's input-symbol string
+ *                       (ViterbiMatrix::traceback(), src/viterbi.cpp:195-304) at
+ *                       decoded + r*decoded_stride, NOT NUL-terminated
+ *   decoded_len[n]      its length
+ *   status[n]           DNAB_READ_*
+ *   path / path_len     optional (NULL to skip): traceback cells as int32 triples
+ *                       (state, pos, mutState) with mutState 0=S,1=D,2+i=T(i+1)
+ *                       (src/viterbi.h:52-56), in traceback order starting at the
+ *                       first cell the reference's loop visits; path_stride triples per read
+ * Returns DNAB_OK or a negative code. */
+int dnab_viterbi_batch(dnab_decoder* d, int64_t n_reads, const uint8_t* packed, const int64_t* read_byte_off,
+                       const int32_t* read_len, double* loglike, char* decoded, int32_t decoded_stride,
+                       int32_t* decoded_len, int32_t* status, int32_t* path, int32_t path_stride, int32_t* path_len);
+
+/* Same computation with every buffer already RESIDENT IN DEVICE MEMORY of the
+ * decoder's device (pointers are device pointers; path output not available).
+ * Asynchronous on `cuda_stream` (a cudaStream_t passed as void*, NULL = default
+ * stream); the caller synchronises.  Scratch for the predecessor records is grown
+ * on demand and kept in the handle.  max_read_len >= every read_len[r]. */
+int dnab_viterbi_batch_device(dnab_decoder* d, int64_t n_reads, int32_t max_read_len, const uint8_t* d_packed,
+                              const int64_t* d_read_byte_off, const int32_t* d_read_len, double* d_loglike,
+                              char* d_decoded, int32_t decoded_stride, int32_t* d_decoded_len, int32_t* d_status,
+                              void* cuda_stream);
+
+/* Debug/parity aid: decode ONE read and also return every DP cell in the reference's
+ * layout cell[(k+2)*(pos*n_states+state)+mut] (src/viterbi.h:65-67); cells must hold
+ * (len+1)*n_states*(k+2) doubles (host memory). */
+int dnab_viterbi_cells(dnab_decoder* d, const uint8_t* packed, int32_t read_len, double* loglike, double* cells);
+
+/* Counters since creation: kernels launched by this library and DP cells filled. */
+typedef struct dnab_decoder_stats {
+  uint64_t kernel_launches;
+  uint64_t fill_launches;
+  uint64_t traceback_launches;
+  uint64_t reads;
+  uint64_t cells;           /* sum over reads of n_states*(len+1)*(k+2) */
+  double last_fill_ms;      /* CUDA-event time of the most recent fill kernel (sync path only) */
+  double last_traceback_ms;
+} dnab_decoder_stats;
+int dnab_decoder_get_stats(const dnab_decoder* d, dnab_decoder_stats* s);
+
+/* ------------------------------------------------------------------------
+ * File-level driver: the drop-in for decodeFastSeqs (src/viterbi.cpp:306-320).
+ * Reads a FASTA/FASTQ file (plain or gzip; multi-line records concatenated,
+ * src/fastseq.cpp:123-148), decodes every record on the decoder's device and
+ * returns the decoded strings in input order.
+ * ---------------------------------------------------------------------- */
+typedef struct dnab_decoded_set dnab_decoded_set;
+dnab_decoded_set* dnab_decode_fasta(dnab_decoder* d, const char* fasta_path);
+int64_t dnab_decoded_count(const dnab_decoded_set* s);
+const char* dnab_decoded_name(const dnab_decoded_set* s, int64_t i);
+const char* dnab_decoded_seq(const dnab_decoded_set* s, int64_t i);   /* NUL-terminated */
+double dnab_decoded_loglike(const dnab_decoded_set* s, int64_t i);
+int32_t dnab_decoded_status(const dnab_decoded_set* s, int64_t i);
+void dnab_decoded_free(dnab_decoded_set* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNASTORE_B200_H */

@@ -1,0 +1,115 @@
+"""Shared helpers for the tests: golden fixtures, machine recipes, the oracle binding.
+
+The ORACLE (oracle/viterbi_oracle.c) is loaded here and only here (plus
+__graft_entry__.smoke and bench.py's CPU baseline): it is the checker, never the
+product.
+"""
+import ctypes as C
+import functools
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+MACHINES = os.path.join(GOLDEN, "machines")
+
+
+def machine_path(name):
+    return os.path.join(MACHINES, name + ".json.gz")
+
+
+@functools.lru_cache(maxsize=None)
+def load_golden():
+    return json.load(open(os.path.join(GOLDEN, "viterbi_golden.json")))["cases"]
+
+
+def golden_case(name):
+    for c in load_golden():
+        if c["name"] == name:
+            return c
+    raise KeyError(name)
+
+
+@functools.lru_cache(maxsize=None)
+def machine_from_recipe(recipe):
+    """recipe = (base, compose1, compose2, ...) as on the dnastore command line."""
+    import dnastore_b200 as d
+    return d.Machine.load_composed(machine_path(recipe[0]), [machine_path(c) for c in recipe[1:]])
+
+
+def error_flags(flags, global_):
+    import dnastore_b200 as d
+    return d.ErrorFlags(length=flags["length"], global_=global_, sub_prob=flags["sub"], iv_ratio=flags["iv"],
+                        dup_prob=flags["dup"], del_open=flags["delopen"], del_ext=flags["delext"])
+
+
+@functools.lru_cache(maxsize=None)
+def _compiled_cached(recipe, flag_items, global_):
+    m = machine_from_recipe(recipe)
+    return m.compile(error_flags(dict(flag_items), global_))
+
+
+def compiled_for_case(case):
+    return _compiled_cached(tuple(case["recipe"]), tuple(sorted(case["flags"].items())), bool(case["global_"]))
+
+
+def compiled_for(recipe, flags=None, global_=True):
+    f = dict(length=12, sub=.01, iv=10., dup=.001, delopen=.001, delext=.01)
+    f.update(flags or {})
+    return _compiled_cached(tuple(recipe), tuple(sorted(f.items())), bool(global_))
+
+
+# ----------------------------------------------------------------------------- oracle
+@functools.lru_cache(maxsize=None)
+def oracle_lib():
+    path = os.path.join(ROOT, "oracle", "_build", "libviterbi_oracle.so")
+    lib = C.CDLL(path)
+    lib.dnab_oracle_viterbi.restype = C.c_int
+    lib.dnab_oracle_viterbi.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_char_p, C.c_int,
+                                        C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+    lib.dnab_oracle_viterbi_batch.restype = C.c_int
+    lib.dnab_oracle_viterbi_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                              C.c_void_p, C.c_void_p]
+    return lib
+
+
+_TOK = np.full(256, 255, dtype=np.uint8)
+for _i, _ch in enumerate("ACGT"):
+    _TOK[ord(_ch)] = _i
+    _TOK[ord(_ch.lower())] = _i
+
+
+def tokens(seq):
+    t = _TOK[np.frombuffer(seq.encode(), dtype=np.uint8)] if seq else np.zeros(0, dtype=np.uint8)
+    assert (t < 4).all()
+    return np.ascontiguousarray(t)
+
+
+def oracle_viterbi(compiled, seq, want_cells=False, want_path=True):
+    """Returns dict(rc, loglike, decoded, path[list of [state,pos,mut]], cells)."""
+    lib = oracle_lib()
+    t = compiled.t
+    tok = tokens(seq)
+    L = len(seq)
+    ll = C.c_double(0)
+    cap = 16 * L + 4096
+    dec = C.create_string_buffer(cap)
+    dec_len = C.c_int(0)
+    pcap = 32 * L + 8192
+    path = np.zeros((pcap, 3), dtype=np.int32)
+    plen = C.c_int(0)
+    cells = np.zeros((L + 1, t.n_states, t.k + 2), dtype=np.float64) if want_cells else None
+    rc = lib.dnab_oracle_viterbi(C.addressof(t), tok.ctypes.data, L, C.byref(ll), dec, cap, C.byref(dec_len),
+                                 path.ctypes.data if want_path else None, pcap, C.byref(plen),
+                                 cells.ctypes.data if want_cells else None)
+    return dict(rc=rc, loglike=ll.value, decoded=dec.raw[:dec_len.value].decode("latin1"),
+                path=path[:plen.value].tolist(), cells=cells)
+
+
+def hexf(x):
+    """Canonical hex-float string of an fp64 (bit-exact comparisons; accepts C's %a output too)."""
+    if isinstance(x, str):
+        x = float.fromhex(x) if "x" in x else float(x)
+    return float(x).hex()

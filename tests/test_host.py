@@ -1,0 +1,107 @@
+"""CPU: the host side above the C ABI -- machine JSON, compose, table compiler, FASTA, packing."""
+import ctypes as C
+import gzip
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dnastore_b200 as d
+import dnab_testutil as util
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(util.ROOT, "include", "dnastore_b200.h")).read()
+    names = set(re.findall(r"\b(dnab_[a-z_0-9]+)\s*\(", header))
+    assert len(names) >= 30
+    for n in sorted(names):
+        assert hasattr(d.lib, n), f"{n} declared in include/dnastore_b200.h but not exported"
+
+
+def test_machine_json_round_trip():
+    """reference Makefile:135: --load-machine X --save-machine - reproduces X."""
+    for name in ["l4c4", "mixradar6", "sync16", "flusher", "water64.1"]:
+        text = gzip.open(util.machine_path(name), "rt").read()
+        assert d.Machine.from_json(text).to_json() == text
+
+
+def test_lenient_json_accepts_missing_and_trailing_commas():
+    text = '{"state":[\n {"n":0,"id":"B","trans":[{"in":"^","out":"^","to":1}]}\n {"n":1,"id":"E","trans":[]},\n]}'
+    m = d.Machine.from_json(text)
+    assert m.n_states == 2
+    with pytest.raises(d.DnabError):
+        d.Machine.from_json('{"state":[{"n":1,"trans":[]}]}')  # n out of sequence
+
+
+def test_compose_matches_reference_sha256():
+    """reference Makefile:151,166,174,181 compose goldens + the BASELINE config 2/4 composites."""
+    want = json.load(open(os.path.join(util.GOLDEN, "composed_sha256.json")))
+    for name, w in want.items():
+        m = util.machine_from_recipe(tuple(w["recipe"]))
+        assert m.n_states == w["n_states"], name
+        assert hashlib.sha256(m.to_json().encode()).hexdigest() == w["sha256"], name
+
+
+def test_input_alphabet_and_context():
+    m = util.machine_from_recipe(("l4c4",))
+    assert m.n_states == 384 and m.max_left_context == 4
+    assert m.input_alphabet() == "$01AB^"
+    assert util.machine_from_recipe(("l4c4", "water64.1")).input_alphabet() == "$01^"
+
+
+def test_score_tables_anchor_values():
+    """SURVEY.md 9.2 anchors (computed by the reference with glibc log)."""
+    a = util.compiled_for(["l4c4"], dict(length=4), True).arrays()
+    assert a["k"] == 2 and len(a["emit_src"]) == 686 and len(a["null_src"]) == 27
+    assert a["noGap"] == -0.0020020026706730793
+    assert a["delOpen"] == a["tanDup"] == -6.9077552789821368
+    assert a["delExtend"] == -4.6051701859880909
+    assert a["delEnd"] == -0.010050335853501451
+    sub = a["sub"].reshape(4, 4)
+    assert sub[0, 0] == 1.3762440252663892 and sub[0, 2] == -3.3141860046725249 and sub[0, 1] == -6.3099182782265162
+    assert a["len"][0] == -0.69314718055994529
+    scores = {chr(c): s for c, s in zip(a["emit_in"], a["emit_score"])}
+    assert scores["0"] == scores["1"] == -1.3863019904853182
+    assert scores["A"] == -12.476656879444443
+    a8 = util.compiled_for(["l4c4"], {}, False).arrays()  # default -l 12: k = min(4, 6)
+    assert a8["k"] == 4 and a8["local"] == 1 and a8["len"][0] == -1.791759469228055
+    w = util.compiled_for(["l4c4", "water64.1"], dict(length=4), True).arrays()
+    assert set(np.unique(w["emit_score"])) <= {0.0, -1.3862943611198906}
+
+
+def test_tables_edge_order_is_reference_list_order():
+    """incoming lists are ordered by (source index, transition index) (src/viterbi.cpp:30-58)."""
+    a = util.compiled_for(["l4c4", "sync16", "flusher", "hamming74"], dict(length=4), True).arrays()
+    for off, src in ((a["emit_off"], a["emit_src"]), (a["null_off"], a["null_src"])):
+        for s in range(a["n_states"]):
+            seg = src[off[s]:off[s + 1]]
+            assert (np.diff(seg.astype(np.int64)) >= 0).all()
+    deg = np.diff(a["null_off"])
+    assert deg.max() == 98  # the hub states of s16h74l4c4 (SURVEY.md 7 hard part 5)
+
+
+def test_null_cycle_is_rejected():
+    text = ('{"state":[{"n":0,"trans":[{"to":1}]},{"n":1,"trans":[{"to":0},{"in":"$","out":"A","to":2}]},'
+            '{"n":2,"trans":[]}]}')
+    with pytest.raises(d.DnabError, match="cyclic"):
+        d.Machine.from_json(text).compile(d.ErrorFlags(length=4))
+
+
+def test_pack_reads_layout_and_errors():
+    packed, off, ln = d.pack_reads(["ACGT", "ttgca", ""])
+    assert ln.tolist() == [4, 5, 0] and off.tolist() == [0, 16, 32]
+    assert packed[0] == 0b11100100  # A=0 C=1 G=2 T=3, base i in bits 2*(i%4)
+    assert packed[16] == (3 | 3 << 2 | 2 << 4 | 1 << 6) and packed[17] == 0
+    with pytest.raises(d.DnabError, match="Unknown symbol N"):
+        d.pack_reads(["ACGN"])
+
+
+def test_decoder_needs_a_gpu_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(d.DnabError, match="no CPU fallback"):
+        d.Decoder(util.compiled_for(["l4c4"], dict(length=4), True))
