@@ -1,0 +1,137 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the golden vectors made by
+the unmodified reference and against the oracle on the same seeded inputs.
+
+Bar: bit-exact fp64 log-likelihoods, identical decoded strings, identical traceback
+paths, identical DP cells.
+"""
+import json
+
+import numpy as np
+import pytest
+
+import dnab_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+CASES = [c["name"] for c in util.load_golden()]
+
+
+@pytest.fixture(scope="module")
+def d():
+    import dnastore_b200
+    return dnastore_b200
+
+
+def _check_against_golden(d, case, configure=None):
+    compiled = util.compiled_for_case(case)
+    dec = d.Decoder(compiled, device=0)
+    if configure:
+        dec.configure(**configure)
+    reads = [r["seq"] for r in case["reads"]]
+    out = dec.viterbi(reads, want_path=True)
+    for i, r in enumerate(case["reads"]):
+        tag = (case["name"], r["name"], configure)
+        assert out["decoded"][i] == r["decoded"], tag
+        assert util.hexf(out["loglike"][i]) == util.hexf(r["loglike_hex"]), tag
+        assert out["path"][i].tolist() == r["path"], tag
+        want_status = d.READ_NO_DECODING if r["loglike"] == "-inf" else d.READ_OK
+        assert out["status"][i] == want_status, tag
+    return dec
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_matches_reference_golden(d, name):
+    dec = _check_against_golden(d, util.golden_case(name))
+    st = dec.stats()
+    assert st["fill_launches"] >= 1 and st["traceback_launches"] >= 1
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("name", ["l4c4_global_mixed", "l4c4_local_mixed", "mr2l4c4_local", "cfg3_global_indels"])
+def test_gpu_every_cluster_size(d, name, cluster):
+    """The state partition over the thread-block cluster must not change a single bit."""
+    case = util.golden_case(name)
+    n_states = util.compiled_for_case(case).t.n_states
+    if cluster == 1 and n_states > 4000:
+        pytest.skip("does not fit one CTA")
+    for tmode in (1, 2):  # duplication columns in shared memory / in global scratch
+        if tmode == 1 and cluster <= 2 and n_states > 4000:
+            continue
+        _check_against_golden(d, case, dict(cluster_size=cluster, t_in_smem_mode=tmode))
+
+
+@pytest.mark.parametrize("threads", [32, 96, 256, 1024])
+def test_gpu_every_block_size(d, threads):
+    _check_against_golden(d, util.golden_case("l4c4_global_mixed"), dict(threads_per_cta=threads))
+
+
+@pytest.mark.parametrize("tag", ["l4c4_global", "l4c4_local"])
+def test_gpu_cells_bit_exact(d, tag):
+    z = np.load(f"{util.GOLDEN}/cells_{tag}.npz")
+    flags = json.loads(str(z["flags"]))
+    compiled = util.compiled_for([str(x) for x in z["recipe"]], flags, bool(z["global_"]))
+    dec = d.Decoder(compiled, device=0)
+    ll, cells = dec.viterbi_cells(str(z["seq"]))
+    assert cells.tobytes() == z["cells"].reshape(cells.shape).tobytes()
+    assert util.hexf(ll) == util.hexf(str(z["loglike_hex"]))
+
+
+def test_gpu_vs_oracle_seeded_batch(d):
+    """A few hundred seeded mutated reads on l4c4 (global and local): GPU == oracle, bit for bit."""
+    from benchdata import synth
+    rng = np.random.default_rng(20261018)
+    pool = [r["seq"] for r in util.golden_case("l4c4_global_mixed")["reads"]]
+    reads = [synth.mutate(pool[i % len(pool)], rng, sub_rate=0.03, dup_rate=0.01, max_dup=2, del_rate=0.01, max_del=4)
+             for i in range(192)]
+    reads += ["", "A", "ACGT" * 3]  # empty and very short reads ride along in the same batch
+    for global_ in (True, False):
+        compiled = util.compiled_for(["l4c4"], dict(length=4), global_)
+        dec = d.Decoder(compiled, device=0)
+        out = dec.viterbi(reads, want_path=True)
+        for i, s in enumerate(reads):
+            o = util.oracle_viterbi(compiled, s)
+            assert out["decoded"][i] == o["decoded"], (global_, i)
+            assert util.hexf(out["loglike"][i]) == util.hexf(o["loglike"]), (global_, i)
+            assert out["path"][i].tolist() == o["path"], (global_, i)
+
+
+def test_gpu_ragged_batch_order_and_chunking(d):
+    """Results come back in input order whatever the batch composition; decoding a read alone or
+    inside a ragged batch gives the same bits."""
+    case = util.golden_case("l4c4_global_mixed")
+    compiled = util.compiled_for_case(case)
+    dec = d.Decoder(compiled, device=0)
+    reads = [r["seq"] for r in case["reads"]]
+    ragged = [reads[0][:5], reads[1], "", reads[2][:77], reads[3]] * 7
+    whole = dec.viterbi(ragged)
+    for i, s in enumerate(ragged):
+        one = dec.viterbi([s])
+        assert one["decoded"][0] == whole["decoded"][i]
+        assert util.hexf(one["loglike"][0]) == util.hexf(whole["loglike"][i])
+
+
+def test_gpu_decode_fasta_drop_in(d, tmp_path):
+    """decodeFastSeqs drop-in: multi-line records, lower case, names kept, input order."""
+    case = util.golden_case("kat186")  # the reference's 3-line record with a deleted base
+    seq = case["reads"][0]["seq"]
+    fa = tmp_path / "reads.fa"
+    fa.write_text(">first some comment\n" + seq[:30] + "\n" + seq[30:60].lower() + "\n" + seq[60:] + "\n>second\n" + seq + "\n")
+    dec = d.Decoder(util.compiled_for_case(case), device=0)
+    got = dec.decode_fasta(fa)
+    assert [g[0] for g in got] == ["first", "second"]
+    assert got[0][1] == got[1][1] == case["reads"][0]["decoded"]
+    assert util.hexf(got[0][2]) == util.hexf(case["reads"][0]["loglike_hex"])
+
+
+def test_gpu_cli_matches_reference_cli_output(d, tmp_path):
+    """bin/dnastore-b200 -V prints what the reference prints for its own known-answer test."""
+    import os
+    import subprocess
+    case = util.golden_case("kat147")
+    fa = tmp_path / "hello.fa"
+    fa.write_text(">hello\n" + case["reads"][0]["seq"] + "\n")
+    exe = os.path.join(util.ROOT, "bin", "dnastore-b200")
+    out = subprocess.run([exe, "-v0", "--load-machine", util.machine_path("l4c4"), "--decode-viterbi", str(fa),
+                          "--error-sub-prob", "0", "--error-dup-prob", "0", "--error-del-open", "0", "--error-global",
+                          "--raw"], capture_output=True, text=True, check=True).stdout
+    assert out == case["reads"][0]["decoded"] + "\n"
