@@ -60,7 +60,8 @@ class DecoderInfo(C.Structure):
 
 class DecoderStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("fill_launches", C.c_uint64), ("traceback_launches", C.c_uint64),
-                ("reads", C.c_uint64), ("cells", C.c_uint64), ("last_fill_ms", C.c_double), ("last_traceback_ms", C.c_double)]
+                ("reads", C.c_uint64), ("cells", C.c_uint64), ("last_fill_ms", C.c_double), ("last_traceback_ms", C.c_double),
+                ("timed_fill_ms", C.c_double), ("timed_traceback_ms", C.c_double), ("timed_fill_launches", C.c_uint64)]
 
 
 def _sig(name, restype, *argtypes):
@@ -92,6 +93,10 @@ _sig("dnab_decoder_destroy", None, _vp)
 _sig("dnab_decoder_get_info", C.c_int, _vp, C.POINTER(DecoderInfo))
 _sig("dnab_decoder_configure", C.c_int, _vp, C.c_uint32, C.c_uint32, C.c_uint32)
 _sig("dnab_decoder_get_stats", C.c_int, _vp, C.POINTER(DecoderStats))
+_sig("dnab_decoder_set_timing", C.c_int, _vp, C.c_int)
+_sig("dnab_decoder_reset_timing", C.c_int, _vp)
+_sig("dnab_decoder_set_debug", C.c_int, _vp, C.c_int)
+_sig("dnab_decoder_debug_counters", C.c_int, _vp, _vp)
 _sig("dnab_packed_size", C.c_size_t, _vp, C.c_int64)
 _sig("dnab_pack_reads", C.c_int, C.c_char_p, _vp, C.c_int64, _vp, _vp, _vp)
 _sig("dnab_viterbi_batch", C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp)
@@ -266,6 +271,21 @@ class Decoder:
         s = DecoderStats()
         lib.dnab_decoder_get_stats(self._h, C.byref(s))
         return {n: getattr(s, n) for n, _ in DecoderStats._fields_}
+
+    def set_timing(self, enabled=True):
+        lib.dnab_decoder_set_timing(self._h, int(enabled))
+
+    def set_debug(self, enabled=True):
+        lib.dnab_decoder_set_debug(self._h, int(enabled))
+
+    def debug_counters(self):
+        out = np.zeros(16, dtype=np.uint64)
+        lib.dnab_decoder_debug_counters(self._h, _ptr(out))
+        names = ["columns", "sweeps", "work_rank0", "cyc_emit", "cyc_closure", "cyc_pred", "rounds", "cyc_dense", "cyc_syncwait", "cyc_compact", "cyc_proc", "cyc_clusterwait"]
+        return {n: int(v) for n, v in zip(names, out)}
+
+    def reset_timing(self):
+        lib.dnab_decoder_reset_timing(self._h)
 
     def viterbi(self, reads, want_path=False, decoded_stride=None, path_stride=None):
         """Decode ASCII reads through host buffers. Returns dict(loglike, decoded, status[, path])."""

@@ -74,13 +74,14 @@ struct dnab_decoder {
   // device-resident structures for the current plan
   LaunchPlan plan;
   DevTables dev{};
-  DevBuf<uint2> dStateRec;
-  DevBuf<uint32_t> dInEdges, dOutOff, dOutEdges, dOrigId;
+  DevBuf<uint32_t> dBlocks, dBlockOff, dOrigId;
   DevBuf<uint8_t> dSymChar;
   // scratch
   DevBuf<uint8_t> dPred;
   DevBuf<double> dTScratch, dPartVal, dCells;
   DevBuf<uint32_t> dStart, dPartOrig, dPartG;
+  DevBuf<unsigned long long> dDbg;
+  bool debug = false;
   // staging for the host-buffer path
   DevBuf<uint8_t> dPacked;
   DevBuf<int64_t> dByteOff;
@@ -88,6 +89,10 @@ struct dnab_decoder {
   DevBuf<double> dLoglike;
   DevBuf<char> dDecoded;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  // device-path timing: (start, mid, end) event triples per chunk, resolved lazily in get_stats
+  bool timing = false;
+  std::vector<cudaEvent_t> evPool;
+  size_t evUsed = 0;
   dnab_decoder_stats stats{};
   size_t predBudgetBytes = 0;
 };
@@ -103,7 +108,7 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
   for (uint32_t C : cands) {
     if (d->wantC && C != d->wantC) continue;
     const uint32_t M = (N + C - 1) / C;
-    if (M >= (1u << 20)) continue;
+    if (M > 65535) continue;  // 16-bit worklist entries
     for (uint32_t tIn = 1; tIn + 1 > 0; --tIn) {  // 1 then 0
       if (d->wantTMode == 1 && !tIn) break;
       if (d->wantTMode == 2 && tIn) continue;
@@ -124,7 +129,7 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
     setLastError("machine does not fit: " + std::to_string(N) + " states need more shared memory than a 16-CTA cluster has");
     return DNAB_EINVAL;
   }
-  uint32_t threads = d->wantThreads ? d->wantThreads : std::min<uint32_t>(1024, std::max<uint32_t>(128, (best.M + 31) / 32 * 32));
+  uint32_t threads = d->wantThreads ? d->wantThreads : std::min<uint32_t>(512, std::max<uint32_t>(128, (best.M + 31) / 32 * 32));
   threads = std::min<uint32_t>(1024, (threads + 31) / 32 * 32);
   best.threads = threads;
   best.maxLen = planLen;
@@ -133,47 +138,48 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
   const uint32_t C = best.C, M = best.M, Np = C * M;
   auto rankOf = [M](uint32_t g) { return g / M; };
   auto localOf = [M](uint32_t g) { return g % M; };
-  std::vector<uint2> stateRec(Np);
-  std::vector<uint32_t> inEdges, origId(Np, 0xFFFFFFFFu);
-  std::vector<std::vector<uint32_t>> outs(Np);
-  inEdges.reserve(d->emitSrc.size() + d->nullSrc.size());
-  for (uint32_t g = 0; g < Np; ++g) {
-    uint2 rec{(uint32_t)inEdges.size(), 0};
-    if (g < N) {
-      origId[g] = g;  // identity permutation
-      const uint32_t nE = d->emitOff[g + 1] - d->emitOff[g], nN = d->nullOff[g + 1] - d->nullOff[g];
-      if (nE > 126 || 2 * nE + nN > 254 || nE + nN + 2 > 254) {
-        setLastError("state " + std::to_string(g) + " has too many incoming transitions for 1-byte predecessor records");
-        return DNAB_EINVAL;
-      }
-      for (uint32_t e = d->emitOff[g]; e < d->emitOff[g + 1]; ++e) {
-        const uint32_t s = d->emitSrc[e];
-        inEdges.push_back(packEdge(localOf(s), rankOf(s), d->emitSym[e], d->emitBase[e]));
-        outs[s].push_back(g);
-      }
-      for (uint32_t e = d->nullOff[g]; e < d->nullOff[g + 1]; ++e) {
-        const uint32_t s = d->nullSrc[e];
-        inEdges.push_back(packEdge(localOf(s), rankOf(s), d->nullSym[e], 0));
-        outs[s].push_back(g);
-      }
-      uint32_t y = nE | (nN << 8) | ((uint32_t)d->mdl[g] << 16);
-      for (uint32_t i = 0; i < d->mdl[g]; ++i) y |= (uint32_t)(d->ctx[(size_t)g * k + i] & 3u) << (20 + 2 * i);
-      rec.y = y;
+  std::vector<uint32_t> origId(Np, 0xFFFFFFFFu);
+  std::vector<std::vector<uint32_t>> ins(Np), outs(Np);
+  std::vector<uint32_t> hdr0(Np, 0), hdr1(Np, 0);
+  for (uint32_t g = 0; g < N; ++g) {
+    origId[g] = g;  // identity permutation
+    const uint32_t nE = d->emitOff[g + 1] - d->emitOff[g], nN = d->nullOff[g + 1] - d->nullOff[g];
+    if (nE > 126 || 2 * nE + nN > 254 || nE + nN + 2 > 254) {
+      setLastError("state " + std::to_string(g) + " has too many incoming transitions for 1-byte predecessor records");
+      return DNAB_EINVAL;
     }
-    stateRec[g] = rec;
+    for (uint32_t e = d->emitOff[g]; e < d->emitOff[g + 1]; ++e) {
+      const uint32_t s = d->emitSrc[e];
+      ins[g].push_back(packEdge(localOf(s), rankOf(s), d->emitSym[e], d->emitBase[e]));
+      outs[s].push_back(g);
+    }
+    for (uint32_t e = d->nullOff[g]; e < d->nullOff[g + 1]; ++e) {
+      const uint32_t s = d->nullSrc[e];
+      ins[g].push_back(packEdge(localOf(s), rankOf(s), d->nullSym[e], 0));
+      outs[s].push_back(g);
+    }
+    hdr0[g] = nE | (nN << 8) | ((uint32_t)d->mdl[g] << 24);
+    for (uint32_t i = 0; i < d->mdl[g]; ++i) hdr1[g] |= (uint32_t)(d->ctx[(size_t)g * k + i] & 3u) << (2 * i);
   }
-  std::vector<uint32_t> outOff(Np + 1, 0), outEdges;
+  std::vector<uint32_t> blocks, blockOff(Np, 0);
   for (uint32_t g = 0; g < Np; ++g) {
     auto& o = outs[g];
     std::sort(o.begin(), o.end());
     o.erase(std::unique(o.begin(), o.end()), o.end());
-    for (uint32_t dest : o) outEdges.push_back(localOf(dest) | (rankOf(dest) << 20));
-    outOff[g + 1] = (uint32_t)outEdges.size();
+    if (o.size() > 255) {
+      setLastError("state " + std::to_string(g) + " has more than 255 distinct successors");
+      return DNAB_EINVAL;
+    }
+    blockOff[g] = (uint32_t)blocks.size();
+    blocks.push_back(hdr0[g] | ((uint32_t)o.size() << 16));
+    blocks.push_back(hdr1[g]);
+    blocks.insert(blocks.end(), ins[g].begin(), ins[g].end());
+    for (uint32_t dest : o) blocks.push_back(packEdge(localOf(dest), rankOf(dest), 0, 0));
+    while (blocks.size() % kBlockWords) blocks.push_back(0);
   }
-  CUDA_TRY(d->dStateRec.upload(stateRec));
-  CUDA_TRY(d->dInEdges.upload(inEdges));
-  CUDA_TRY(d->dOutOff.upload(outOff));
-  CUDA_TRY(d->dOutEdges.upload(outEdges));
+  for (uint32_t j = 0; j < kBlockWords; ++j) blocks.push_back(0);  // the 32-byte prefetch never runs off the end
+  CUDA_TRY(d->dBlocks.upload(blocks));
+  CUDA_TRY(d->dBlockOff.upload(blockOff));
   CUDA_TRY(d->dOrigId.upload(origId));
   CUDA_TRY(d->dSymChar.upload(d->symChar));
 
@@ -187,10 +193,8 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
   t.startG = 0;
   t.endG = N - 1;
   t.tInSmem = best.tInSmem;
-  t.stateRec = d->dStateRec.p;
-  t.inEdges = d->dInEdges.p;
-  t.outOff = d->dOutOff.p;
-  t.outEdges = d->dOutEdges.p;
+  t.blocks = d->dBlocks.p;
+  t.blockOff = d->dBlockOff.p;
   t.origId = d->dOrigId.p;
   t.symChar = d->dSymChar.p;
   for (int i = 0; i < kMaxSyms; ++i) t.symScore[i] = i < (int)d->symScore.size() ? d->symScore[i] : 0.;
@@ -241,6 +245,7 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
   for (int64_t at = 0; at < nReads; at += chunk) {
     const int64_t n = std::min(chunk, nReads - at);
     FillArgs fa{};
+    fa.lay = makeLayout(d->plan.M, d->k, d->plan.tInSmem, (uint32_t)d->plan.maxLen);
     fa.nReads = n;
     fa.maxLen = maxLen;
     fa.packed = dPacked;
@@ -254,10 +259,25 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
     fa.partOrig = d->dPartOrig.p;
     fa.partG = d->dPartG.p;
     fa.cells = at == 0 ? dCells : nullptr;
+    fa.dbg = d->debug ? d->dDbg.p : nullptr;
     const uint32_t nClusters = (uint32_t)std::min<int64_t>(d->plan.nClusters, n);
-    if (timeIt) CUDA_TRY(cudaEventRecord(d->ev0, stream));
+    cudaEvent_t e0 = d->ev0, e1 = d->ev1, e2 = d->ev2;
+    const bool pooled = d->timing && !timeIt;
+    if (pooled) {
+      while (d->evPool.size() < d->evUsed + 3) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        d->evPool.push_back(e);
+      }
+      e0 = d->evPool[d->evUsed];
+      e1 = d->evPool[d->evUsed + 1];
+      e2 = d->evPool[d->evUsed + 2];
+      d->evUsed += 3;
+    }
+    const bool rec = timeIt || pooled;
+    if (rec) CUDA_TRY(cudaEventRecord(e0, stream));
     CUDA_TRY(launchFill(d->dev, fa, nClusters, d->plan.threads, d->plan.smemBytes, stream));
-    if (timeIt) CUDA_TRY(cudaEventRecord(d->ev1, stream));
+    if (rec) CUDA_TRY(cudaEventRecord(e1, stream));
     TracebackArgs ta{};
     ta.nReads = n;
     ta.maxLen = maxLen;
@@ -276,7 +296,7 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
     ta.pathStride = pathStride;
     ta.pathLen = dPathLen ? dPathLen + at : nullptr;
     CUDA_TRY(launchTraceback(d->dev, ta, stream));
-    if (timeIt) CUDA_TRY(cudaEventRecord(d->ev2, stream));
+    if (rec) CUDA_TRY(cudaEventRecord(e2, stream));
     d->stats.kernel_launches += 2;
     d->stats.fill_launches += 1;
     d->stats.traceback_launches += 1;
@@ -381,6 +401,7 @@ void dnab_decoder_destroy(dnab_decoder* d) {
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   if (d->ev2) cudaEventDestroy(d->ev2);
+  for (cudaEvent_t e : d->evPool) cudaEventDestroy(e);
   delete d;
 }
 
@@ -412,9 +433,54 @@ int dnab_decoder_get_info(const dnab_decoder* dc, dnab_decoder_info* info) {
   return DNAB_OK;
 }
 
-int dnab_decoder_get_stats(const dnab_decoder* d, dnab_decoder_stats* s) {
-  if (!d || !s) return DNAB_EINVAL;
+/* Profiling aid (not part of the stable ABI): counters accumulated by rank 0 / thread 0 of every
+ * cluster: [0] columns, [1] frontier sweeps after the first dense one, [2] worklist entries of
+ * rank 0, [3..5] SM cycles in the emission step / closure / predecessor pass. */
+int dnab_decoder_set_debug(dnab_decoder* d, int enabled) {
+  if (!d) return DNAB_EINVAL;
+  cudaSetDevice(d->device);
+  if (enabled) {
+    if (d->dDbg.ensure(16) != cudaSuccess) return DNAB_ECUDA;
+    cudaMemset(d->dDbg.p, 0, 16 * sizeof(unsigned long long));
+  }
+  d->debug = enabled != 0;
+  return DNAB_OK;
+}
+int dnab_decoder_debug_counters(dnab_decoder* d, unsigned long long* out16) {
+  if (!d || !d->dDbg.p) return DNAB_EINVAL;
+  cudaSetDevice(d->device);
+  return cudaMemcpy(out16, d->dDbg.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? DNAB_OK : DNAB_ECUDA;
+}
+
+int dnab_decoder_set_timing(dnab_decoder* d, int enabled) {
+  if (!d) return DNAB_EINVAL;
+  d->timing = enabled != 0;
+  return DNAB_OK;
+}
+
+int dnab_decoder_get_stats(const dnab_decoder* dc, dnab_decoder_stats* s) {
+  if (!dc || !s) return DNAB_EINVAL;
+  auto* d = const_cast<dnab_decoder*>(dc);
+  // resolve the pooled event triples of the device path (the caller has synchronised)
+  for (size_t i = 0; i + 2 < d->evUsed; i += 3) {
+    float a = 0, b = 0;
+    if (cudaEventElapsedTime(&a, d->evPool[i], d->evPool[i + 1]) == cudaSuccess &&
+        cudaEventElapsedTime(&b, d->evPool[i + 1], d->evPool[i + 2]) == cudaSuccess) {
+      d->stats.timed_fill_ms += a;
+      d->stats.timed_traceback_ms += b;
+      d->stats.timed_fill_launches += 1;
+    }
+  }
+  d->evUsed = 0;
   *s = d->stats;
+  return DNAB_OK;
+}
+
+int dnab_decoder_reset_timing(dnab_decoder* d) {
+  if (!d) return DNAB_EINVAL;
+  d->evUsed = 0;
+  d->stats.timed_fill_ms = d->stats.timed_traceback_ms = 0;
+  d->stats.timed_fill_launches = 0;
   return DNAB_OK;
 }
 

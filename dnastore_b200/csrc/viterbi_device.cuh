@@ -6,15 +6,16 @@
 namespace dnab {
 
 constexpr int kMaxSyms = 32;     // distinct input symbols incl. the "no input" symbol 0
-constexpr int kMaxK = 6;         // duplication depth supported by the packed state record (-l <= 13)
+constexpr int kMaxK = 6;         // duplication depth supported by the packed state block (-l <= 13)
 constexpr int kMaxCluster = 16;
 constexpr uint32_t kNoPred = 255;  // predecessor record: "no candidate"
+constexpr uint32_t kBlockWords = 8;  // state blocks are padded to 32 bytes (one L2 sector)
 
-// Packed incoming edge: source = (rank, local index) in the cluster partition.
-//   bits  0..19  local index of the source state inside its CTA's slice
-//   bits 20..23  cluster rank of the CTA owning the source
-//   bits 24..28  input-symbol id (0 = no input symbol, score 0)
-//   bits 29..30  emitted base (emit edges only)
+// Packed edge word: the OTHER endpoint = (rank, local index) in the cluster partition.
+//   bits  0..19  local index of that state inside its CTA's slice
+//   bits 20..23  cluster rank of the CTA owning it
+//   bits 24..28  input-symbol id (0 = no input symbol, score 0)   [incoming edges]
+//   bits 29..30  emitted base                                     [incoming emit edges]
 __host__ __device__ inline uint32_t edgeLocal(uint32_t w) { return w & 0xFFFFFu; }
 __host__ __device__ inline uint32_t edgeRank(uint32_t w) { return (w >> 20) & 0xFu; }
 __host__ __device__ inline uint32_t edgeSym(uint32_t w) { return (w >> 24) & 0x1Fu; }
@@ -23,15 +24,18 @@ __host__ __device__ inline uint32_t packEdge(uint32_t local, uint32_t rank, uint
   return local | (rank << 20) | (sym << 24) | (base << 29);
 }
 
-// Per-state record (uint2):
-//   .x  offset of the state's incoming edges in inEdges: [emit edges][null edges],
-//       each group in the reference's list order (source index, transition index)
-//   .y  bits 0..7 nEmit, 8..15 nNull, 16..19 mdl, 20..31 ctx (2 bits per
-//       duplication index i: tanDupBase(ss,i))
-__host__ __device__ inline uint32_t recNEmit(uint32_t y) { return y & 0xFFu; }
-__host__ __device__ inline uint32_t recNNull(uint32_t y) { return (y >> 8) & 0xFFu; }
-__host__ __device__ inline uint32_t recMdl(uint32_t y) { return (y >> 16) & 0xFu; }
-__host__ __device__ inline uint32_t recCtx(uint32_t y, uint32_t i) { return (y >> (20 + 2 * i)) & 0x3u; }
+// State block (32-byte aligned run of 32-bit words in `blocks`, found through blockOff):
+//   word 0   nEmit | nNull<<8 | nOut<<16 | mdl<<24
+//   word 1   ctx: 2 bits per duplication index i = tanDupBase(ss,i)
+//   then     nEmit incoming emit edges, nNull incoming null edges -- each group in the
+//            reference's list order (source index, transition index) --
+//   then     nOut outgoing edges (destinations to wake when this state's cells grow)
+// One sector fetch brings the header and the first six edge words.
+__host__ __device__ inline uint32_t hdrNEmit(uint32_t w0) { return w0 & 0xFFu; }
+__host__ __device__ inline uint32_t hdrNNull(uint32_t w0) { return (w0 >> 8) & 0xFFu; }
+__host__ __device__ inline uint32_t hdrNOut(uint32_t w0) { return (w0 >> 16) & 0xFFu; }
+__host__ __device__ inline uint32_t hdrMdl(uint32_t w0) { return (w0 >> 24) & 0xFu; }
+__host__ __device__ inline uint32_t hdrCtx(uint32_t w1, uint32_t i) { return (w1 >> (2 * i)) & 0x3u; }
 
 struct DevTables {
   uint32_t nStates;   // real states
@@ -43,10 +47,8 @@ struct DevTables {
   uint32_t startG;    // padded-space index of reference state 0
   uint32_t endG;      // padded-space index of the reference's last state
   uint32_t tInSmem;   // T columns in shared memory (else in global scratch)
-  const uint2* stateRec;      // [Np]
-  const uint32_t* inEdges;    // packed incoming edges
-  const uint32_t* outOff;     // [Np+1] outgoing (emit+null) adjacency, for dirty marking
-  const uint32_t* outEdges;   // local | rank<<20
+  const uint32_t* blocks;     // state blocks
+  const uint32_t* blockOff;   // [Np] word offset of each state's block (multiple of kBlockWords)
   const uint32_t* origId;     // [Np] reference state index, 0xFFFFFFFF for padding
   const uint8_t* symChar;     // [nSyms] input-symbol character of each id
   double symScore[kMaxSyms];  // log(symProb) per id (0 for id 0)

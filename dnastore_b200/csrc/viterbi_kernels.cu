@@ -54,17 +54,18 @@ __device__ __forceinline__ double ldClusterF64(uint32_t addr) {
 // raising the same cells concurrently
 __device__ __forceinline__ double ldRelaxedF64(uint32_t addr) {
   double v;
-  asm volatile("ld.relaxed.cluster.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  asm volatile("ld.relaxed.cluster.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void stRelaxedF64(uint32_t addr, double v) {
   asm volatile("st.relaxed.cluster.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
-__device__ __forceinline__ void stRelaxedU8(uint32_t addr, uint32_t v) {
-  asm volatile("st.relaxed.cluster.shared::cluster.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+// flag / control stores into a peer: made visible by the next cluster barrier
+__device__ __forceinline__ void stClusterU8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void stRelaxedU32(uint32_t addr, uint32_t v) {
-  asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void stClusterU32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // std::max(a,b) of the reference: keeps a on ties, no NaN handling needed
@@ -76,54 +77,6 @@ __device__ __forceinline__ double negInf() { return __longlong_as_double(0xFFF00
 // shared-memory carve-up (identical in every CTA of a cluster, which is what lets
 // a local offset be mapped into a peer with mapa)
 // ---------------------------------------------------------------------------
-struct SmemLayout {
-  uint32_t sBuf[2];   // byte offsets of the two S columns
-  uint32_t dBuf;
-  uint32_t tBuf;      // k*M doubles, only if tInSmem
-  uint32_t tsE;       // [nSyms*16] (score+noGap)+sub  -- traceback association, src/viterbi.cpp:255
-  uint32_t symScore;  // [kMaxSyms]
-  uint32_t tsDext;    // [kMaxSyms] score+delExtend    -- src/viterbi.cpp:272
-  uint32_t tsDopen;   // [kMaxSyms] score+delOpen      -- src/viterbi.cpp:273
-  uint32_t sub;       // [16]
-  uint32_t tsT;       // [kMaxK] tanDup+len[i]         -- src/viterbi.cpp:286
-  uint32_t len;       // [kMaxK]
-  uint32_t chg;       // [2][kMaxCluster] u32
-  uint32_t count;     // u32 (+pad)
-  uint32_t work;      // [M] u32
-  uint32_t dirty[2];  // [Mpad] u8 each
-  uint32_t seq;       // packed read
-  uint32_t total;
-};
-
-__host__ __device__ inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t maxLen) {
-  SmemLayout L;
-  uint32_t at = 0;
-  auto take = [&](uint32_t bytes) {
-    const uint32_t here = at;
-    at += (bytes + 15u) & ~15u;
-    return here;
-  };
-  L.sBuf[0] = take(M * 8);
-  L.sBuf[1] = take(M * 8);
-  L.dBuf = take(M * 8);
-  L.tBuf = tInSmem ? take(k * M * 8) : 0;
-  L.tsE = take(kMaxSyms * 16 * 8);
-  L.symScore = take(kMaxSyms * 8);
-  L.tsDext = take(kMaxSyms * 8);
-  L.tsDopen = take(kMaxSyms * 8);
-  L.sub = take(16 * 8);
-  L.tsT = take(8 * 8);
-  L.len = take(8 * 8);
-  L.chg = take(2 * kMaxCluster * 4);
-  L.count = take(16);
-  L.work = take(M * 4);
-  L.dirty[0] = take(M);
-  L.dirty[1] = take(M);
-  L.seq = take((maxLen + 3) / 4 + 16);
-  L.total = at;
-  return L;
-}
-
 uint32_t fillSmemBytes(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t maxLen) {
   return makeLayout(M, k, tInSmem, maxLen).total;
 }
@@ -131,61 +84,111 @@ uint32_t fillSmemBytes(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t maxLen
 // ---------------------------------------------------------------------------
 // fill kernel
 // ---------------------------------------------------------------------------
-struct ColumnCtx {
-  // per-CTA constants
+struct Cta {
   const DevTables* tb;
   unsigned char* smem;
   uint32_t smemBase;  // shared-window address of smem[0]
-  SmemLayout lay;
-  uint32_t rank, M, C, k;
+  const SmemLayout* layp;  // lives in the kernel parameter (constant) space
+  uint32_t rank, M, tid, nThreads;
+  const double* symScore;
+  const uint32_t* boff;
 };
 
-// One relaxation of state `i` of this CTA's slice (pull form of src/viterbi.cpp:118-158):
+// The first eight words of a state block in registers (one 32-byte sector).
+struct BlockRegs {
+  uint32_t w0, w1, e0, e1, e2, e3, e4, e5;
+  const uint32_t* p;
+};
+__device__ __forceinline__ BlockRegs loadBlock(const Cta& c, uint32_t i) {
+  BlockRegs b;
+  b.p = c.tb->blocks + c.boff[i];
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(b.p));
+  const uint4 d = __ldg(reinterpret_cast<const uint4*>(b.p) + 1);
+  b.w0 = a.x; b.w1 = a.y; b.e0 = a.z; b.e1 = a.w;
+  b.e2 = d.x; b.e3 = d.y; b.e4 = d.z; b.e5 = d.w;
+  return b;
+}
+// Edge words [base, base+4) of a block: from registers for the first chunk, else from L1/L2.
+__device__ __forceinline__ void chunkWords(const BlockRegs& b, uint32_t base, uint32_t n, uint32_t (&w)[4]) {
+  if (base == 0) {
+    w[0] = b.e0; w[1] = b.e1; w[2] = b.e2; w[3] = b.e3;
+  } else {
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) w[j] = (base + j < n) ? __ldg(b.p + 2 + base + j) : 0u;
+  }
+}
+
+// Wake every successor of local state i (its cells grew). Returns true if a peer CTA was marked.
+// bit 0 of the result: a state of this CTA was woken; bit 1: a peer CTA was woken.
+__device__ __forceinline__ uint32_t wakeSuccessors(const Cta& c, const BlockRegs& b, uint32_t nIn, uint32_t nOut,
+                                                   uint32_t localBuf, uint32_t remoteBuf) {
+  uint32_t sent = 0;
+  for (uint32_t j = 0; j < nOut; ++j) {
+    const uint32_t idx = 2 + nIn + j;
+    const uint32_t w = idx == 2 ? b.e0 : idx == 3 ? b.e1 : idx == 4 ? b.e2 : idx == 5 ? b.e3 : idx == 6 ? b.e4
+                     : idx == 7 ? b.e5 : __ldg(b.p + idx);
+    const uint32_t r = edgeRank(w), l = edgeLocal(w);
+    if (r == c.rank) {
+      c.smem[c.layp->flagLocal[localBuf] + l] = 1;
+      sent |= 1u;
+    } else {
+      stClusterU8(mapToRank(c.smemBase + c.layp->flagRemote[remoteBuf] + l, r), 1u);
+      sent |= 2u;
+    }
+  }
+  return sent;
+}
+
+// One relaxation of local state i (pull form of src/viterbi.cpp:118-158):
 //   D(d) = max( D(d), max_emit-in ( max(D(s)+delExtend, S(s)+delOpen) + score ), max_null-in ( D(s)+score ) )
 //   S(d) = max( S(d), max_null-in ( S(s)+score ), D(d)+delEnd )
 // where the stored S(s) already contains D(s)+delEnd from s's own last relaxation.
-// Returns true (and marks every successor dirty in `markBuf`) when a cell grew.
-__device__ __forceinline__ bool relaxState(const ColumnCtx& c, uint32_t i, uint32_t sCurOff, uint32_t markBuf) {
+// When a cell grew, every successor is woken (result: see wakeSuccessors).
+__device__ __forceinline__ uint32_t relaxState(const Cta& c, uint32_t i, uint32_t sCurOff, uint32_t localBuf,
+                                               uint32_t remoteBuf) {
   const DevTables& tb = *c.tb;
-  const uint32_t g = c.rank * c.M + i;
-  const uint2 rec = __ldg(&tb.stateRec[g]);
-  const uint32_t nE = recNEmit(rec.y), nN = recNNull(rec.y);
-  const double* symScore = reinterpret_cast<const double*>(c.smem + c.lay.symScore);
-  const uint32_t myS = c.smemBase + sCurOff + i * 8, myD = c.smemBase + c.lay.dBuf + i * 8;
+  const BlockRegs b = loadBlock(c, i);
+  const uint32_t nE = hdrNEmit(b.w0), nN = hdrNNull(b.w0), nIn = nE + nN;
+  const uint32_t myS = c.smemBase + sCurOff + i * 8, myD = c.smemBase + c.layp->dBuf + i * 8;
   const double oldS = ldRelaxedF64(myS), oldD = ldRelaxedF64(myD);
   double newS = oldS, newD = oldD;
-  const uint32_t dMinusS = c.lay.dBuf - sCurOff;
-  const uint32_t* edges = tb.inEdges + rec.x;
-  for (uint32_t e = 0; e < nE; ++e) {
-    const uint32_t w = __ldg(&edges[e]);
-    const uint32_t aS = mapToRank(c.smemBase + sCurOff + edgeLocal(w) * 8, edgeRank(w));
-    const double ss = ldRelaxedF64(aS), ds = ldRelaxedF64(aS + dMinusS);
-    const double cand = dmax(ds + tb.delExtend, ss + tb.delOpen) + symScore[edgeSym(w)];
-    newD = dmax(newD, cand);
-  }
-  for (uint32_t e = 0; e < nN; ++e) {
-    const uint32_t w = __ldg(&edges[nE + e]);
-    const uint32_t aS = mapToRank(c.smemBase + sCurOff + edgeLocal(w) * 8, edgeRank(w));
-    const double ss = ldRelaxedF64(aS), ds = ldRelaxedF64(aS + dMinusS);
-    const double sc = symScore[edgeSym(w)];
-    newD = dmax(newD, ds + sc);
-    newS = dmax(newS, ss + sc);
+  const uint32_t dMinusS = c.layp->dBuf - sCurOff;
+  for (uint32_t base = 0; base < nIn; base += 4) {
+    uint32_t w[4];
+    chunkWords(b, base, nIn, w);
+    double ss[4], ds[4];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j)
+      if (base + j < nIn) {  // issue every load of the chunk before the first use
+        const uint32_t aS = mapToRank(c.smemBase + sCurOff + edgeLocal(w[j]) * 8, edgeRank(w[j]));
+        ss[j] = ldRelaxedF64(aS);
+        ds[j] = ldRelaxedF64(aS + dMinusS);
+      }
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j)
+      if (base + j < nIn) {
+        const double sc = c.symScore[edgeSym(w[j])];
+        if (base + j < nE) {
+          newD = dmax(newD, dmax(ds[j] + tb.delExtend, ss[j] + tb.delOpen) + sc);
+        } else {
+          newD = dmax(newD, ds[j] + sc);
+          newS = dmax(newS, ss[j] + sc);
+        }
+      }
   }
   newS = dmax(newS, newD + tb.delEnd);
-  const bool grew = (newD > oldD) || (newS > oldS);
-  if (grew) {
+  uint32_t sent = 0;
+  if ((newD > oldD) || (newS > oldS)) {
     if (newD > oldD) stRelaxedF64(myD, newD);
     if (newS > oldS) stRelaxedF64(myS, newS);
-    const uint32_t o0 = __ldg(&tb.outOff[g]), o1 = __ldg(&tb.outOff[g + 1]);
-    for (uint32_t o = o0; o < o1; ++o) {
-      const uint32_t w = __ldg(&tb.outEdges[o]);
-      stRelaxedU8(mapToRank(c.smemBase + c.lay.dirty[markBuf] + edgeLocal(w), edgeRank(w)), 1u);
-    }
+    sent = wakeSuccessors(c, b, nIn, hdrNOut(b.w0), localBuf, remoteBuf);
   }
-  return grew;
+  return sent;
 }
 
-__global__ void __launch_bounds__(1024, 1) viterbiFillKernel(const __grid_constant__ DevTables tb, const FillArgs args) {
+template <int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
+    viterbiFillKernel(const __grid_constant__ DevTables tb, const __grid_constant__ FillArgs args) {
   extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t C = tb.C, M = tb.M, k = tb.k;
@@ -196,16 +199,16 @@ __global__ void __launch_bounds__(1024, 1) viterbiFillKernel(const __grid_consta
   const uint32_t Np = C * M;
   const double NEG = negInf();
 
-  ColumnCtx c;
+  Cta c;
   c.tb = &tb;
   c.smem = smem;
   c.smemBase = smemAddr(smem);
-  c.lay = makeLayout(M, k, tb.tInSmem, args.maxLen);
+  c.layp = &args.lay;
   c.rank = rank;
   c.M = M;
-  c.C = C;
-  c.k = k;
-  const SmemLayout& lay = c.lay;
+  c.tid = tid;
+  c.nThreads = nThreads;
+  const SmemLayout& lay = args.lay;
 
   double* symScore = reinterpret_cast<double*>(smem + lay.symScore);
   double* tsE = reinterpret_cast<double*>(smem + lay.tsE);
@@ -214,15 +217,16 @@ __global__ void __launch_bounds__(1024, 1) viterbiFillKernel(const __grid_consta
   double* subS = reinterpret_cast<double*>(smem + lay.sub);
   double* tsT = reinterpret_cast<double*>(smem + lay.tsT);
   double* lenS = reinterpret_cast<double*>(smem + lay.len);
-  volatile uint32_t* chg = reinterpret_cast<volatile uint32_t*>(smem + lay.chg);
-  uint32_t* count = reinterpret_cast<uint32_t*>(smem + lay.count);
-  uint32_t* work = reinterpret_cast<uint32_t*>(smem + lay.work);
+  volatile uint32_t* ctl = reinterpret_cast<volatile uint32_t*>(smem + lay.ctl);
+  uint32_t* boff = reinterpret_cast<uint32_t*>(smem + lay.boff);
   uint8_t* seqS = smem + lay.seq;
   double* dCol = reinterpret_cast<double*>(smem + lay.dBuf);
   double* tCol = tb.tInSmem ? reinterpret_cast<double*>(smem + lay.tBuf)
                             : args.tScratch + ((size_t)clusterId * C + rank) * (size_t)k * M;
+  c.symScore = symScore;
+  c.boff = boff;
 
-  // read-independent score tables; the traceback-association sums are formed here once
+  // read-independent tables; the traceback-association sums are formed here once
   for (uint32_t s = tid; s < kMaxSyms; s += nThreads) {
     const double sc = s < tb.nSyms ? tb.symScore[s] : NEG;
     symScore[s] = sc;
@@ -234,9 +238,19 @@ __global__ void __launch_bounds__(1024, 1) viterbiFillKernel(const __grid_consta
     lenS[j] = j < k ? tb.len[j] : NEG;
     tsT[j] = j < k ? tb.tanDup + tb.len[j] : NEG;
   }
-  for (uint32_t j = tid; j < tb.nSyms * 16; j += nThreads) {
-    const uint32_t s = j >> 4, bx = j & 15;
-    tsE[j] = (tb.symScore[s] + tb.noGap) + tb.sub[bx];
+  auto buildTsE = [&]() {
+    for (uint32_t j = tid; j < tb.nSyms * 16; j += nThreads) {
+      const uint32_t s = j >> 4, bx = j & 15;
+      tsE[j] = (tb.symScore[s] + tb.noGap) + tb.sub[bx];
+    }
+  };
+  buildTsE();
+  for (uint32_t i = tid; i < M; i += nThreads) boff[i] = __ldg(&tb.blockOff[rank * M + i]);
+  for (uint32_t j = tid; j < 64; j += nThreads) ctl[j] = 0;
+  {
+    uint32_t* fl = reinterpret_cast<uint32_t*>(smem + lay.flagLocal[0]);
+    const uint32_t nFlagWords = (lay.seq - lay.flagLocal[0]) / 4;  // the four flag arrays are contiguous
+    for (uint32_t j = tid; j < nFlagWords; j += nThreads) fl[j] = 0;
   }
   __syncthreads();
 
@@ -246,6 +260,11 @@ __global__ void __launch_bounds__(1024, 1) viterbiFillKernel(const __grid_consta
     else
       __syncthreads();
   };
+  clusterBarrier();  // every CTA's flags are clear before a peer can set them
+
+  unsigned long long dbgDense = 0, dbgSyncWait = 0, dbgCompact = 0, dbgProc = 0, dbgClusterWait = 0;
+  unsigned long long dbgRounds = 0, dbgIters = 0, dbgT1 = 0, dbgT2 = 0, dbgT3 = 0, dbgCols = 0, dbgWork = 0;
+  const bool dbgOn = args.dbg != nullptr;
 
   for (int64_t read = clusterId; read < args.nReads; read += nClusters) {
     const int32_t L = args.readLen[read];
@@ -264,147 +283,190 @@ __global__ void __launch_bounds__(1024, 1) viterbiFillKernel(const __grid_consta
       double* sCur = reinterpret_cast<double*>(smem + sCurOff);
       const uint32_t x = pos > 0 ? (seqS[(pos - 1) >> 2] >> (2 * ((pos - 1) & 3))) & 3u : 0u;
 
+      long long tc0 = dbgOn ? clock64() : 0;
       // ---- (1) emission step: S0 from the previous column, T shift (src/viterbi.cpp:92-106) ----
       for (uint32_t i = tid; i < M; i += nThreads) {
-        const uint32_t g = rank * M + i;
-        const uint2 rec = __ldg(&tb.stateRec[g]);
-        const uint32_t nE = recNEmit(rec.y), mdl = recMdl(rec.y);
         double s = NEG;
         if (pos == 0) {
+          const uint32_t g = rank * M + i;
           const bool real = __ldg(&tb.origId[g]) != 0xFFFFFFFFu;
           s = (real && (tb.local || g == tb.startG)) ? 0.0 : NEG;  // src/viterbi.cpp:75-79
           for (uint32_t j = 0; j < k; ++j) tCol[j * M + i] = NEG;
         } else {
-          const uint32_t* edges = tb.inEdges + rec.x;
-          for (uint32_t e = 0; e < nE; ++e) {
-            const uint32_t w = __ldg(&edges[e]);
-            const double v = ldClusterF64(mapToRank(c.smemBase + sPrevOff + edgeLocal(w) * 8, edgeRank(w)));
-            const double cand = ((v + symScore[edgeSym(w)]) + tb.noGap) + subS[edgeBase(w) * 4 + x];
-            s = dmax(s, cand);
+          const BlockRegs b = loadBlock(c, i);
+          const uint32_t nE = hdrNEmit(b.w0), mdl = hdrMdl(b.w0);
+          double t0 = NEG;
+          if (mdl > 0) t0 = tCol[i];
+          for (uint32_t base = 0; base < nE; base += 4) {
+            uint32_t w[4];
+            chunkWords(b, base, nE, w);
+            double v[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+              if (base + j < nE) v[j] = ldClusterF64(mapToRank(c.smemBase + sPrevOff + edgeLocal(w[j]) * 8, edgeRank(w[j])));
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+              if (base + j < nE)
+                s = dmax(s, ((v[j] + symScore[edgeSym(w[j])]) + tb.noGap) + subS[edgeBase(w[j]) * 4 + x]);
           }
           if (mdl > 0) {
-            const double t2s = tCol[i] + subS[recCtx(rec.y, 0) * 4 + x];
+            const double t2s = t0 + subS[hdrCtx(b.w1, 0) * 4 + x];
             s = dmax(s, t2s);
-            for (uint32_t j = 0; j + 1 < mdl; ++j) tCol[j * M + i] = tCol[(j + 1) * M + i] + subS[recCtx(rec.y, j + 1) * 4 + x];
+            for (uint32_t j = 0; j + 1 < mdl; ++j) tCol[j * M + i] = tCol[(j + 1) * M + i] + subS[hdrCtx(b.w1, j + 1) * 4 + x];
             tCol[(mdl - 1) * M + i] = t2s;  // slot mdl-1 is free until step (4): park the T->S candidate there
           }
         }
         sCur[i] = s;
         dCol[i] = NEG;
-        smem[lay.dirty[0] + i] = 0;
-        smem[lay.dirty[1] + i] = 0;
       }
       clusterBarrier();
+      long long tc1 = dbgOn ? clock64() : 0;
 
       // ---- (2) closure: null transitions + deletions (src/viterbi.cpp:110-159) ----
-      bool grew = false;
-      for (uint32_t i = tid; i < M; i += nThreads) grew |= relaxState(c, i, sCurOff, 1);  // sweep 1: every state
-      for (uint32_t sweep = 1;; ++sweep) {
-        const uint32_t par = sweep & 1;
-        const int anyLocal = __syncthreads_or(grew ? 1 : 0);
-        uint32_t any = (uint32_t)anyLocal;
-        if (C > 1) {
-          if (tid < C) stRelaxedU32(mapToRank(c.smemBase + lay.chg + (par * kMaxCluster + rank) * 4, tid), any);
-          cluster.sync();
-          any = 0;
-          for (uint32_t r = 0; r < C; ++r) any |= chg[par * kMaxCluster + r];
-        }
-        if (!any) break;
-        // compact this CTA's dirty flags into a dense worklist
-        if (tid == 0) *count = 0;
-        __syncthreads();
-        uint8_t* flags = smem + lay.dirty[par];
-        for (uint32_t base = 0; base < M; base += nThreads) {
-          const uint32_t i = base + tid;
-          const bool set = i < M && flags[i];
-          if (set) flags[i] = 0;
-          const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, set);
-          if (ballot) {
-            const uint32_t lane = tid & 31;
-            uint32_t at = 0;
-            if (lane == 0) at = atomicAdd(count, __popc(ballot));
-            at = __shfl_sync(0xFFFFFFFFu, at, 0);
-            if (set) work[at + __popc(ballot & ((1u << lane) - 1))] = i;
+      // Round 0 relaxes every state once.  Then: each CTA iterates over the states woken by its
+      // OWN states until none is left (CTA barriers only); states woken by a peer wait in the
+      // remote flag buffer of the current round and are picked up after the next cluster
+      // barrier.  The cluster is done when a whole round woke nobody across CTAs.
+      {
+        // Every thread owns the 4-state flag words tid, tid+nThreads, ...: it relaxes the states whose
+        // flag is set in the buffers being consumed and sets flags in the buffers being filled.
+        const uint32_t nWords = (M + 3) / 4;
+        uint32_t round = 0, it = 0, sent = 0;
+        for (uint32_t i = tid; i < M; i += nThreads) sent |= relaxState(c, i, sCurOff, 1, 0);
+        if (dbgOn && tid == 0) dbgDense += clock64() - tc1;
+        bool pickRemote = false;
+        for (;;) {
+          // local fixed point: one CTA barrier per iteration
+          while (__syncthreads_or((int)(sent & 1u)) || pickRemote) {
+            ++it;
+            sent &= 2u;
+            uint32_t* fl = reinterpret_cast<uint32_t*>(smem + lay.flagLocal[it & 1]);
+            uint32_t* fr = reinterpret_cast<uint32_t*>(smem + lay.flagRemote[(round & 1) ^ 1]);
+            for (uint32_t w = tid; w < nWords; w += nThreads) {
+              uint32_t f = fl[w];
+              if (f) fl[w] = 0;
+              if (pickRemote) {
+                const uint32_t g = fr[w];
+                if (g) fr[w] = 0;
+                f |= g;
+              }
+              if (f) {
+                if (dbgOn) dbgWork += __popc(f & 0x01010101u);
+#pragma unroll 1
+                for (uint32_t q = 0; q < 4; ++q)
+                  if (f & (0xFFu << (8 * q))) sent |= relaxState(c, 4 * w + q, sCurOff, (it & 1) ^ 1, round & 1);
+              }
+            }
+            pickRemote = false;
+            if (dbgOn && tid == 0) dbgIters++;
           }
+          if (C == 1) break;
+          long long tcb = dbgOn ? clock64() : 0;
+          const uint32_t anySent = (uint32_t)__syncthreads_or((int)(sent & 2u));
+          if (tid < C) stClusterU32(mapToRank(c.smemBase + lay.ctl + (16 + (round & 1) * kMaxCluster + rank) * 4, tid), anySent);
+          cluster.sync();
+          if (dbgOn && tid == 0) dbgClusterWait += clock64() - tcb;
+          uint32_t tot = 0;
+          for (uint32_t r = 0; r < C; ++r) tot |= ctl[16 + (round & 1) * kMaxCluster + r];
+          if (!tot) break;
+          if (dbgOn && tid == 0) dbgRounds++;
+          ++round;  // peers now fill the other remote buffer; the one just completed is picked up next
+          pickRemote = true;
+          sent = 0;
         }
-        __syncthreads();
-        const uint32_t n = *count;
-        grew = false;
-        for (uint32_t j = tid; j < n; j += nThreads) grew |= relaxState(c, work[j], sCurOff, par ^ 1);
       }
 
+      long long tc2 = dbgOn ? clock64() : 0;
       // ---- (3) predecessor records with the traceback's arithmetic (src/viterbi.cpp:251-286)
       //      (4) duplication opens (src/viterbi.cpp:161-168) ----
       uint8_t* predCol = predRead + (size_t)pos * (k + 2) * Np;
       for (uint32_t i = tid; i < M; i += nThreads) {
         const uint32_t g = rank * M + i;
-        const uint2 rec = __ldg(&tb.stateRec[g]);
-        const uint32_t nE = recNEmit(rec.y), nN = recNNull(rec.y), mdl = recMdl(rec.y);
-        const uint32_t* edges = tb.inEdges + rec.x;
+        const BlockRegs b = loadBlock(c, i);
+        const uint32_t nE = hdrNEmit(b.w0), nN = hdrNNull(b.w0), mdl = hdrMdl(b.w0), nIn = nE + nN;
         const double sHere = sCur[i], dHere = dCol[i];
         const uint32_t dMinusS = lay.dBuf - sCurOff;
+        const double parked = (mdl > 0 && pos > 0) ? tCol[(mdl - 1) * M + i] : NEG;  // T(state,pos-1,0)+sub
 
-        double best = NEG;
-        uint32_t idx = kNoPred;
-        double bestD = NEG;
-        uint32_t idxD = kNoPred;
-        for (uint32_t e = 0; e < nE; ++e) {
-          const uint32_t w = __ldg(&edges[e]);
-          const uint32_t sym = edgeSym(w);
-          if (pos > 0) {
-            const double v = ldClusterF64(mapToRank(c.smemBase + sPrevOff + edgeLocal(w) * 8, edgeRank(w))) +
-                             tsE[sym * 16 + edgeBase(w) * 4 + x];
-            if (v > best) {
-              best = v;
-              idx = e;
+        double best = NEG, bestD = NEG;
+        uint32_t idx = kNoPred, idxD = kNoPred;
+        for (uint32_t base = 0; base < nIn; base += 2) {
+          uint32_t w[2];
+          if (base == 0) {
+            w[0] = b.e0;
+            w[1] = b.e1;
+          } else if (base == 2) {
+            w[0] = b.e2;
+            w[1] = b.e3;
+          } else if (base == 4) {
+            w[0] = b.e4;
+            w[1] = b.e5;
+          } else {
+            w[0] = __ldg(b.p + 2 + base);
+            w[1] = base + 1 < nIn ? __ldg(b.p + 3 + base) : 0u;
+          }
+          double vp[2], vs[2], vd[2];
+#pragma unroll
+          for (uint32_t j = 0; j < 2; ++j)
+            if (base + j < nIn) {
+              const uint32_t aS = mapToRank(c.smemBase + sCurOff + edgeLocal(w[j]) * 8, edgeRank(w[j]));
+              vs[j] = ldClusterF64(aS);
+              vd[j] = ldClusterF64(aS + dMinusS);
+              if (base + j < nE && pos > 0) vp[j] = ldClusterF64(aS + (sPrevOff - sCurOff));
             }
-          }
-          const uint32_t aS = mapToRank(c.smemBase + sCurOff + edgeLocal(w) * 8, edgeRank(w));
-          const double vd = ldClusterF64(aS + dMinusS) + tsDext[sym];
-          if (vd > bestD) {
-            bestD = vd;
-            idxD = 2 * e;
-          }
-          const double vs = ldClusterF64(aS) + tsDopen[sym];
-          if (vs > bestD) {
-            bestD = vs;
-            idxD = 2 * e + 1;
-          }
-        }
-        for (uint32_t e = 0; e < nN; ++e) {
-          const uint32_t w = __ldg(&edges[nE + e]);
-          const double sc = symScore[edgeSym(w)];
-          const uint32_t aS = mapToRank(c.smemBase + sCurOff + edgeLocal(w) * 8, edgeRank(w));
-          const double v = ldClusterF64(aS) + sc;
-          if (v > best) {
-            best = v;
-            idx = nE + e;
-          }
-          const double vd = ldClusterF64(aS + dMinusS) + sc;
-          if (vd > bestD) {
-            bestD = vd;
-            idxD = 2 * nE + e;
-          }
+#pragma unroll
+          for (uint32_t j = 0; j < 2; ++j)
+            if (base + j < nIn) {
+              const uint32_t e = base + j, sym = edgeSym(w[j]);
+              if (e < nE) {
+                if (pos > 0) {
+                  const double v = vp[j] + tsE[sym * 16 + edgeBase(w[j]) * 4 + x];
+                  if (v > best) {
+                    best = v;
+                    idx = e;
+                  }
+                }
+                const double ve = vd[j] + tsDext[sym];
+                if (ve > bestD) {
+                  bestD = ve;
+                  idxD = 2 * e;
+                }
+                const double vo = vs[j] + tsDopen[sym];
+                if (vo > bestD) {
+                  bestD = vo;
+                  idxD = 2 * e + 1;
+                }
+              } else {
+                const double sc = symScore[sym];
+                const double v = vs[j] + sc;
+                if (v > best) {
+                  best = v;
+                  idx = e;
+                }
+                const double vn = vd[j] + sc;
+                if (vn > bestD) {
+                  bestD = vn;
+                  idxD = nE + e;  // = 2*nE + (e - nE)
+                }
+              }
+            }
         }
         {
           const double v = dHere + tb.delEnd;
           if (v > best) {
             best = v;
-            idx = nE + nN;
+            idx = nIn;
           }
         }
-        if (mdl > 0 && pos > 0) {
-          const double v = tCol[(mdl - 1) * M + i];  // parked T(state,pos-1,0)+sub
-          if (v > best) {
-            best = v;
-            idx = nE + nN + 1;
-          }
+        if (mdl > 0 && pos > 0 && parked > best) {
+          best = parked;
+          idx = nIn + 1;
         }
         if (tb.local && pos == 0) {
           const double v = ldClusterF64(mapToRank(c.smemBase + sCurOff + (tb.startG % M) * 8, tb.startG / M)) + 0.0;
           if (v > best) {
             best = v;
-            idx = nE + nN + 2;
+            idx = nIn + 2;
           }
         }
         const bool real = __ldg(&tb.origId[g]) != 0xFFFFFFFFu;
@@ -413,14 +475,9 @@ __global__ void __launch_bounds__(1024, 1) viterbiFillKernel(const __grid_consta
         for (uint32_t j = 0; j < k; ++j) {
           uint32_t idxT = kNoPred;
           if (pos > 0 && j < mdl) {
-            double bestT = NEG;
             const double shifted = (j + 1 < mdl) ? tCol[j * M + i] : NEG;
-            if (j + 1 < mdl && shifted > bestT) {
-              bestT = shifted;
-              idxT = 0;
-            }
-            const double open = sHere + tsT[j];
-            if (open > bestT) idxT = 1;
+            if (j + 1 < mdl && shifted > NEG) idxT = 0;
+            if (sHere + tsT[j] > shifted) idxT = 1;
             tCol[j * M + i] = dmax(shifted, (sHere + tb.tanDup) + lenS[j]);  // (4)
           }
           predCol[(size_t)(2 + j) * Np + g] = (uint8_t)idxT;
@@ -433,6 +490,13 @@ __global__ void __launch_bounds__(1024, 1) viterbiFillKernel(const __grid_consta
         }
       }
       clusterBarrier();
+      if (dbgOn && tid == 0) {
+        const long long tc3 = clock64();
+        dbgT1 += tc1 - tc0;
+        dbgT2 += tc2 - tc1;
+        dbgT3 += tc3 - tc2;
+        dbgCols++;
+      }
     }
 
     // ---- end of read: log-likelihood and traceback start (src/viterbi.cpp:171-173, 239-245) ----
@@ -469,9 +533,9 @@ __global__ void __launch_bounds__(1024, 1) viterbiFillKernel(const __grid_consta
           }
         }
         __syncthreads();
-        // reuse the worklist area as reduction scratch: [warp] -> (value, orig, g)
-        double* rv = reinterpret_cast<double*>(smem + lay.tsE);  // >= 32 doubles, free between reads
-        uint32_t* ro = work;
+        // reduction scratch: the tsE table (rebuilt below) is free between reads
+        double* rv = tsE;
+        uint32_t* ro = reinterpret_cast<uint32_t*>(tsE + 32);
         if ((tid & 31) == 0) {
           rv[tid >> 5] = bv;
           ro[2 * (tid >> 5)] = bo;
@@ -491,14 +555,24 @@ __global__ void __launch_bounds__(1024, 1) viterbiFillKernel(const __grid_consta
           args.partG[read * C + rank] = bg;
         }
         __syncthreads();
-        // tsE was clobbered: rebuild it before the next read
-        for (uint32_t j = tid; j < tb.nSyms * 16; j += nThreads) {
-          const uint32_t s = j >> 4, bx = j & 15;
-          tsE[j] = (tb.symScore[s] + tb.noGap) + tb.sub[bx];
-        }
+        buildTsE();
         __syncthreads();
       }
     }
+  }
+  if (dbgOn && tid == 0 && rank == 0) {
+    atomicAdd(&args.dbg[0], dbgCols);
+    atomicAdd(&args.dbg[1], dbgIters);
+    atomicAdd(&args.dbg[2], dbgWork);
+    atomicAdd(&args.dbg[3], dbgT1);
+    atomicAdd(&args.dbg[4], dbgT2);
+    atomicAdd(&args.dbg[5], dbgT3);
+    atomicAdd(&args.dbg[6], dbgRounds);
+    atomicAdd(&args.dbg[7], dbgDense);
+    atomicAdd(&args.dbg[8], dbgSyncWait);
+    atomicAdd(&args.dbg[9], dbgCompact);
+    atomicAdd(&args.dbg[10], dbgProc);
+    atomicAdd(&args.dbg[11], dbgClusterWait);
   }
   clusterBarrier();  // no CTA may exit while a peer can still read its shared memory
 }
@@ -568,9 +642,9 @@ __global__ void viterbiTracebackKernel(const DevTables tb, const TracebackArgs a
       status = DNAB_READ_TRACEBACK_FAILED_;
       break;
     }
-    const uint2 rec = tb.stateRec[g];
-    const uint32_t nE = recNEmit(rec.y), nN = recNNull(rec.y);
-    const uint32_t* edges = tb.inEdges + rec.x;
+    const uint32_t* blk = tb.blocks + tb.blockOff[g];
+    const uint32_t nE = hdrNEmit(blk[0]), nN = hdrNNull(blk[0]);
+    const uint32_t* edges = blk + 2;
     uint32_t sym = 0;
     if (mut == 0) {
       if (p < nE) {
@@ -626,14 +700,26 @@ __global__ void viterbiTracebackKernel(const DevTables tb, const TracebackArgs a
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
+typedef void (*FillKernelPtr)(const DevTables, const FillArgs);
+static FillKernelPtr pickFillKernel(uint32_t threads) {
+  if (threads > 512) return viterbiFillKernel<1024, 1>;  // 64 registers/thread
+  if (threads > 256) return viterbiFillKernel<512, 1>;   // 128
+  if (threads > 128) return viterbiFillKernel<256, 2>;   // 128
+  return viterbiFillKernel<128, 4>;                      // 128
+}
+
+static cudaError_t prepFill(FillKernelPtr kern, const DevTables& tb, uint32_t smemBytes) {
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+  if (err != cudaSuccess) return err;
+  if (tb.C > 8) err = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return err;
+}
+
 cudaError_t launchFill(const DevTables& tb, const FillArgs& args, uint32_t nClusters, uint32_t threads,
                        uint32_t smemBytes, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(viterbiFillKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+  FillKernelPtr kern = pickFillKernel(threads);
+  cudaError_t err = prepFill(kern, tb, smemBytes);
   if (err != cudaSuccess) return err;
-  if (tb.C > 8) {
-    err = cudaFuncSetAttribute(viterbiFillKernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (err != cudaSuccess) return err;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nClusters * tb.C);
   cfg.blockDim = dim3(threads);
@@ -646,16 +732,13 @@ cudaError_t launchFill(const DevTables& tb, const FillArgs& args, uint32_t nClus
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, viterbiFillKernel, tb, args);
+  return cudaLaunchKernelEx(&cfg, kern, tb, args);
 }
 
 cudaError_t queryMaxClusters(const DevTables& tb, uint32_t threads, uint32_t smemBytes, int* nClusters) {
-  cudaError_t err = cudaFuncSetAttribute(viterbiFillKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+  FillKernelPtr kern = pickFillKernel(threads);
+  cudaError_t err = prepFill(kern, tb, smemBytes);
   if (err != cudaSuccess) return err;
-  if (tb.C > 8) {
-    err = cudaFuncSetAttribute(viterbiFillKernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (err != cudaSuccess) return err;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tb.C);
   cfg.blockDim = dim3(threads);
@@ -667,7 +750,7 @@ cudaError_t queryMaxClusters(const DevTables& tb, uint32_t threads, uint32_t sme
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaOccupancyMaxActiveClusters(nClusters, viterbiFillKernel, &cfg);
+  return cudaOccupancyMaxActiveClusters(nClusters, kern, &cfg);
 }
 
 cudaError_t launchTraceback(const DevTables& tb, const TracebackArgs& args, cudaStream_t stream) {

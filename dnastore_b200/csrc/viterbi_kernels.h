@@ -14,7 +14,61 @@ constexpr int32_t DNAB_READ_NO_DECODING_ = 1;
 constexpr int32_t DNAB_READ_OVERFLOW_ = 2;
 constexpr int32_t DNAB_READ_TRACEBACK_FAILED_ = 3;
 
+// ---------------------------------------------------------------------------
+// shared-memory carve-up (identical in every CTA of a cluster, which is what lets
+// a local offset be mapped into a peer with mapa)
+// ---------------------------------------------------------------------------
+struct SmemLayout {
+  uint32_t sBuf[2];    // byte offsets of the two S columns
+  uint32_t dBuf;
+  uint32_t tBuf;       // k*M doubles, only if tInSmem
+  uint32_t boff;       // [M] u32: word offset of each local state's block
+  uint32_t tsE;        // [nSyms*16] (score+noGap)+sub  -- traceback association, src/viterbi.cpp:255
+  uint32_t symScore;   // [kMaxSyms]
+  uint32_t tsDext;     // [kMaxSyms] score+delExtend    -- src/viterbi.cpp:272
+  uint32_t tsDopen;    // [kMaxSyms] score+delOpen      -- src/viterbi.cpp:273
+  uint32_t sub;        // [16]
+  uint32_t tsT;        // [kMaxK] tanDup+len[i]         -- src/viterbi.cpp:286
+  uint32_t len;        // [kMaxK]
+  uint32_t ctl;        // u32: [16..47] sent[2][kMaxCluster]
+  uint32_t flagLocal[2];   // [Mf] u8 each: woken by a state of this CTA, double-buffered by local iteration
+  uint32_t flagRemote[2];  // [Mf] u8 each: woken by a peer CTA, double-buffered by cluster round
+  uint32_t seq;        // packed read
+  uint32_t total;
+};
+
+__host__ __device__ inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t maxLen) {
+  SmemLayout L;
+  uint32_t at = 0;
+  auto take = [&](uint32_t bytes) {
+    const uint32_t here = at;
+    at += (bytes + 15u) & ~15u;
+    return here;
+  };
+  L.sBuf[0] = take(M * 8);
+  L.sBuf[1] = take(M * 8);
+  L.dBuf = take(M * 8);
+  L.tBuf = tInSmem ? take(k * M * 8) : 0;
+  L.boff = take(M * 4);
+  L.tsE = take(kMaxSyms * 16 * 8);
+  L.symScore = take(kMaxSyms * 8);
+  L.tsDext = take(kMaxSyms * 8);
+  L.tsDopen = take(kMaxSyms * 8);
+  L.sub = take(16 * 8);
+  L.tsT = take(8 * 8);
+  L.len = take(8 * 8);
+  L.ctl = take(64 * 4);
+  L.flagLocal[0] = take(M);
+  L.flagLocal[1] = take(M);
+  L.flagRemote[0] = take(M);
+  L.flagRemote[1] = take(M);
+  L.seq = take((maxLen + 3) / 4 + 16);
+  L.total = at;
+  return L;
+}
+
 struct FillArgs {
+  SmemLayout lay;            // makeLayout(M, k, tInSmem, maxLen), computed by the host
   int64_t nReads;
   int32_t maxLen;            // pred stride: every read owns (maxLen+1) columns of records
   const uint8_t* packed;     // 2-bit reads
@@ -28,6 +82,7 @@ struct FillArgs {
   uint32_t* partOrig;        //             ... its reference state index (tie-break) ...
   uint32_t* partG;           //             ... and padded index
   double* cells;             // optional debug dump of read 0: [(L+1)][nStates][k+2]
+  unsigned long long* dbg;   // optional [16] profiling counters (see dnab_decoder_debug_counters)
 };
 
 struct TracebackArgs {

@@ -168,10 +168,21 @@ typedef struct dnab_decoder_stats {
   uint64_t traceback_launches;
   uint64_t reads;
   uint64_t cells;           /* sum over reads of n_states*(len+1)*(k+2) */
-  double last_fill_ms;      /* CUDA-event time of the most recent fill kernel (sync path only) */
+  double last_fill_ms;      /* CUDA-event time of the most recent fill kernel (host-buffer path) */
   double last_traceback_ms;
+  /* device path, when dnab_decoder_set_timing(d,1): CUDA-event time summed over every fill /
+   * traceback launch since the last dnab_decoder_reset_timing (events on the launching stream) */
+  double timed_fill_ms;
+  double timed_traceback_ms;
+  uint64_t timed_fill_launches;
 } dnab_decoder_stats;
+/* Resolves pending timing events: call only after the stream(s) used have been synchronised. */
 int dnab_decoder_get_stats(const dnab_decoder* d, dnab_decoder_stats* s);
+int dnab_decoder_set_timing(dnab_decoder* d, int enabled);
+int dnab_decoder_reset_timing(dnab_decoder* d);
+/* Profiling aid: in-kernel counters (columns, closure sweeps, worklist entries, SM cycles per phase). */
+int dnab_decoder_set_debug(dnab_decoder* d, int enabled);
+int dnab_decoder_debug_counters(dnab_decoder* d, unsigned long long* out16);
 
 /* ------------------------------------------------------------------------
  * File-level driver: the drop-in for decodeFastSeqs (src/viterbi.cpp:306-320).
