@@ -55,7 +55,7 @@ class ErrorFlags(C.Structure):
 
 class DecoderInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_states", "k", "local", "cluster_size", "states_per_cta", "threads_per_cta",
-                                          "smem_bytes_per_cta", "t_in_smem", "n_clusters", "sm_count")]
+                                          "smem_bytes_per_cta", "t_in_smem", "table_in_smem", "n_clusters", "sm_count")]
 
 
 class DecoderStats(C.Structure):
@@ -92,6 +92,7 @@ _sig("dnab_decoder_create", _vp, C.POINTER(Tables), C.c_int)
 _sig("dnab_decoder_destroy", None, _vp)
 _sig("dnab_decoder_get_info", C.c_int, _vp, C.POINTER(DecoderInfo))
 _sig("dnab_decoder_configure", C.c_int, _vp, C.c_uint32, C.c_uint32, C.c_uint32)
+_sig("dnab_decoder_configure_ex", C.c_int, _vp, C.c_uint32, C.c_uint32)
 _sig("dnab_decoder_get_stats", C.c_int, _vp, C.POINTER(DecoderStats))
 _sig("dnab_decoder_set_timing", C.c_int, _vp, C.c_int)
 _sig("dnab_decoder_reset_timing", C.c_int, _vp)
@@ -255,8 +256,11 @@ class Decoder:
         self._h = h
         self.device = int(device)
 
-    def configure(self, cluster_size=0, threads_per_cta=0, t_in_smem_mode=0):
+    def configure(self, cluster_size=0, threads_per_cta=0, t_in_smem_mode=0, table_mode=0, partition_mode=0):
         rc = lib.dnab_decoder_configure(self._h, cluster_size, threads_per_cta, t_in_smem_mode)
+        if rc:
+            raise _err(rc)
+        rc = lib.dnab_decoder_configure_ex(self._h, table_mode, partition_mode)
         if rc:
             raise _err(rc)
 

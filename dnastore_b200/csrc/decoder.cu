@@ -50,7 +50,7 @@ struct DevBuf {
 };
 
 struct LaunchPlan {
-  uint32_t C = 0, M = 0, threads = 0, tInSmem = 0, smemBytes = 0, nClusters = 0;
+  uint32_t C = 0, M = 0, threads = 0, tInSmem = 0, blocksInSmem = 0, sliceWords = 0, smemBytes = 0, nClusters = 0;
   int32_t maxLen = -1;
 };
 
@@ -71,10 +71,12 @@ struct dnab_decoder {
   double sub[16], len[kMaxK], noGap, delOpen, delExtend, delEnd, tanDup;
   // user overrides
   uint32_t wantC = 0, wantThreads = 0, wantTMode = 0;  // tMode: 0 auto, 1 smem, 2 global
+  uint32_t wantBlockMode = 0;   // transition table: 0 auto, 1 shared memory, 2 global memory
+  uint32_t wantPartition = 0;   // 0 DFS runs + degree sort, 1 index order + degree sort, 2 DFS runs, no sort
   // device-resident structures for the current plan
   LaunchPlan plan;
   DevTables dev{};
-  DevBuf<uint32_t> dBlocks, dBlockOff, dOrigId;
+  DevBuf<uint32_t> dBlocks, dBlockOff, dSliceOff, dOrigId;
   DevBuf<uint8_t> dSymChar;
   // scratch
   DevBuf<uint8_t> dPred;
@@ -99,88 +101,192 @@ struct dnab_decoder {
 
 namespace dnab {
 
+// Locality-preserving order of the states: depth-first preorder over the transition graph.
+// Cutting it into C equal runs keeps most transitions inside one CTA (85% on the BASELINE
+// config 2 machine against 56% for index order), which turns DSMEM gathers into local LDS.
+static std::vector<uint32_t> dfsOrder(const dnab_decoder* d) {
+  const uint32_t N = d->nStates;
+  std::vector<uint32_t> outOff(N + 1, 0), outDst;
+  auto countEdges = [&](const std::vector<uint32_t>& src) {
+    for (uint32_t s : src) ++outOff[s + 1];
+  };
+  countEdges(d->emitSrc);
+  countEdges(d->nullSrc);
+  for (uint32_t s = 0; s < N; ++s) outOff[s + 1] += outOff[s];
+  outDst.resize(outOff[N]);
+  std::vector<uint32_t> fill(outOff.begin(), outOff.end() - 1);
+  for (uint32_t g = 0; g < N; ++g) {
+    for (uint32_t e = d->emitOff[g]; e < d->emitOff[g + 1]; ++e) outDst[fill[d->emitSrc[e]]++] = g;
+    for (uint32_t e = d->nullOff[g]; e < d->nullOff[g + 1]; ++e) outDst[fill[d->nullSrc[e]]++] = g;
+  }
+  std::vector<uint32_t> order;
+  order.reserve(N);
+  std::vector<char> seen(N, 0);
+  std::vector<uint32_t> stack;
+  for (uint32_t root = 0; root < N; ++root) {
+    if (seen[root]) continue;
+    seen[root] = 1;
+    stack.push_back(root);
+    while (!stack.empty()) {
+      const uint32_t v = stack.back();
+      stack.pop_back();
+      order.push_back(v);
+      for (uint32_t e = outOff[v]; e < outOff[v + 1]; ++e) {
+        const uint32_t u = outDst[e];
+        if (!seen[u]) {
+          seen[u] = 1;
+          stack.push_back(u);
+        }
+      }
+    }
+  }
+  return order;
+}
+
+// Word count of one CTA's slice of state blocks for cluster size C (used to decide whether
+// the slice fits in shared memory before the blocks are actually built).
+struct Partition {
+  uint32_t C = 0, M = 0;
+  std::vector<uint32_t> newOf;   // reference state -> padded index g
+  std::vector<uint32_t> origOf;  // padded index g -> reference state (0xFFFFFFFF = padding)
+  std::vector<uint32_t> blocks, blockOff, sliceOff;
+  uint32_t maxSliceWords = 0;
+};
+
+static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
+  const uint32_t N = d->nStates, k = d->k;
+  const uint32_t M = (N + C - 1) / C, Np = C * M;
+  P.C = C;
+  P.M = M;
+  // 1. CTA assignment: equal runs of the DFS order (identity order for a single CTA)
+  std::vector<uint32_t> order;
+  if (C > 1 && d->wantPartition != 1)
+    order = dfsOrder(d);
+  else {
+    order.resize(N);
+    for (uint32_t s = 0; s < N; ++s) order[s] = s;
+  }
+  // 2. inside a CTA: descending in-degree, so that the 32 lanes of a warp walk equally long edge
+  //    lists (dense passes) and the few hub states sit together; stable, so runs keep DFS order
+  auto inDeg = [&](uint32_t s) { return (d->emitOff[s + 1] - d->emitOff[s]) + (d->nullOff[s + 1] - d->nullOff[s]); };
+  P.origOf.assign(Np, 0xFFFFFFFFu);
+  P.newOf.assign(N, 0);
+  for (uint32_t r = 0; r < C; ++r) {
+    const uint32_t lo = std::min(N, r * M), hi = std::min(N, (r + 1) * M);
+    std::vector<uint32_t> mine(order.begin() + lo, order.begin() + hi);
+    if (d->wantPartition != 2)
+      std::stable_sort(mine.begin(), mine.end(), [&](uint32_t a, uint32_t b) { return inDeg(a) > inDeg(b); });
+    for (uint32_t j = 0; j < mine.size(); ++j) {
+      P.origOf[r * M + j] = mine[j];
+      P.newOf[mine[j]] = r * M + j;
+    }
+  }
+  // 3. state blocks (viterbi_device.cuh)
+  std::vector<std::vector<uint32_t>> outs(N);
+  for (uint32_t s = 0; s < N; ++s) {
+    for (uint32_t e = d->emitOff[s]; e < d->emitOff[s + 1]; ++e) outs[d->emitSrc[e]].push_back(P.newOf[s]);
+    for (uint32_t e = d->nullOff[s]; e < d->nullOff[s + 1]; ++e) outs[d->nullSrc[e]].push_back(P.newOf[s]);
+  }
+  P.blocks.clear();
+  P.blockOff.assign(Np, 0);
+  P.sliceOff.assign(C + 1, 0);
+  P.maxSliceWords = 0;
+  for (uint32_t g = 0; g < Np; ++g) {
+    const uint32_t rank = g / M;
+    if (g % M == 0) P.sliceOff[rank] = (uint32_t)P.blocks.size();
+    P.blockOff[g] = (uint32_t)P.blocks.size();
+    const uint32_t s = P.origOf[g];
+    if (s == 0xFFFFFFFFu) {
+      P.blocks.push_back(0);
+      P.blocks.push_back(0);
+    } else {
+      const uint32_t nE = d->emitOff[s + 1] - d->emitOff[s], nN = d->nullOff[s + 1] - d->nullOff[s];
+      if (nE > 126 || 2 * nE + nN > 254 || nE + nN + 2 > 254) {
+        setLastError("state " + std::to_string(s) + " has too many incoming transitions for 1-byte predecessor records");
+        return DNAB_EINVAL;
+      }
+      auto& o = outs[s];
+      std::sort(o.begin(), o.end());
+      o.erase(std::unique(o.begin(), o.end()), o.end());
+      if (o.size() > 255) {
+        setLastError("state " + std::to_string(s) + " has more than 255 distinct successors");
+        return DNAB_EINVAL;
+      }
+      uint32_t w1 = 0;
+      for (uint32_t i = 0; i < d->mdl[s]; ++i) w1 |= (uint32_t)(d->ctx[(size_t)s * k + i] & 3u) << (2 * i);
+      P.blocks.push_back(nE | ((nE + nN) << 8) | ((uint32_t)o.size() << 16) | ((uint32_t)d->mdl[s] << 24));
+      P.blocks.push_back(w1);
+      auto pushIn = [&](uint32_t src, uint32_t sym, uint32_t base) {
+        const uint32_t sg = P.newOf[src], sr = sg / M;
+        P.blocks.push_back(((sg % M) * 8) | (sr << 20) | (sr != rank ? kEdgeRemote : 0u));
+        P.blocks.push_back((sym * 8) | ((sym * 128 + base * 32) << 8));
+      };
+      for (uint32_t e = d->emitOff[s]; e < d->emitOff[s + 1]; ++e) pushIn(d->emitSrc[e], d->emitSym[e], d->emitBase[e]);
+      for (uint32_t e = d->nullOff[s]; e < d->nullOff[s + 1]; ++e) pushIn(d->nullSrc[e], d->nullSym[e], 0);
+      for (uint32_t dg : o) P.blocks.push_back((dg % M) | ((dg / M) << 20) | (dg / M != rank ? kEdgeRemote : 0u));
+    }
+    if (P.blocks.size() & 1) P.blocks.push_back(0);
+    if ((g + 1) % M == 0) {
+      P.sliceOff[rank + 1] = (uint32_t)P.blocks.size();
+      P.maxSliceWords = std::max(P.maxSliceWords, P.sliceOff[rank + 1] - P.sliceOff[rank]);
+    }
+  }
+  return DNAB_OK;
+}
+
 static int buildPlan(dnab_decoder* d, int32_t maxLen) {
   if (d->plan.maxLen >= maxLen && d->plan.C) return DNAB_OK;
   const uint32_t N = d->nStates, k = d->k;
   const int32_t planLen = std::max(maxLen, 1024);
+  // Preference: the smallest cluster that holds the three live columns; within it, keep the T
+  // columns and the CTA's slice of the transition table in shared memory when they fit too.
   LaunchPlan best;
+  Partition P;
   const uint32_t cands[] = {1, 2, 4, 8, 16};
   for (uint32_t C : cands) {
     if (d->wantC && C != d->wantC) continue;
     const uint32_t M = (N + C - 1) / C;
-    if (M > 65535) continue;  // 16-bit worklist entries
-    for (uint32_t tIn = 1; tIn + 1 > 0; --tIn) {  // 1 then 0
-      if (d->wantTMode == 1 && !tIn) break;
+    if (M > 65535) continue;  // 16-bit local indices in the out-edge words
+    if (makeLayout(M, k, 0, 0, (uint32_t)planLen).total > d->smemOptin) continue;
+    int rc = buildPartition(d, C, P);
+    if (rc != DNAB_OK) return rc;
+    // options in order of preference: (T,blocks) in smem, blocks only, T only, neither
+    const uint32_t opts[4][2] = {{1, 1}, {0, 1}, {1, 0}, {0, 0}};
+    for (const auto& o : opts) {
+      const uint32_t tIn = (k == 0) ? 0 : o[0], bIn = o[1];
+      if (d->wantTMode == 1 && k && !tIn) continue;
       if (d->wantTMode == 2 && tIn) continue;
-      if (k == 0 && !tIn) break;
-      const uint32_t smem = fillSmemBytes(M, k, tIn, (uint32_t)planLen);
+      if (d->wantBlockMode == 1 && !bIn) continue;
+      if (d->wantBlockMode == 2 && bIn) continue;
+      const uint32_t smem = makeLayout(M, k, tIn, bIn ? P.maxSliceWords : 0, (uint32_t)planLen).total;
       if (smem <= d->smemOptin) {
         best.C = C;
         best.M = M;
         best.tInSmem = tIn;
+        best.blocksInSmem = bIn;
         best.smemBytes = smem;
         break;
       }
-      if (!tIn) break;
     }
     if (best.C) break;
   }
   if (!best.C) {
-    setLastError("machine does not fit: " + std::to_string(N) + " states need more shared memory than a 16-CTA cluster has");
+    setLastError("machine does not fit: " + std::to_string(N) +
+                 " states need more shared memory than a 16-CTA cluster has (or the requested configuration is infeasible)");
     return DNAB_EINVAL;
   }
   uint32_t threads = d->wantThreads ? d->wantThreads : std::min<uint32_t>(512, std::max<uint32_t>(128, (best.M + 31) / 32 * 32));
   threads = std::min<uint32_t>(1024, (threads + 31) / 32 * 32);
   best.threads = threads;
   best.maxLen = planLen;
+  best.sliceWords = P.maxSliceWords;
 
-  // ---- device tables for this partition -------------------------------------------------
-  const uint32_t C = best.C, M = best.M, Np = C * M;
-  auto rankOf = [M](uint32_t g) { return g / M; };
-  auto localOf = [M](uint32_t g) { return g % M; };
-  std::vector<uint32_t> origId(Np, 0xFFFFFFFFu);
-  std::vector<std::vector<uint32_t>> ins(Np), outs(Np);
-  std::vector<uint32_t> hdr0(Np, 0), hdr1(Np, 0);
-  for (uint32_t g = 0; g < N; ++g) {
-    origId[g] = g;  // identity permutation
-    const uint32_t nE = d->emitOff[g + 1] - d->emitOff[g], nN = d->nullOff[g + 1] - d->nullOff[g];
-    if (nE > 126 || 2 * nE + nN > 254 || nE + nN + 2 > 254) {
-      setLastError("state " + std::to_string(g) + " has too many incoming transitions for 1-byte predecessor records");
-      return DNAB_EINVAL;
-    }
-    for (uint32_t e = d->emitOff[g]; e < d->emitOff[g + 1]; ++e) {
-      const uint32_t s = d->emitSrc[e];
-      ins[g].push_back(packEdge(localOf(s), rankOf(s), d->emitSym[e], d->emitBase[e]));
-      outs[s].push_back(g);
-    }
-    for (uint32_t e = d->nullOff[g]; e < d->nullOff[g + 1]; ++e) {
-      const uint32_t s = d->nullSrc[e];
-      ins[g].push_back(packEdge(localOf(s), rankOf(s), d->nullSym[e], 0));
-      outs[s].push_back(g);
-    }
-    hdr0[g] = nE | (nN << 8) | ((uint32_t)d->mdl[g] << 24);
-    for (uint32_t i = 0; i < d->mdl[g]; ++i) hdr1[g] |= (uint32_t)(d->ctx[(size_t)g * k + i] & 3u) << (2 * i);
-  }
-  std::vector<uint32_t> blocks, blockOff(Np, 0);
-  for (uint32_t g = 0; g < Np; ++g) {
-    auto& o = outs[g];
-    std::sort(o.begin(), o.end());
-    o.erase(std::unique(o.begin(), o.end()), o.end());
-    if (o.size() > 255) {
-      setLastError("state " + std::to_string(g) + " has more than 255 distinct successors");
-      return DNAB_EINVAL;
-    }
-    blockOff[g] = (uint32_t)blocks.size();
-    blocks.push_back(hdr0[g] | ((uint32_t)o.size() << 16));
-    blocks.push_back(hdr1[g]);
-    blocks.insert(blocks.end(), ins[g].begin(), ins[g].end());
-    for (uint32_t dest : o) blocks.push_back(packEdge(localOf(dest), rankOf(dest), 0, 0));
-    while (blocks.size() % kBlockWords) blocks.push_back(0);
-  }
-  for (uint32_t j = 0; j < kBlockWords; ++j) blocks.push_back(0);  // the 32-byte prefetch never runs off the end
-  CUDA_TRY(d->dBlocks.upload(blocks));
-  CUDA_TRY(d->dBlockOff.upload(blockOff));
-  CUDA_TRY(d->dOrigId.upload(origId));
+  const uint32_t C = best.C, M = best.M;
+  P.blocks.resize(P.blocks.size() + 8, 0);
+  CUDA_TRY(d->dBlocks.upload(P.blocks));
+  CUDA_TRY(d->dBlockOff.upload(P.blockOff));
+  CUDA_TRY(d->dSliceOff.upload(P.sliceOff));
+  CUDA_TRY(d->dOrigId.upload(P.origOf));
   CUDA_TRY(d->dSymChar.upload(d->symChar));
 
   DevTables& t = d->dev;
@@ -190,11 +296,13 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
   t.k = k;
   t.local = d->local;
   t.nSyms = (uint32_t)d->symChar.size();
-  t.startG = 0;
-  t.endG = N - 1;
+  t.startG = P.newOf[0];
+  t.endG = P.newOf[N - 1];
   t.tInSmem = best.tInSmem;
+  t.blocksInSmem = best.blocksInSmem;
   t.blocks = d->dBlocks.p;
   t.blockOff = d->dBlockOff.p;
+  t.sliceOff = d->dSliceOff.p;
   t.origId = d->dOrigId.p;
   t.symChar = d->dSymChar.p;
   for (int i = 0; i < kMaxSyms; ++i) t.symScore[i] = i < (int)d->symScore.size() ? d->symScore[i] : 0.;
@@ -213,7 +321,7 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
     return DNAB_ECUDA;
   }
   best.nClusters = (uint32_t)nClusters;
-  if (!best.tInSmem) CUDA_TRY(d->dTScratch.ensure((size_t)nClusters * C * k * M));
+  if (!best.tInSmem && k) CUDA_TRY(d->dTScratch.ensure((size_t)nClusters * C * k * M));
   d->plan = best;
   return DNAB_OK;
 }
@@ -245,7 +353,8 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
   for (int64_t at = 0; at < nReads; at += chunk) {
     const int64_t n = std::min(chunk, nReads - at);
     FillArgs fa{};
-    fa.lay = makeLayout(d->plan.M, d->k, d->plan.tInSmem, (uint32_t)d->plan.maxLen);
+    fa.lay = makeLayout(d->plan.M, d->k, d->plan.tInSmem, d->plan.blocksInSmem ? d->plan.sliceWords : 0,
+                        (uint32_t)d->plan.maxLen);
     fa.nReads = n;
     fa.maxLen = maxLen;
     fa.packed = dPacked;
@@ -414,6 +523,14 @@ int dnab_decoder_configure(dnab_decoder* d, uint32_t cluster_size, uint32_t thre
   return DNAB_OK;
 }
 
+int dnab_decoder_configure_ex(dnab_decoder* d, uint32_t block_table_mode, uint32_t partition_mode) {
+  if (!d) return DNAB_EINVAL;
+  d->wantBlockMode = block_table_mode;
+  d->wantPartition = partition_mode;
+  d->plan = LaunchPlan();
+  return DNAB_OK;
+}
+
 int dnab_decoder_get_info(const dnab_decoder* dc, dnab_decoder_info* info) {
   if (!dc || !info) return DNAB_EINVAL;
   auto* d = const_cast<dnab_decoder*>(dc);
@@ -428,6 +545,7 @@ int dnab_decoder_get_info(const dnab_decoder* dc, dnab_decoder_info* info) {
   info->threads_per_cta = d->plan.threads;
   info->smem_bytes_per_cta = d->plan.smemBytes;
   info->t_in_smem = d->plan.tInSmem;
+  info->table_in_smem = d->plan.blocksInSmem;
   info->n_clusters = d->plan.nClusters;
   info->sm_count = (uint32_t)d->smCount;
   return DNAB_OK;

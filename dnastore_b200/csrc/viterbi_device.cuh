@@ -9,33 +9,39 @@ constexpr int kMaxSyms = 32;     // distinct input symbols incl. the "no input" 
 constexpr int kMaxK = 6;         // duplication depth supported by the packed state block (-l <= 13)
 constexpr int kMaxCluster = 16;
 constexpr uint32_t kNoPred = 255;  // predecessor record: "no candidate"
-constexpr uint32_t kBlockWords = 8;  // state blocks are padded to 32 bytes (one L2 sector)
 
-// Packed edge word: the OTHER endpoint = (rank, local index) in the cluster partition.
-//   bits  0..19  local index of that state inside its CTA's slice
-//   bits 20..23  cluster rank of the CTA owning it
-//   bits 24..28  input-symbol id (0 = no input symbol, score 0)   [incoming edges]
-//   bits 29..30  emitted base                                     [incoming emit edges]
-__host__ __device__ inline uint32_t edgeLocal(uint32_t w) { return w & 0xFFFFFu; }
-__host__ __device__ inline uint32_t edgeRank(uint32_t w) { return (w >> 20) & 0xFu; }
-__host__ __device__ inline uint32_t edgeSym(uint32_t w) { return (w >> 24) & 0x1Fu; }
-__host__ __device__ inline uint32_t edgeBase(uint32_t w) { return (w >> 29) & 0x3u; }
-__host__ __device__ inline uint32_t packEdge(uint32_t local, uint32_t rank, uint32_t sym, uint32_t base) {
-  return local | (rank << 20) | (sym << 24) | (base << 29);
-}
-
-// State block (32-byte aligned run of 32-bit words in `blocks`, found through blockOff):
-//   word 0   nEmit | nNull<<8 | nOut<<16 | mdl<<24
+// ---------------------------------------------------------------------------
+// State blocks.  The padded state space (Np = C*M states; state g lives in CTA
+// rank g/M at local index g%M) is described by one block of 32-bit words per state,
+// 8-byte aligned, found through blockOff[g]:
+//
+//   word 0   nEmit | nIn<<8 | nOut<<16 | mdl<<24        (nIn = nEmit + nNull)
 //   word 1   ctx: 2 bits per duplication index i = tanDupBase(ss,i)
-//   then     nEmit incoming emit edges, nNull incoming null edges -- each group in the
-//            reference's list order (source index, transition index) --
-//   then     nOut outgoing edges (destinations to wake when this state's cells grow)
-// One sector fetch brings the header and the first six edge words.
+//   then     nIn incoming edges, TWO words each, emit edges first, each group in the
+//            reference's list order (source index, transition index):
+//              a: bits 0..19  byte offset of the source's cell inside a column (local*8)
+//                 bits 20..23 cluster rank of the CTA owning the source
+//                 bit  24     set when that CTA is not the block's own CTA
+//              b: bits 0..7   sym*8            (byte offset into the per-symbol score tables)
+//                 bits 8..20  sym*128+base*32  (byte offset of the (sym,base) row of the
+//                                               traceback emit table; bits 13..14 = base)
+//   then     nOut outgoing edges, one word each (states to wake when this one grows):
+//              bits 0..15 local index, bits 20..23 rank, bit 24 "other CTA"
+//   padding to an even number of words.
+// Everything the inner loops need is pre-shifted so that an edge costs two ANDs.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kEdgeRemote = 1u << 24;
 __host__ __device__ inline uint32_t hdrNEmit(uint32_t w0) { return w0 & 0xFFu; }
-__host__ __device__ inline uint32_t hdrNNull(uint32_t w0) { return (w0 >> 8) & 0xFFu; }
+__host__ __device__ inline uint32_t hdrNIn(uint32_t w0) { return (w0 >> 8) & 0xFFu; }
 __host__ __device__ inline uint32_t hdrNOut(uint32_t w0) { return (w0 >> 16) & 0xFFu; }
 __host__ __device__ inline uint32_t hdrMdl(uint32_t w0) { return (w0 >> 24) & 0xFu; }
 __host__ __device__ inline uint32_t hdrCtx(uint32_t w1, uint32_t i) { return (w1 >> (2 * i)) & 0x3u; }
+__host__ __device__ inline uint32_t edgeOff(uint32_t a) { return a & 0xFFFFFu; }
+__host__ __device__ inline uint32_t edgeRank(uint32_t a) { return (a >> 20) & 0xFu; }
+__host__ __device__ inline uint32_t edgeSymOff(uint32_t b) { return b & 0xFFu; }
+__host__ __device__ inline uint32_t edgeTsEOff(uint32_t b) { return (b >> 8) & 0x1FFFu; }
+__host__ __device__ inline uint32_t edgeSubOff(uint32_t b) { return (b >> 8) & 0x60u; }  // base*32
+__host__ __device__ inline uint32_t outLocal(uint32_t w) { return w & 0xFFFFu; }
 
 struct DevTables {
   uint32_t nStates;   // real states
@@ -47,8 +53,10 @@ struct DevTables {
   uint32_t startG;    // padded-space index of reference state 0
   uint32_t endG;      // padded-space index of the reference's last state
   uint32_t tInSmem;   // T columns in shared memory (else in global scratch)
-  const uint32_t* blocks;     // state blocks
-  const uint32_t* blockOff;   // [Np] word offset of each state's block (multiple of kBlockWords)
+  uint32_t blocksInSmem;  // every CTA keeps its slice of the state blocks in shared memory
+  const uint32_t* blocks;     // state blocks; the blocks of one CTA's slice are contiguous
+  const uint32_t* blockOff;   // [Np] word offset of each state's block
+  const uint32_t* sliceOff;   // [C+1] word offset where each rank's slice of `blocks` begins
   const uint32_t* origId;     // [Np] reference state index, 0xFFFFFFFF for padding
   const uint8_t* symChar;     // [nSyms] input-symbol character of each id
   double symScore[kMaxSyms];  // log(symProb) per id (0 for id 0)

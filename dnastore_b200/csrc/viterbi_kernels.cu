@@ -4,25 +4,26 @@
 // (reference src/viterbi.cpp:62-176 and :195-304) for a BATCH of reads; how they
 // compute it is B200-native:
 //
-//  * One thread-block CLUSTER per read.  The state space is cut into C contiguous
-//    slices; CTA `rank` keeps its slice of the three live fp64 columns -- S(pos-1),
-//    S(pos), D(pos) -- and (when they fit) the k duplication columns T in its own
-//    shared memory.  A transition whose source lives in another CTA is read through
-//    distributed shared memory (mapa + ld.shared::cluster), never through HBM.
+//  * One thread-block CLUSTER per read.  The state space is cut into C slices (the host
+//    picks a locality-preserving partition); CTA `rank` keeps its slice of the three live
+//    fp64 columns -- S(pos-1), S(pos), D(pos) -- and, when they fit, the k duplication
+//    columns T and its slice of the transition table in its own shared memory.  A
+//    transition whose source lives in another CTA is read through distributed shared
+//    memory (mapa + ld.shared::cluster), never through HBM.
 //  * Per column: (1) emission step from the previous column; (2) the within-column
 //    closure over null transitions and deletions as a frontier-driven, pull-style
 //    chaotic relaxation -- the system is monotone, so ANY schedule reaches the same
-//    least fixed point bit for bit; races are benign (values only
-//    grow towards the fixed point) and are made well-defined with relaxed
-//    cluster-scope accesses; (3) one predecessor byte per DP cell, evaluated with
-//    the TRACEBACK's own floating-point association and candidate order
-//    (src/viterbi.cpp:251-286) on the converged column, streamed to HBM with
-//    coalesced byte-plane stores; (4) duplication opens.
-//  * A second kernel walks the predecessor bytes on the device, one thread per
-//    read, and emits the decoded input-symbol string, log-likelihood and status.
+//    least fixed point bit for bit; races are benign (values only grow
+//    towards the fixed point) and use volatile / relaxed cluster-scope accesses;
+//    (3) one predecessor byte per DP cell, evaluated with the TRACEBACK's own
+//    floating-point association and candidate order (src/viterbi.cpp:251-286) on the
+//    converged column, streamed to HBM with coalesced byte-plane stores;
+//    (4) duplication opens.
+//  * A second kernel walks the predecessor bytes on the device, one thread per read,
+//    and emits the decoded input-symbol string, log-likelihood and status.
 //
-// Only fp64 add / compare / select are used on the device; every score is computed
-// on the host with the reference's libm calls (include/dnab_tables.h).
+// Only fp64 add / compare / select are used on the device; every score is computed on
+// the host with the reference's libm calls (include/dnab_tables.h).
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
@@ -35,37 +36,62 @@ namespace cg = cooperative_groups;
 namespace dnab {
 
 // ---------------------------------------------------------------------------
-// small PTX helpers
+// PTX helpers.  Shared memory is addressed with 32-bit shared-window addresses so
+// that local accesses are plain LDS/STS; peers are reached through mapa.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// score tables: constant after set-up and always addressed through data loaded after the set-up
+// barrier, so these may be plain (reorderable, CSE-able) loads.  Never use for DP cells.
+__device__ __forceinline__ double ldsTab(uint32_t a) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 ldsV2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+// DP cells of this CTA: volatile so that every relaxation re-reads them
+__device__ __forceinline__ double ldsCell(uint32_t a) {
+  double v;
+  asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void stsCell(uint32_t a, double v) {
+  asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void stsU8(uint32_t a, uint32_t v) {
+  asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// DP cells of a peer CTA
 __device__ __forceinline__ uint32_t mapToRank(uint32_t localAddr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(localAddr), "r"(rank));
   return r;
 }
-// plain (weak) DSMEM load: used where the column being read is final
-__device__ __forceinline__ double ldClusterF64(uint32_t addr) {
+__device__ __forceinline__ double ldPeerFinal(uint32_t localAddr, uint32_t rank) {  // column is final
   double v;
-  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(mapToRank(localAddr, rank)));
   return v;
 }
-// relaxed cluster-scope accesses: used inside the closure where other CTAs may be
-// raising the same cells concurrently
-__device__ __forceinline__ double ldRelaxedF64(uint32_t addr) {
+__device__ __forceinline__ double ldPeerRacing(uint32_t localAddr, uint32_t rank) {  // inside the closure
   double v;
-  asm volatile("ld.relaxed.cluster.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  asm volatile("ld.relaxed.cluster.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(mapToRank(localAddr, rank)));
   return v;
-}
-__device__ __forceinline__ void stRelaxedF64(uint32_t addr, double v) {
-  asm volatile("st.relaxed.cluster.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 // flag / control stores into a peer: made visible by the next cluster barrier
-__device__ __forceinline__ void stClusterU8(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void stPeerU8(uint32_t localAddr, uint32_t rank, uint32_t v) {
+  asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(mapToRank(localAddr, rank)), "r"(v) : "memory");
 }
-__device__ __forceinline__ void stClusterU32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void stPeerU32(uint32_t localAddr, uint32_t rank, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapToRank(localAddr, rank)), "r"(v) : "memory");
 }
 
 // std::max(a,b) of the reference: keeps a on ties, no NaN handling needed
@@ -74,119 +100,103 @@ __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b 
 __device__ __forceinline__ double negInf() { return __longlong_as_double(0xFFF0000000000000LL); }
 
 // ---------------------------------------------------------------------------
-// shared-memory carve-up (identical in every CTA of a cluster, which is what lets
-// a local offset be mapped into a peer with mapa)
-// ---------------------------------------------------------------------------
-uint32_t fillSmemBytes(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t maxLen) {
-  return makeLayout(M, k, tInSmem, maxLen).total;
-}
-
-// ---------------------------------------------------------------------------
-// fill kernel
+// per-CTA context: shared-window addresses of everything the inner loops touch
 // ---------------------------------------------------------------------------
 struct Cta {
-  const DevTables* tb;
-  unsigned char* smem;
-  uint32_t smemBase;  // shared-window address of smem[0]
-  const SmemLayout* layp;  // lives in the kernel parameter (constant) space
+  uint32_t aD, aBoff, aSym, aExt, aOpen, aSub, aTsE;
   uint32_t rank, M, tid, nThreads;
-  const double* symScore;
-  const uint32_t* boff;
+  double noGap, delOpen, delExtend, delEnd;
 };
 
-// The first eight words of a state block in registers (one 32-byte sector).
-struct BlockRegs {
-  uint32_t w0, w1, e0, e1, e2, e3, e4, e5;
-  const uint32_t* p;
+// The CTA's slice of the state blocks: in shared memory (kBS) or in global memory behind L1/L2.
+template <bool kBS>
+struct Blocks {
+  uint32_t aBase;         // shared address of the slice (kBS)
+  const uint32_t* gBase;  // global address of the slice (!kBS)
+  __device__ __forceinline__ uint2 ld2(uint32_t wordOff) const {
+    if (kBS) return ldsV2(aBase + wordOff * 4);
+    return __ldg(reinterpret_cast<const uint2*>(gBase + wordOff));
+  }
+  __device__ __forceinline__ uint32_t ld1(uint32_t wordOff) const {
+    if (kBS) return lds32(aBase + wordOff * 4);
+    return __ldg(gBase + wordOff);
+  }
 };
-__device__ __forceinline__ BlockRegs loadBlock(const Cta& c, uint32_t i) {
-  BlockRegs b;
-  b.p = c.tb->blocks + c.boff[i];
-  const uint4 a = __ldg(reinterpret_cast<const uint4*>(b.p));
-  const uint4 d = __ldg(reinterpret_cast<const uint4*>(b.p) + 1);
-  b.w0 = a.x; b.w1 = a.y; b.e0 = a.z; b.e1 = a.w;
-  b.e2 = d.x; b.e3 = d.y; b.e4 = d.z; b.e5 = d.w;
-  return b;
-}
-// Edge words [base, base+4) of a block: from registers for the first chunk, else from L1/L2.
-__device__ __forceinline__ void chunkWords(const BlockRegs& b, uint32_t base, uint32_t n, uint32_t (&w)[4]) {
-  if (base == 0) {
-    w[0] = b.e0; w[1] = b.e1; w[2] = b.e2; w[3] = b.e3;
-  } else {
-#pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) w[j] = (base + j < n) ? __ldg(b.p + 2 + base + j) : 0u;
-  }
-}
 
-// Wake every successor of local state i (its cells grew). Returns true if a peer CTA was marked.
-// bit 0 of the result: a state of this CTA was woken; bit 1: a peer CTA was woken.
-__device__ __forceinline__ uint32_t wakeSuccessors(const Cta& c, const BlockRegs& b, uint32_t nIn, uint32_t nOut,
-                                                   uint32_t localBuf, uint32_t remoteBuf) {
-  uint32_t sent = 0;
-  for (uint32_t j = 0; j < nOut; ++j) {
-    const uint32_t idx = 2 + nIn + j;
-    const uint32_t w = idx == 2 ? b.e0 : idx == 3 ? b.e1 : idx == 4 ? b.e2 : idx == 5 ? b.e3 : idx == 6 ? b.e4
-                     : idx == 7 ? b.e5 : __ldg(b.p + idx);
-    const uint32_t r = edgeRank(w), l = edgeLocal(w);
-    if (r == c.rank) {
-      c.smem[c.layp->flagLocal[localBuf] + l] = 1;
-      sent |= 1u;
-    } else {
-      stClusterU8(mapToRank(c.smemBase + c.layp->flagRemote[remoteBuf] + l, r), 1u);
-      sent |= 2u;
-    }
-  }
-  return sent;
+// A cell of column `aCol` (shared address of the column in THIS CTA) addressed by an edge word.
+__device__ __forceinline__ double ldEdgeFinal(uint32_t aCol, uint32_t ea) {
+  const uint32_t a = aCol + edgeOff(ea);
+  return (ea & kEdgeRemote) ? ldPeerFinal(a, edgeRank(ea)) : ldsCell(a);
+}
+__device__ __forceinline__ double ldEdgeRacing(uint32_t aCol, uint32_t ea) {
+  const uint32_t a = aCol + edgeOff(ea);
+  return (ea & kEdgeRemote) ? ldPeerRacing(a, edgeRank(ea)) : ldsCell(a);
 }
 
 // One relaxation of local state i (pull form of src/viterbi.cpp:118-158):
 //   D(d) = max( D(d), max_emit-in ( max(D(s)+delExtend, S(s)+delOpen) + score ), max_null-in ( D(s)+score ) )
 //   S(d) = max( S(d), max_null-in ( S(s)+score ), D(d)+delEnd )
 // where the stored S(s) already contains D(s)+delEnd from s's own last relaxation.
-// When a cell grew, every successor is woken (result: see wakeSuccessors).
-__device__ __forceinline__ uint32_t relaxState(const Cta& c, uint32_t i, uint32_t sCurOff, uint32_t localBuf,
-                                               uint32_t remoteBuf) {
-  const DevTables& tb = *c.tb;
-  const BlockRegs b = loadBlock(c, i);
-  const uint32_t nE = hdrNEmit(b.w0), nN = hdrNNull(b.w0), nIn = nE + nN;
-  const uint32_t myS = c.smemBase + sCurOff + i * 8, myD = c.smemBase + c.layp->dBuf + i * 8;
-  const double oldS = ldRelaxedF64(myS), oldD = ldRelaxedF64(myD);
+// When a cell grew every successor is woken: flag byte in the local buffer at aFlagLocal, or in
+// the remote buffer at aFlagRemote of the peer that owns it.  Result bit 0: woke a state of this CTA;
+// bit 1: woke a peer.
+template <bool kBS>
+__device__ __forceinline__ uint32_t relaxState(const Cta& c, const Blocks<kBS>& blk, uint32_t i, uint32_t aSc,
+                                               uint32_t aFlagLocal, uint32_t aFlagRemote) {
+  const uint32_t off = lds32(c.aBoff + 4 * i);
+  const uint2 h = blk.ld2(off);
+  const uint32_t nE = hdrNEmit(h.x), nIn = hdrNIn(h.x);
+  const uint32_t myS = aSc + 8 * i, myD = c.aD + 8 * i;
+  const double oldS = ldsCell(myS), oldD = ldsCell(myD);
   double newS = oldS, newD = oldD;
-  const uint32_t dMinusS = c.layp->dBuf - sCurOff;
-  for (uint32_t base = 0; base < nIn; base += 4) {
-    uint32_t w[4];
-    chunkWords(b, base, nIn, w);
-    double ss[4], ds[4];
-#pragma unroll
-    for (uint32_t j = 0; j < 4; ++j)
-      if (base + j < nIn) {  // issue every load of the chunk before the first use
-        const uint32_t aS = mapToRank(c.smemBase + sCurOff + edgeLocal(w[j]) * 8, edgeRank(w[j]));
-        ss[j] = ldRelaxedF64(aS);
-        ds[j] = ldRelaxedF64(aS + dMinusS);
+  for (uint32_t j = 0; j < nIn; j += 2) {
+    const bool two = j + 1 < nIn;
+    const uint2 e0 = blk.ld2(off + 2 + 2 * j);
+    const uint2 e1 = two ? blk.ld2(off + 4 + 2 * j) : e0;
+    // issue every load of the pair before the first use
+    const double ss0 = ldEdgeRacing(aSc, e0.x), ds0 = ldEdgeRacing(c.aD, e0.x);
+    double ss1 = ss0, ds1 = ds0;
+    if (two) {
+      ss1 = ldEdgeRacing(aSc, e1.x);
+      ds1 = ldEdgeRacing(c.aD, e1.x);
+    }
+    const double sc0 = ldsTab(c.aSym + edgeSymOff(e0.y)), sc1 = ldsTab(c.aSym + edgeSymOff(e1.y));
+    if (j < nE) {
+      newD = dmax(newD, dmax(ds0 + c.delExtend, ss0 + c.delOpen) + sc0);
+    } else {
+      newD = dmax(newD, ds0 + sc0);
+      newS = dmax(newS, ss0 + sc0);
+    }
+    if (two) {
+      if (j + 1 < nE) {
+        newD = dmax(newD, dmax(ds1 + c.delExtend, ss1 + c.delOpen) + sc1);
+      } else {
+        newD = dmax(newD, ds1 + sc1);
+        newS = dmax(newS, ss1 + sc1);
       }
-#pragma unroll
-    for (uint32_t j = 0; j < 4; ++j)
-      if (base + j < nIn) {
-        const double sc = c.symScore[edgeSym(w[j])];
-        if (base + j < nE) {
-          newD = dmax(newD, dmax(ds[j] + tb.delExtend, ss[j] + tb.delOpen) + sc);
-        } else {
-          newD = dmax(newD, ds[j] + sc);
-          newS = dmax(newS, ss[j] + sc);
-        }
-      }
+    }
   }
-  newS = dmax(newS, newD + tb.delEnd);
-  uint32_t sent = 0;
+  newS = dmax(newS, newD + c.delEnd);
+  uint32_t woke = 0;
   if ((newD > oldD) || (newS > oldS)) {
-    if (newD > oldD) stRelaxedF64(myD, newD);
-    if (newS > oldS) stRelaxedF64(myS, newS);
-    sent = wakeSuccessors(c, b, nIn, hdrNOut(b.w0), localBuf, remoteBuf);
+    if (newD > oldD) stsCell(myD, newD);
+    if (newS > oldS) stsCell(myS, newS);
+    const uint32_t nOut = hdrNOut(h.x), o0 = off + 2 + 2 * nIn;
+    for (uint32_t j = 0; j < nOut; ++j) {
+      const uint32_t w = blk.ld1(o0 + j);
+      if (w & kEdgeRemote) {
+        stPeerU8(aFlagRemote + outLocal(w), edgeRank(w), 1u);
+        woke |= 2u;
+      } else {
+        stsU8(aFlagLocal + outLocal(w), 1u);
+        woke |= 1u;
+      }
+    }
   }
-  return sent;
+  return woke;
 }
 
-template <int kMaxThreads, int kMinBlocks>
+template <int kMaxThreads, int kMinBlocks, bool kBS>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
     viterbiFillKernel(const __grid_constant__ DevTables tb, const __grid_constant__ FillArgs args) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -198,17 +208,30 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   const uint32_t tid = threadIdx.x, nThreads = blockDim.x;
   const uint32_t Np = C * M;
   const double NEG = negInf();
+  const SmemLayout& lay = args.lay;
+  const uint32_t sm = smemAddr(smem);
 
   Cta c;
-  c.tb = &tb;
-  c.smem = smem;
-  c.smemBase = smemAddr(smem);
-  c.layp = &args.lay;
+  c.aD = sm + lay.dBuf;
+  c.aBoff = sm + lay.boff;
+  c.aSym = sm + lay.symScore;
+  c.aExt = sm + lay.tsDext;
+  c.aOpen = sm + lay.tsDopen;
+  c.aSub = sm + lay.sub;
+  c.aTsE = sm + lay.tsE;
   c.rank = rank;
   c.M = M;
   c.tid = tid;
   c.nThreads = nThreads;
-  const SmemLayout& lay = args.lay;
+  c.noGap = tb.noGap;
+  c.delOpen = tb.delOpen;
+  c.delExtend = tb.delExtend;
+  c.delEnd = tb.delEnd;
+
+  const uint32_t sliceBegin = __ldg(&tb.sliceOff[rank]), sliceEnd = __ldg(&tb.sliceOff[rank + 1]);
+  Blocks<kBS> blk;
+  blk.aBase = sm + lay.blocks;
+  blk.gBase = tb.blocks + sliceBegin;
 
   double* symScore = reinterpret_cast<double*>(smem + lay.symScore);
   double* tsE = reinterpret_cast<double*>(smem + lay.tsE);
@@ -220,11 +243,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   volatile uint32_t* ctl = reinterpret_cast<volatile uint32_t*>(smem + lay.ctl);
   uint32_t* boff = reinterpret_cast<uint32_t*>(smem + lay.boff);
   uint8_t* seqS = smem + lay.seq;
-  double* dCol = reinterpret_cast<double*>(smem + lay.dBuf);
   double* tCol = tb.tInSmem ? reinterpret_cast<double*>(smem + lay.tBuf)
                             : args.tScratch + ((size_t)clusterId * C + rank) * (size_t)k * M;
-  c.symScore = symScore;
-  c.boff = boff;
 
   // read-independent tables; the traceback-association sums are formed here once
   for (uint32_t s = tid; s < kMaxSyms; s += nThreads) {
@@ -245,7 +265,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
     }
   };
   buildTsE();
-  for (uint32_t i = tid; i < M; i += nThreads) boff[i] = __ldg(&tb.blockOff[rank * M + i]);
+  for (uint32_t i = tid; i < M; i += nThreads) boff[i] = __ldg(&tb.blockOff[rank * M + i]) - sliceBegin;
+  if (kBS) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + lay.blocks);
+    for (uint32_t j = tid; j < sliceEnd - sliceBegin; j += nThreads) dst[j] = __ldg(tb.blocks + sliceBegin + j);
+  }
   for (uint32_t j = tid; j < 64; j += nThreads) ctl[j] = 0;
   {
     uint32_t* fl = reinterpret_cast<uint32_t*>(smem + lay.flagLocal[0]);
@@ -262,7 +286,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   };
   clusterBarrier();  // every CTA's flags are clear before a peer can set them
 
-  unsigned long long dbgDense = 0, dbgSyncWait = 0, dbgCompact = 0, dbgProc = 0, dbgClusterWait = 0;
+  unsigned long long dbgDense = 0, dbgClusterWait = 0;
   unsigned long long dbgRounds = 0, dbgIters = 0, dbgT1 = 0, dbgT2 = 0, dbgT3 = 0, dbgCols = 0, dbgWork = 0;
   const bool dbgOn = args.dbg != nullptr;
 
@@ -279,9 +303,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 
     for (int32_t pos = 0; pos <= L; ++pos) {
       const uint32_t cur = pos & 1, prev = cur ^ 1;
-      const uint32_t sCurOff = lay.sBuf[cur], sPrevOff = lay.sBuf[prev];
-      double* sCur = reinterpret_cast<double*>(smem + sCurOff);
+      const uint32_t aScur = sm + (cur ? lay.sBuf[1] : lay.sBuf[0]), aSprev = sm + (prev ? lay.sBuf[1] : lay.sBuf[0]);
       const uint32_t x = pos > 0 ? (seqS[(pos - 1) >> 2] >> (2 * ((pos - 1) & 3))) & 3u : 0u;
+      const uint32_t x8 = x * 8;
 
       long long tc0 = dbgOn ? clock64() : 0;
       // ---- (1) emission step: S0 from the previous column, T shift (src/viterbi.cpp:92-106) ----
@@ -293,55 +317,58 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           s = (real && (tb.local || g == tb.startG)) ? 0.0 : NEG;  // src/viterbi.cpp:75-79
           for (uint32_t j = 0; j < k; ++j) tCol[j * M + i] = NEG;
         } else {
-          const BlockRegs b = loadBlock(c, i);
-          const uint32_t nE = hdrNEmit(b.w0), mdl = hdrMdl(b.w0);
+          const uint32_t off = lds32(c.aBoff + 4 * i);
+          const uint2 h = blk.ld2(off);
+          const uint32_t nE = hdrNEmit(h.x), mdl = hdrMdl(h.x);
           double t0 = NEG;
           if (mdl > 0) t0 = tCol[i];
-          for (uint32_t base = 0; base < nE; base += 4) {
-            uint32_t w[4];
-            chunkWords(b, base, nE, w);
-            double v[4];
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j)
-              if (base + j < nE) v[j] = ldClusterF64(mapToRank(c.smemBase + sPrevOff + edgeLocal(w[j]) * 8, edgeRank(w[j])));
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j)
-              if (base + j < nE)
-                s = dmax(s, ((v[j] + symScore[edgeSym(w[j])]) + tb.noGap) + subS[edgeBase(w[j]) * 4 + x]);
+          for (uint32_t j = 0; j < nE; j += 2) {
+            const bool two = j + 1 < nE;
+            const uint2 e0 = blk.ld2(off + 2 + 2 * j);
+            const uint2 e1 = two ? blk.ld2(off + 4 + 2 * j) : e0;
+            const double v0 = ldEdgeFinal(aSprev, e0.x);
+            const double v1 = two ? ldEdgeFinal(aSprev, e1.x) : NEG;
+            const double c0 = ((v0 + ldsTab(c.aSym + edgeSymOff(e0.y))) + c.noGap) + ldsTab(c.aSub + edgeSubOff(e0.y) + x8);
+            const double c1 = ((v1 + ldsTab(c.aSym + edgeSymOff(e1.y))) + c.noGap) + ldsTab(c.aSub + edgeSubOff(e1.y) + x8);
+            s = dmax(s, c0);
+            s = dmax(s, c1);  // v1 = -inf when the pair is incomplete
           }
           if (mdl > 0) {
-            const double t2s = t0 + subS[hdrCtx(b.w1, 0) * 4 + x];
+            const double t2s = t0 + subS[hdrCtx(h.y, 0) * 4 + x];
             s = dmax(s, t2s);
-            for (uint32_t j = 0; j + 1 < mdl; ++j) tCol[j * M + i] = tCol[(j + 1) * M + i] + subS[hdrCtx(b.w1, j + 1) * 4 + x];
+            for (uint32_t j = 0; j + 1 < mdl; ++j) tCol[j * M + i] = tCol[(j + 1) * M + i] + subS[hdrCtx(h.y, j + 1) * 4 + x];
             tCol[(mdl - 1) * M + i] = t2s;  // slot mdl-1 is free until step (4): park the T->S candidate there
           }
         }
-        sCur[i] = s;
-        dCol[i] = NEG;
+        stsCell(aScur + 8 * i, s);
+        stsCell(c.aD + 8 * i, NEG);
       }
       clusterBarrier();
       long long tc1 = dbgOn ? clock64() : 0;
 
       // ---- (2) closure: null transitions + deletions (src/viterbi.cpp:110-159) ----
-      // Round 0 relaxes every state once.  Then: each CTA iterates over the states woken by its
-      // OWN states until none is left (CTA barriers only); states woken by a peer wait in the
-      // remote flag buffer of the current round and are picked up after the next cluster
+      // Round 0 relaxes every state once.  Then each CTA iterates over the states woken by its OWN
+      // states until none is left (one CTA barrier per iteration); states woken by a peer wait in
+      // the remote flag buffer of the current round and are picked up after the next cluster
       // barrier.  The cluster is done when a whole round woke nobody across CTAs.
       {
         // Every thread owns the 4-state flag words tid, tid+nThreads, ...: it relaxes the states whose
         // flag is set in the buffers being consumed and sets flags in the buffers being filled.
         const uint32_t nWords = (M + 3) / 4;
-        uint32_t round = 0, it = 0, sent = 0;
-        for (uint32_t i = tid; i < M; i += nThreads) sent |= relaxState(c, i, sCurOff, 1, 0);
+        uint32_t round = 0, it = 0, woke = 0;
+        for (uint32_t i = tid; i < M; i += nThreads)
+          woke |= relaxState<kBS>(c, blk, i, aScur, sm + lay.flagLocal[1], sm + lay.flagRemote[0]);
         if (dbgOn && tid == 0) dbgDense += clock64() - tc1;
         bool pickRemote = false;
         for (;;) {
-          // local fixed point: one CTA barrier per iteration
-          while (__syncthreads_or((int)(sent & 1u)) || pickRemote) {
+          while (__syncthreads_or((int)(woke & 1u)) || pickRemote) {
             ++it;
-            sent &= 2u;
-            uint32_t* fl = reinterpret_cast<uint32_t*>(smem + lay.flagLocal[it & 1]);
-            uint32_t* fr = reinterpret_cast<uint32_t*>(smem + lay.flagRemote[(round & 1) ^ 1]);
+            woke &= 2u;
+            const uint32_t oFlagIn = (it & 1) ? lay.flagLocal[1] : lay.flagLocal[0];
+            const uint32_t aFlagOut = sm + ((it & 1) ? lay.flagLocal[0] : lay.flagLocal[1]);
+            const uint32_t aRemoteOut = sm + ((round & 1) ? lay.flagRemote[1] : lay.flagRemote[0]);
+            uint32_t* fl = reinterpret_cast<uint32_t*>(smem + oFlagIn);
+            uint32_t* fr = reinterpret_cast<uint32_t*>(smem + ((round & 1) ? lay.flagRemote[0] : lay.flagRemote[1]));
             for (uint32_t w = tid; w < nWords; w += nThreads) {
               uint32_t f = fl[w];
               if (f) fl[w] = 0;
@@ -354,7 +381,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                 if (dbgOn) dbgWork += __popc(f & 0x01010101u);
 #pragma unroll 1
                 for (uint32_t q = 0; q < 4; ++q)
-                  if (f & (0xFFu << (8 * q))) sent |= relaxState(c, 4 * w + q, sCurOff, (it & 1) ^ 1, round & 1);
+                  if (f & (0xFFu << (8 * q))) woke |= relaxState<kBS>(c, blk, 4 * w + q, aScur, aFlagOut, aRemoteOut);
               }
             }
             pickRemote = false;
@@ -362,8 +389,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           }
           if (C == 1) break;
           long long tcb = dbgOn ? clock64() : 0;
-          const uint32_t anySent = (uint32_t)__syncthreads_or((int)(sent & 2u));
-          if (tid < C) stClusterU32(mapToRank(c.smemBase + lay.ctl + (16 + (round & 1) * kMaxCluster + rank) * 4, tid), anySent);
+          const uint32_t anyWoke = (uint32_t)__syncthreads_or((int)(woke & 2u));
+          if (tid < C) stPeerU32(sm + lay.ctl + (16 + (round & 1) * kMaxCluster + rank) * 4, tid, anyWoke);
           cluster.sync();
           if (dbgOn && tid == 0) dbgClusterWait += clock64() - tcb;
           uint32_t tot = 0;
@@ -372,7 +399,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           if (dbgOn && tid == 0) dbgRounds++;
           ++round;  // peers now fill the other remote buffer; the one just completed is picked up next
           pickRemote = true;
-          sent = 0;
+          woke = 0;
         }
       }
 
@@ -382,77 +409,51 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
       uint8_t* predCol = predRead + (size_t)pos * (k + 2) * Np;
       for (uint32_t i = tid; i < M; i += nThreads) {
         const uint32_t g = rank * M + i;
-        const BlockRegs b = loadBlock(c, i);
-        const uint32_t nE = hdrNEmit(b.w0), nN = hdrNNull(b.w0), mdl = hdrMdl(b.w0), nIn = nE + nN;
-        const double sHere = sCur[i], dHere = dCol[i];
-        const uint32_t dMinusS = lay.dBuf - sCurOff;
+        const uint32_t off = lds32(c.aBoff + 4 * i);
+        const uint2 h = blk.ld2(off);
+        const uint32_t nE = hdrNEmit(h.x), nIn = hdrNIn(h.x), mdl = hdrMdl(h.x);
+        const double sHere = ldsCell(aScur + 8 * i), dHere = ldsCell(c.aD + 8 * i);
         const double parked = (mdl > 0 && pos > 0) ? tCol[(mdl - 1) * M + i] : NEG;  // T(state,pos-1,0)+sub
 
         double best = NEG, bestD = NEG;
         uint32_t idx = kNoPred, idxD = kNoPred;
-        for (uint32_t base = 0; base < nIn; base += 2) {
-          uint32_t w[2];
-          if (base == 0) {
-            w[0] = b.e0;
-            w[1] = b.e1;
-          } else if (base == 2) {
-            w[0] = b.e2;
-            w[1] = b.e3;
-          } else if (base == 4) {
-            w[0] = b.e4;
-            w[1] = b.e5;
-          } else {
-            w[0] = __ldg(b.p + 2 + base);
-            w[1] = base + 1 < nIn ? __ldg(b.p + 3 + base) : 0u;
-          }
-          double vp[2], vs[2], vd[2];
-#pragma unroll
-          for (uint32_t j = 0; j < 2; ++j)
-            if (base + j < nIn) {
-              const uint32_t aS = mapToRank(c.smemBase + sCurOff + edgeLocal(w[j]) * 8, edgeRank(w[j]));
-              vs[j] = ldClusterF64(aS);
-              vd[j] = ldClusterF64(aS + dMinusS);
-              if (base + j < nE && pos > 0) vp[j] = ldClusterF64(aS + (sPrevOff - sCurOff));
-            }
-#pragma unroll
-          for (uint32_t j = 0; j < 2; ++j)
-            if (base + j < nIn) {
-              const uint32_t e = base + j, sym = edgeSym(w[j]);
-              if (e < nE) {
-                if (pos > 0) {
-                  const double v = vp[j] + tsE[sym * 16 + edgeBase(w[j]) * 4 + x];
-                  if (v > best) {
-                    best = v;
-                    idx = e;
-                  }
-                }
-                const double ve = vd[j] + tsDext[sym];
-                if (ve > bestD) {
-                  bestD = ve;
-                  idxD = 2 * e;
-                }
-                const double vo = vs[j] + tsDopen[sym];
-                if (vo > bestD) {
-                  bestD = vo;
-                  idxD = 2 * e + 1;
-                }
-              } else {
-                const double sc = symScore[sym];
-                const double v = vs[j] + sc;
-                if (v > best) {
-                  best = v;
-                  idx = e;
-                }
-                const double vn = vd[j] + sc;
-                if (vn > bestD) {
-                  bestD = vn;
-                  idxD = nE + e;  // = 2*nE + (e - nE)
-                }
+        for (uint32_t e = 0; e < nIn; ++e) {
+          const uint2 ew = blk.ld2(off + 2 + 2 * e);
+          const double vs = ldEdgeRacing(aScur, ew.x), vd = ldEdgeRacing(c.aD, ew.x);
+          if (e < nE) {
+            if (pos > 0) {
+              const double v = ldEdgeFinal(aSprev, ew.x) + ldsTab(c.aTsE + edgeTsEOff(ew.y) + x8);
+              if (v > best) {
+                best = v;
+                idx = e;
               }
             }
+            const double ve = vd + ldsTab(c.aExt + edgeSymOff(ew.y));
+            if (ve > bestD) {
+              bestD = ve;
+              idxD = 2 * e;
+            }
+            const double vo = vs + ldsTab(c.aOpen + edgeSymOff(ew.y));
+            if (vo > bestD) {
+              bestD = vo;
+              idxD = 2 * e + 1;
+            }
+          } else {
+            const double sc = ldsTab(c.aSym + edgeSymOff(ew.y));
+            const double v = vs + sc;
+            if (v > best) {
+              best = v;
+              idx = e;
+            }
+            const double vn = vd + sc;
+            if (vn > bestD) {
+              bestD = vn;
+              idxD = nE + e;  // = 2*nE + (e - nE)
+            }
+          }
         }
         {
-          const double v = dHere + tb.delEnd;
+          const double v = dHere + c.delEnd;
           if (v > best) {
             best = v;
             idx = nIn;
@@ -463,7 +464,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           idx = nIn + 1;
         }
         if (tb.local && pos == 0) {
-          const double v = ldClusterF64(mapToRank(c.smemBase + sCurOff + (tb.startG % M) * 8, tb.startG / M)) + 0.0;
+          const uint32_t a = aScur + (tb.startG % M) * 8, r = tb.startG / M;
+          const double v = (r == rank ? ldsCell(a) : ldPeerRacing(a, r)) + 0.0;
           if (v > best) {
             best = v;
             idx = nIn + 2;
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 
     // ---- end of read: log-likelihood and traceback start (src/viterbi.cpp:171-173, 239-245) ----
     {
-      const double* sLast = reinterpret_cast<const double*>(smem + lay.sBuf[L & 1]);
+      const double* sLast = reinterpret_cast<const double*>(smem + ((L & 1) ? lay.sBuf[1] : lay.sBuf[0]));
       if (!tb.local) {
         if (rank == tb.endG / M && tid == 0) {
           args.loglike[read] = sLast[tb.endG % M];
@@ -522,10 +524,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             bg = g;
           }
         }
-        for (int off = 16; off > 0; off >>= 1) {
-          const double ov = __shfl_down_sync(0xFFFFFFFFu, bv, off);
-          const uint32_t oo = __shfl_down_sync(0xFFFFFFFFu, bo, off);
-          const uint32_t og = __shfl_down_sync(0xFFFFFFFFu, bg, off);
+        for (int sh = 16; sh > 0; sh >>= 1) {
+          const double ov = __shfl_down_sync(0xFFFFFFFFu, bv, sh);
+          const uint32_t oo = __shfl_down_sync(0xFFFFFFFFu, bo, sh);
+          const uint32_t og = __shfl_down_sync(0xFFFFFFFFu, bg, sh);
           if (ov > bv || (ov == bv && oo < bo)) {
             bv = ov;
             bo = oo;
@@ -569,9 +571,6 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
     atomicAdd(&args.dbg[5], dbgT3);
     atomicAdd(&args.dbg[6], dbgRounds);
     atomicAdd(&args.dbg[7], dbgDense);
-    atomicAdd(&args.dbg[8], dbgSyncWait);
-    atomicAdd(&args.dbg[9], dbgCompact);
-    atomicAdd(&args.dbg[10], dbgProc);
     atomicAdd(&args.dbg[11], dbgClusterWait);
   }
   clusterBarrier();  // no CTA may exit while a peer can still read its shared memory
@@ -642,23 +641,20 @@ __global__ void viterbiTracebackKernel(const DevTables tb, const TracebackArgs a
       status = DNAB_READ_TRACEBACK_FAILED_;
       break;
     }
-    const uint32_t* blk = tb.blocks + tb.blockOff[g];
-    const uint32_t nE = hdrNEmit(blk[0]), nN = hdrNNull(blk[0]);
-    const uint32_t* edges = blk + 2;
+    const uint32_t* blkp = tb.blocks + tb.blockOff[g];
+    const uint32_t nE = hdrNEmit(blkp[0]), nIn = hdrNIn(blkp[0]);
+    const uint2* edges = reinterpret_cast<const uint2*>(blkp + 2);
+    auto srcOf = [&](uint2 e) { return edgeRank(e.x) * M + edgeOff(e.x) / 8; };
     uint32_t sym = 0;
     if (mut == 0) {
-      if (p < nE) {
-        const uint32_t w = edges[p];
-        sym = edgeSym(w);
-        g = edgeRank(w) * M + edgeLocal(w);
-        --pos;
-      } else if (p < nE + nN) {
-        const uint32_t w = edges[p];
-        sym = edgeSym(w);
-        g = edgeRank(w) * M + edgeLocal(w);
-      } else if (p == nE + nN) {
+      if (p < nIn) {  // incoming emit edge (previous column) or null edge (same column)
+        const uint2 e = edges[p];
+        sym = edgeSymOff(e.y) / 8;
+        g = srcOf(e);
+        if (p < nE) --pos;
+      } else if (p == nIn) {
         mut = 1;
-      } else if (p == nE + nN + 1) {
+      } else if (p == nIn + 1) {
         mut = 2;
         --pos;
       } else {
@@ -666,14 +662,14 @@ __global__ void viterbiTracebackKernel(const DevTables tb, const TracebackArgs a
       }
     } else if (mut == 1) {
       if (p < 2 * nE) {
-        const uint32_t w = edges[p >> 1];
-        sym = edgeSym(w);
-        g = edgeRank(w) * M + edgeLocal(w);
+        const uint2 e = edges[p >> 1];
+        sym = edgeSymOff(e.y) / 8;
+        g = srcOf(e);
         mut = (p & 1) ? 0 : 1;
       } else {
-        const uint32_t w = edges[nE + (p - 2 * nE)];
-        sym = edgeSym(w);
-        g = edgeRank(w) * M + edgeLocal(w);
+        const uint2 e = edges[p - nE];  // null edge number p-2*nE sits after the nE emit edges
+        sym = edgeSymOff(e.y) / 8;
+        g = srcOf(e);
       }
     } else {
       if (p == 0) {
@@ -701,11 +697,17 @@ __global__ void viterbiTracebackKernel(const DevTables tb, const TracebackArgs a
 // launchers
 // ---------------------------------------------------------------------------
 typedef void (*FillKernelPtr)(const DevTables, const FillArgs);
-static FillKernelPtr pickFillKernel(uint32_t threads) {
-  if (threads > 512) return viterbiFillKernel<1024, 1>;  // 64 registers/thread
-  if (threads > 256) return viterbiFillKernel<512, 1>;   // 128
-  if (threads > 128) return viterbiFillKernel<256, 2>;   // 128
-  return viterbiFillKernel<128, 4>;                      // 128
+static FillKernelPtr pickFillKernel(uint32_t threads, bool blocksInSmem) {
+  if (blocksInSmem) {
+    if (threads > 512) return viterbiFillKernel<1024, 1, true>;  // 64 registers/thread
+    if (threads > 256) return viterbiFillKernel<512, 1, true>;   // 128
+    if (threads > 128) return viterbiFillKernel<256, 2, true>;   // 128
+    return viterbiFillKernel<128, 4, true>;                      // 128
+  }
+  if (threads > 512) return viterbiFillKernel<1024, 1, false>;
+  if (threads > 256) return viterbiFillKernel<512, 1, false>;
+  if (threads > 128) return viterbiFillKernel<256, 2, false>;
+  return viterbiFillKernel<128, 4, false>;
 }
 
 static cudaError_t prepFill(FillKernelPtr kern, const DevTables& tb, uint32_t smemBytes) {
@@ -715,41 +717,39 @@ static cudaError_t prepFill(FillKernelPtr kern, const DevTables& tb, uint32_t sm
   return err;
 }
 
-cudaError_t launchFill(const DevTables& tb, const FillArgs& args, uint32_t nClusters, uint32_t threads,
-                       uint32_t smemBytes, cudaStream_t stream) {
-  FillKernelPtr kern = pickFillKernel(threads);
-  cudaError_t err = prepFill(kern, tb, smemBytes);
-  if (err != cudaSuccess) return err;
-  cudaLaunchConfig_t cfg{};
+static void clusterConfig(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, const DevTables& tb, uint32_t nClusters,
+                          uint32_t threads, uint32_t smemBytes, cudaStream_t stream) {
+  cfg = cudaLaunchConfig_t{};
   cfg.gridDim = dim3(nClusters * tb.C);
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = tb.C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+}
+
+cudaError_t launchFill(const DevTables& tb, const FillArgs& args, uint32_t nClusters, uint32_t threads,
+                       uint32_t smemBytes, cudaStream_t stream) {
+  FillKernelPtr kern = pickFillKernel(threads, tb.blocksInSmem != 0);
+  cudaError_t err = prepFill(kern, tb, smemBytes);
+  if (err != cudaSuccess) return err;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  clusterConfig(cfg, attr, tb, nClusters, threads, smemBytes, stream);
   return cudaLaunchKernelEx(&cfg, kern, tb, args);
 }
 
 cudaError_t queryMaxClusters(const DevTables& tb, uint32_t threads, uint32_t smemBytes, int* nClusters) {
-  FillKernelPtr kern = pickFillKernel(threads);
+  FillKernelPtr kern = pickFillKernel(threads, tb.blocksInSmem != 0);
   cudaError_t err = prepFill(kern, tb, smemBytes);
   if (err != cudaSuccess) return err;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(tb.C);
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smemBytes;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = tb.C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  clusterConfig(cfg, attr, tb, 1, threads, smemBytes, nullptr);
   return cudaOccupancyMaxActiveClusters(nClusters, kern, &cfg);
 }
 

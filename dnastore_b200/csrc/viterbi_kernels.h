@@ -16,13 +16,15 @@ constexpr int32_t DNAB_READ_TRACEBACK_FAILED_ = 3;
 
 // ---------------------------------------------------------------------------
 // shared-memory carve-up (identical in every CTA of a cluster, which is what lets
-// a local offset be mapped into a peer with mapa)
+// a local offset be mapped into a peer with mapa); byte offsets from the start of
+// dynamic shared memory, computed once by the host
 // ---------------------------------------------------------------------------
 struct SmemLayout {
-  uint32_t sBuf[2];    // byte offsets of the two S columns
-  uint32_t dBuf;
+  uint32_t sBuf[2];    // the two S columns (fp64 per local state)
+  uint32_t dBuf;       // the D column
   uint32_t tBuf;       // k*M doubles, only if tInSmem
-  uint32_t boff;       // [M] u32: word offset of each local state's block
+  uint32_t boff;       // [M] u32: word offset of each local state's block inside the CTA's slice
+  uint32_t blocks;     // the CTA's slice of the state blocks, only if blocksInSmem
   uint32_t tsE;        // [nSyms*16] (score+noGap)+sub  -- traceback association, src/viterbi.cpp:255
   uint32_t symScore;   // [kMaxSyms]
   uint32_t tsDext;     // [kMaxSyms] score+delExtend    -- src/viterbi.cpp:272
@@ -30,14 +32,14 @@ struct SmemLayout {
   uint32_t sub;        // [16]
   uint32_t tsT;        // [kMaxK] tanDup+len[i]         -- src/viterbi.cpp:286
   uint32_t len;        // [kMaxK]
-  uint32_t ctl;        // u32: [16..47] sent[2][kMaxCluster]
-  uint32_t flagLocal[2];   // [Mf] u8 each: woken by a state of this CTA, double-buffered by local iteration
-  uint32_t flagRemote[2];  // [Mf] u8 each: woken by a peer CTA, double-buffered by cluster round
+  uint32_t ctl;        // u32 control words: [16..47] sent[2][kMaxCluster]
+  uint32_t flagLocal[2];   // [M] u8 each: woken by a state of this CTA, double-buffered by local iteration
+  uint32_t flagRemote[2];  // [M] u8 each: woken by a peer CTA, double-buffered by cluster round
   uint32_t seq;        // packed read
   uint32_t total;
 };
 
-__host__ __device__ inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t maxLen) {
+inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t blockSliceWords, uint32_t maxLen) {
   SmemLayout L;
   uint32_t at = 0;
   auto take = [&](uint32_t bytes) {
@@ -50,6 +52,7 @@ __host__ __device__ inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_
   L.dBuf = take(M * 8);
   L.tBuf = tInSmem ? take(k * M * 8) : 0;
   L.boff = take(M * 4);
+  L.blocks = blockSliceWords ? take(blockSliceWords * 4) : 0;
   L.tsE = take(kMaxSyms * 16 * 8);
   L.symScore = take(kMaxSyms * 8);
   L.tsDext = take(kMaxSyms * 8);
@@ -68,7 +71,7 @@ __host__ __device__ inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_
 }
 
 struct FillArgs {
-  SmemLayout lay;            // makeLayout(M, k, tInSmem, maxLen), computed by the host
+  SmemLayout lay;
   int64_t nReads;
   int32_t maxLen;            // pred stride: every read owns (maxLen+1) columns of records
   const uint8_t* packed;     // 2-bit reads
@@ -104,7 +107,6 @@ struct TracebackArgs {
   int32_t* pathLen;
 };
 
-uint32_t fillSmemBytes(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t maxLen);
 cudaError_t queryMaxClusters(const DevTables& tb, uint32_t threads, uint32_t smemBytes, int* nClusters);
 cudaError_t launchFill(const DevTables& tb, const FillArgs& args, uint32_t nClusters, uint32_t threads,
                        uint32_t smemBytes, cudaStream_t stream);

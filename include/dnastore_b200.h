@@ -111,6 +111,7 @@ typedef struct dnab_decoder_info {
   uint32_t threads_per_cta;
   uint32_t smem_bytes_per_cta;
   uint32_t t_in_smem;        /* 1: duplication (T) columns live in shared memory, 0: in global scratch */
+  uint32_t table_in_smem;    /* 1: each CTA keeps its slice of the transition table in shared memory */
   uint32_t n_clusters;       /* clusters resident at once = reads in flight */
   uint32_t sm_count;
 } dnab_decoder_info;
@@ -118,6 +119,9 @@ int dnab_decoder_get_info(const dnab_decoder* d, dnab_decoder_info* info);
 
 /* Tuning overrides (0 = automatic); must be set before the first batch. */
 int dnab_decoder_configure(dnab_decoder* d, uint32_t cluster_size, uint32_t threads_per_cta, uint32_t t_in_smem_mode);
+/* block_table_mode: 0 auto, 1 transition table in shared memory, 2 in global memory;
+ * partition_mode: 0 locality-preserving (DFS) partition + in-degree sort, 1 index order + sort, 2 DFS, no sort. */
+int dnab_decoder_configure_ex(dnab_decoder* d, uint32_t block_table_mode, uint32_t partition_mode);
 
 /* Reads are packed 2 bits per base, A,C,G,T = 0..3 (src/kmer.h:11-13, src/fastseq.cpp:9-15),
  * base i of a read in bits 2*(i%4).. of byte i/4; read r starts at byte
