@@ -70,6 +70,24 @@ __device__ __forceinline__ void stsCell(uint32_t a, double v) {
 __device__ __forceinline__ void stsU8(uint32_t a, uint32_t v) {
   asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ldsVolatile32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t atomOrShared(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t atomExchShared(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void redAddShared(uint32_t a, int32_t v) {
+  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 // DP cells of a peer CTA
 __device__ __forceinline__ uint32_t mapToRank(uint32_t localAddr, uint32_t rank) {
   uint32_t r;
@@ -103,7 +121,7 @@ __device__ __forceinline__ double negInf() { return __longlong_as_double(0xFFF00
 // per-CTA context: shared-window addresses of everything the inner loops touch
 // ---------------------------------------------------------------------------
 struct Cta {
-  uint32_t aD, aBoff, aSym, aExt, aOpen, aSub, aTsE;
+  uint32_t aD, aBoff, aSym, aExt, aOpen, aSub, aTsE, aFlag, aPending;
   uint32_t rank, M, tid, nThreads;
   double noGap, delOpen, delExtend, delEnd;
 };
@@ -137,63 +155,53 @@ __device__ __forceinline__ double ldEdgeRacing(uint32_t aCol, uint32_t ea) {
 //   D(d) = max( D(d), max_emit-in ( max(D(s)+delExtend, S(s)+delOpen) + score ), max_null-in ( D(s)+score ) )
 //   S(d) = max( S(d), max_null-in ( S(s)+score ), D(d)+delEnd )
 // where the stored S(s) already contains D(s)+delEnd from s's own last relaxation.
-// When a cell grew every successor is woken: flag byte in the local buffer at aFlagLocal, or in
-// the remote buffer at aFlagRemote of the peer that owns it.  Result bit 0: woke a state of this CTA;
-// bit 1: woke a peer.
+// When a cell grew every successor is woken: a successor in this CTA gets its flag word
+// bit set atomically in the CTA's bitmap (and the CTA's pending count incremented if it was clear); a successor in a peer
+// gets a byte in that peer's remote buffer at aFlagRemote.  Returns true if a peer was woken.
 template <bool kBS>
-__device__ __forceinline__ uint32_t relaxState(const Cta& c, const Blocks<kBS>& blk, uint32_t i, uint32_t aSc,
-                                               uint32_t aFlagLocal, uint32_t aFlagRemote) {
+__device__ __forceinline__ bool relaxState(const Cta& c, const Blocks<kBS>& blk, uint32_t i, uint32_t aSc,
+                                           uint32_t aFlagRemote) {
   const uint32_t off = lds32(c.aBoff + 4 * i);
   const uint2 h = blk.ld2(off);
   const uint32_t nE = hdrNEmit(h.x), nIn = hdrNIn(h.x);
   const uint32_t myS = aSc + 8 * i, myD = c.aD + 8 * i;
   const double oldS = ldsCell(myS), oldD = ldsCell(myD);
   double newS = oldS, newD = oldD;
-  for (uint32_t j = 0; j < nIn; j += 2) {
-    const bool two = j + 1 < nIn;
-    const uint2 e0 = blk.ld2(off + 2 + 2 * j);
-    const uint2 e1 = two ? blk.ld2(off + 4 + 2 * j) : e0;
-    // issue every load of the pair before the first use
-    const double ss0 = ldEdgeRacing(aSc, e0.x), ds0 = ldEdgeRacing(c.aD, e0.x);
-    double ss1 = ss0, ds1 = ds0;
-    if (two) {
-      ss1 = ldEdgeRacing(aSc, e1.x);
-      ds1 = ldEdgeRacing(c.aD, e1.x);
-    }
-    const double sc0 = ldsTab(c.aSym + edgeSymOff(e0.y)), sc1 = ldsTab(c.aSym + edgeSymOff(e1.y));
-    if (j < nE) {
-      newD = dmax(newD, dmax(ds0 + c.delExtend, ss0 + c.delOpen) + sc0);
-    } else {
-      newD = dmax(newD, ds0 + sc0);
-      newS = dmax(newS, ss0 + sc0);
-    }
-    if (two) {
-      if (j + 1 < nE) {
-        newD = dmax(newD, dmax(ds1 + c.delExtend, ss1 + c.delOpen) + sc1);
-      } else {
-        newD = dmax(newD, ds1 + sc1);
-        newS = dmax(newS, ss1 + sc1);
-      }
-    }
+  uint32_t e = off + 2;
+  for (uint32_t j = 0; j < nE; ++j, e += 2) {
+    const uint2 w = blk.ld2(e);
+    const double ss = ldEdgeRacing(aSc, w.x), ds = ldEdgeRacing(c.aD, w.x);
+    newD = dmax(newD, dmax(ds + c.delExtend, ss + c.delOpen) + ldsTab(c.aSym + edgeSymOff(w.y)));
+  }
+  for (uint32_t j = nE; j < nIn; ++j, e += 2) {
+    const uint2 w = blk.ld2(e);
+    const double ss = ldEdgeRacing(aSc, w.x), ds = ldEdgeRacing(c.aD, w.x);
+    const double sc = ldsTab(c.aSym + edgeSymOff(w.y));
+    newD = dmax(newD, ds + sc);
+    newS = dmax(newS, ss + sc);
   }
   newS = dmax(newS, newD + c.delEnd);
-  uint32_t woke = 0;
+  bool sentRemote = false;
   if ((newD > oldD) || (newS > oldS)) {
     if (newD > oldD) stsCell(myD, newD);
     if (newS > oldS) stsCell(myS, newS);
-    const uint32_t nOut = hdrNOut(h.x), o0 = off + 2 + 2 * nIn;
-    for (uint32_t j = 0; j < nOut; ++j) {
-      const uint32_t w = blk.ld1(o0 + j);
+    __threadfence_block();  // the new cells are visible in this CTA before any successor is woken
+    const uint32_t nOut = hdrNOut(h.x);
+    for (uint32_t j = 0; j < nOut; ++j, ++e) {
+      const uint32_t w = blk.ld1(e);
       if (w & kEdgeRemote) {
         stPeerU8(aFlagRemote + outLocal(w), edgeRank(w), 1u);
-        woke |= 2u;
+        sentRemote = true;
       } else {
-        stsU8(aFlagLocal + outLocal(w), 1u);
-        woke |= 1u;
+        // count first, publish second: `pending` may transiently over-count but never under-count,
+        // so no warp can see 0 while a bit is set or about to be set
+        const uint32_t l = outLocal(w), bit = 1u << (l & 31);
+        redAddShared(c.aPending, 1);
+        if (atomOrShared(c.aFlag + 4 * (l >> 5), bit) & bit) redAddShared(c.aPending, -1);
       }
     }
   }
-  return woke;
+  return sentRemote;
 }
 
 template <int kMaxThreads, int kMinBlocks, bool kBS>
@@ -219,6 +227,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   c.aOpen = sm + lay.tsDopen;
   c.aSub = sm + lay.sub;
   c.aTsE = sm + lay.tsE;
+  c.aFlag = sm + lay.flag;
+  c.aPending = sm + lay.ctl;
   c.rank = rank;
   c.M = M;
   c.tid = tid;
@@ -272,8 +282,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   }
   for (uint32_t j = tid; j < 64; j += nThreads) ctl[j] = 0;
   {
-    uint32_t* fl = reinterpret_cast<uint32_t*>(smem + lay.flagLocal[0]);
-    const uint32_t nFlagWords = (lay.seq - lay.flagLocal[0]) / 4;  // the four flag arrays are contiguous
+    uint32_t* fl = reinterpret_cast<uint32_t*>(smem + lay.flag);
+    const uint32_t nFlagWords = (lay.seq - lay.flag) / 4;  // the flag arrays are contiguous
     for (uint32_t j = tid; j < nFlagWords; j += nThreads) fl[j] = 0;
   }
   __syncthreads();
@@ -343,64 +353,111 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         stsCell(aScur + 8 * i, s);
         stsCell(c.aD + 8 * i, NEG);
       }
+      if (tid == 0) ctl[0] = nThreads >> 5;  // closure: one token per warp, returned after its first sweep
       clusterBarrier();
       long long tc1 = dbgOn ? clock64() : 0;
 
       // ---- (2) closure: null transitions + deletions (src/viterbi.cpp:110-159) ----
-      // Round 0 relaxes every state once.  Then each CTA iterates over the states woken by its OWN
-      // states until none is left (one CTA barrier per iteration); states woken by a peer wait in
-      // the remote flag buffer of the current round and are picked up after the next cluster
-      // barrier.  The cluster is done when a whole round woke nobody across CTAs.
+      // Inside a CTA the relaxation is ASYNCHRONOUS.  Warp w owns the 32-state groups w, w+nWarps,
+      // ... and one word of the CTA's dirty bitmap per group.  It first relaxes all its states once,
+      // then keeps sweeping: it takes the set bits of its words (atomic exchange), compacts the
+      // dirty states into a warp-private list and relaxes them 32 at a time, one state per lane.
+      // A state that grows sets the bits of its successors (atomic OR); `pending` counts bits that
+      // are set or being served, so pending == 0 means the CTA is at a fixed point -- no CTA
+      // barrier separates the hops of a propagation chain.  Successors owned by a peer CTA are
+      // recorded in that peer's remote buffer of the current round; the cluster meets at a
+      // barrier when every CTA is locally quiet, the recorded states are flagged, and the next
+      // round starts.  The cluster is done when a whole round woke nobody across CTAs.
       {
-        // Every thread owns the 4-state flag words tid, tid+nThreads, ...: it relaxes the states whose
-        // flag is set in the buffers being consumed and sets flags in the buffers being filled.
-        const uint32_t nWords = (M + 3) / 4;
-        uint32_t round = 0, it = 0, woke = 0;
-        for (uint32_t i = tid; i < M; i += nThreads)
-          woke |= relaxState<kBS>(c, blk, i, aScur, sm + lay.flagLocal[1], sm + lay.flagRemote[0]);
+        const uint32_t warp = tid >> 5, lane = tid & 31, nWarps = nThreads >> 5;
+        const uint32_t nGroups = (M + 31) / 32;
+        const uint32_t myGroups = nGroups > warp ? (nGroups - warp + nWarps - 1) / nWarps : 0;  // <= 32 * 32 states
+        uint16_t* myList = reinterpret_cast<uint16_t*>(smem + lay.list) + warp * ((nGroups + nWarps - 1) / nWarps) * 32;
+        uint32_t round = 0;
+        bool sent = false;
+        // round 0, first sweep: every state once
+        for (uint32_t g = warp; g < nGroups; g += nWarps) {
+          const uint32_t i = 32 * g + lane;
+          if (i < M) sent |= relaxState<kBS>(c, blk, i, aScur, sm + lay.flagRemote[0]);
+        }
+        __syncwarp();
+        if (lane == 0) redAddShared(c.aPending, -1);  // pending == 0 now also means every warp swept once
         if (dbgOn && tid == 0) dbgDense += clock64() - tc1;
-        bool pickRemote = false;
         for (;;) {
-          while (__syncthreads_or((int)(woke & 1u)) || pickRemote) {
-            ++it;
-            woke &= 2u;
-            const uint32_t oFlagIn = (it & 1) ? lay.flagLocal[1] : lay.flagLocal[0];
-            const uint32_t aFlagOut = sm + ((it & 1) ? lay.flagLocal[0] : lay.flagLocal[1]);
-            const uint32_t aRemoteOut = sm + ((round & 1) ? lay.flagRemote[1] : lay.flagRemote[0]);
-            uint32_t* fl = reinterpret_cast<uint32_t*>(smem + oFlagIn);
-            uint32_t* fr = reinterpret_cast<uint32_t*>(smem + ((round & 1) ? lay.flagRemote[0] : lay.flagRemote[1]));
-            for (uint32_t w = tid; w < nWords; w += nThreads) {
-              uint32_t f = fl[w];
-              if (f) fl[w] = 0;
-              if (pickRemote) {
-                const uint32_t g = fr[w];
-                if (g) fr[w] = 0;
-                f |= g;
+          const uint32_t aRemoteOut = sm + ((round & 1) ? lay.flagRemote[1] : lay.flagRemote[0]);
+          // `pending` is exact only when nobody is relaxing: a warp that reads 0 parks at the CTA barrier
+          // below, where the count is re-read once every warp has arrived (all atomics completed)
+          uint32_t spins = 0;
+          do {
+            for (;;) {
+              // the exit decision must be warp-uniform: the sweep below uses warp collectives
+              __syncwarp();
+              uint32_t p = lane == 0 ? ldsVolatile32(c.aPending) : 0u;
+              p = __shfl_sync(0xFFFFFFFFu, p, 0);
+              if (p == 0u) break;
+              if (++spins > (1u << 22)) __trap();  // never hang the GPU: a stuck closure is a bug
+              // take this warp's dirty bits: lane j looks after the warp's j-th group (myGroups <= 32)
+              uint32_t taken = 0;
+              for (uint32_t base = 0; base < myGroups; base += 32) {
+                const uint32_t j = base + lane;
+                const uint32_t aWord = c.aFlag + 4 * (warp + j * nWarps);
+                taken = (j < myGroups && ldsVolatile32(aWord)) ? atomExchShared(aWord, 0u) : 0u;
+                const uint32_t cnt = __popc(taken);
+                uint32_t incl = cnt;  // inclusive prefix sum over the lanes
+  #pragma unroll
+                for (uint32_t d = 1; d < 32; d <<= 1) {
+                  const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                  if (lane >= d) incl += up;
+                }
+                const uint32_t n = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                if (n == 0) continue;
+                uint32_t at = incl - cnt;
+                const uint32_t stateBase = 32 * (warp + j * nWarps);
+                while (taken) {
+                  const uint32_t b = __ffs(taken) - 1;
+                  taken &= taken - 1;
+                  myList[at++] = (uint16_t)(stateBase + b);
+                }
+                __syncwarp();
+                __threadfence_block();  // cells written before these bits were set are visible from here on
+                for (uint32_t q = lane; q < n; q += 32) sent |= relaxState<kBS>(c, blk, myList[q], aScur, aRemoteOut);
+                __syncwarp();
+                if (lane == 0) redAddShared(c.aPending, -(int32_t)n);  // only now: the successors they woke are counted
+                if (dbgOn && tid == 0) dbgWork += n;
               }
-              if (f) {
-                if (dbgOn) dbgWork += __popc(f & 0x01010101u);
-#pragma unroll 1
-                for (uint32_t q = 0; q < 4; ++q)
-                  if (f & (0xFFu << (8 * q))) woke |= relaxState<kBS>(c, blk, 4 * w + q, aScur, aFlagOut, aRemoteOut);
-              }
+              if (dbgOn && tid == 0) dbgIters++;
             }
-            pickRemote = false;
-            if (dbgOn && tid == 0) dbgIters++;
-          }
+          } while (__syncthreads_or(ldsVolatile32(c.aPending) != 0u));
           if (C == 1) break;
           long long tcb = dbgOn ? clock64() : 0;
-          const uint32_t anyWoke = (uint32_t)__syncthreads_or((int)(woke & 2u));
-          if (tid < C) stPeerU32(sm + lay.ctl + (16 + (round & 1) * kMaxCluster + rank) * 4, tid, anyWoke);
+          const uint32_t anySent = (uint32_t)__syncthreads_or(sent ? 1 : 0);
+          if (tid < C) stPeerU32(sm + lay.ctl + (16 + (round & 1) * kMaxCluster + rank) * 4, tid, anySent);
           cluster.sync();
           if (dbgOn && tid == 0) dbgClusterWait += clock64() - tcb;
           uint32_t tot = 0;
           for (uint32_t r = 0; r < C; ++r) tot |= ctl[16 + (round & 1) * kMaxCluster + r];
           if (!tot) break;
           if (dbgOn && tid == 0) dbgRounds++;
-          ++round;  // peers now fill the other remote buffer; the one just completed is picked up next
-          pickRemote = true;
-          woke = 0;
+          // flag the states peers woke during the round just completed; peers now fill the other buffer
+          uint32_t* fr = reinterpret_cast<uint32_t*>(smem + ((round & 1) ? lay.flagRemote[1] : lay.flagRemote[0]));
+          for (uint32_t w = tid; w < (M + 3) / 4; w += nThreads) {
+            const uint32_t f = fr[w];
+            if (f) {
+              fr[w] = 0;
+#pragma unroll
+              for (uint32_t q = 0; q < 4; ++q)
+                if ((f >> (8 * q)) & 0xFFu) {
+                  const uint32_t l = 4 * w + q, bit = 1u << (l & 31);
+                  redAddShared(c.aPending, 1);
+                  if (atomOrShared(c.aFlag + 4 * (l >> 5), bit) & bit) redAddShared(c.aPending, -1);
+                }
+            }
+          }
+          ++round;
+          sent = false;
+          __syncthreads();
         }
+        __syncthreads();  // every warp has left the sweep before the columns are read as final
       }
 
       long long tc2 = dbgOn ? clock64() : 0;

@@ -32,8 +32,9 @@ struct SmemLayout {
   uint32_t sub;        // [16]
   uint32_t tsT;        // [kMaxK] tanDup+len[i]         -- src/viterbi.cpp:286
   uint32_t len;        // [kMaxK]
-  uint32_t ctl;        // u32 control words: [16..47] sent[2][kMaxCluster]
-  uint32_t flagLocal[2];   // [M] u8 each: woken by a state of this CTA, double-buffered by local iteration
+  uint32_t ctl;        // u32 control words: [0] pending count, [16..47] sent[2][kMaxCluster]
+  uint32_t flag;       // [ceil(M/32)] u32 bitmap: bit set = the state must be relaxed again (atomic OR / exchange)
+  uint32_t list;       // [32*ceil(M/32)] u16: per-warp compacted lists of the states taken from the bitmap
   uint32_t flagRemote[2];  // [M] u8 each: woken by a peer CTA, double-buffered by cluster round
   uint32_t seq;        // packed read
   uint32_t total;
@@ -61,8 +62,8 @@ inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t 
   L.tsT = take(8 * 8);
   L.len = take(8 * 8);
   L.ctl = take(64 * 4);
-  L.flagLocal[0] = take(M);
-  L.flagLocal[1] = take(M);
+  L.flag = take(((M + 31) / 32) * 4);
+  L.list = take(((M + 31) / 32 + 32) * 32 * 2);  // ceil(groups/warps)*warps <= groups + 31 lists of 32
   L.flagRemote[0] = take(M);
   L.flagRemote[1] = take(M);
   L.seq = take((maxLen + 3) / 4 + 16);
