@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--tmode", type=int, default=0)
+    ap.add_argument("--table-mode", type=int, default=0)
+    ap.add_argument("--partition", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=4, help="reads in the single-core CPU baseline sample (0 = skip)")
     args = ap.parse_args()
 
@@ -246,10 +248,10 @@ def main():
     compiled = machine.compile(d.ErrorFlags(length=w["length"], global_=True))
     t = compiled.t
     dec = d.Decoder(compiled, device=local_rank)
-    if args.cluster or args.threads or args.tmode:
-        dec.configure(args.cluster, args.threads, args.tmode)
+    if args.cluster or args.threads or args.tmode or args.table_mode or args.partition:
+        dec.configure(args.cluster, args.threads, args.tmode, args.table_mode, args.partition)
     info = dec.info()
-    default_rps = {"cfg2": 2048, "cfg1": 262144, "cfg3": 8192, "cfg4": 16384}[args.workload]
+    default_rps = {"cfg2": 960, "cfg1": 65536, "cfg3": 4096, "cfg4": 8192}[args.workload]
     rps = args.reads_per_step or default_rps
 
     # distinct batch per step, generated before timing and resident in HBM
@@ -379,7 +381,7 @@ def main():
                         reads_per_step_per_gpu=rps, n_states=int(t.n_states), k=int(t.k),
                         cluster_size=info["cluster_size"], states_per_cta=info["states_per_cta"],
                         threads_per_cta=info["threads_per_cta"], smem_bytes_per_cta=info["smem_bytes_per_cta"],
-                        t_in_smem=info["t_in_smem"], reads_in_flight=info["n_clusters"],
+                        t_in_smem=info["t_in_smem"], table_in_smem=info["table_in_smem"], reads_in_flight=info["n_clusters"],
                         l2="working set >> L2: every step streams reads_per_step x ~37 MB of predecessor records "
                            "and uses a distinct read batch" if args.workload == "cfg2" else
                            "distinct read batch per step; predecessor-record stream exceeds L2",

@@ -193,7 +193,24 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
   P.maxSliceWords = 0;
   for (uint32_t g = 0; g < Np; ++g) {
     const uint32_t rank = g / M;
-    if (g % M == 0) P.sliceOff[rank] = (uint32_t)P.blocks.size();
+    if (g % M == 0) {
+      while (P.blocks.size() % 8) P.blocks.push_back(0);  // slices start sector-aligned
+      P.sliceOff[rank] = (uint32_t)P.blocks.size();
+    }
+    {
+      // a block that fits one 32-byte sector must not straddle two (one L1/L2 access per state)
+      const uint32_t s0 = P.origOf[g];
+      uint32_t words = 2;
+      if (s0 != 0xFFFFFFFFu) {
+        const uint32_t nIn0 = (d->emitOff[s0 + 1] - d->emitOff[s0]) + (d->nullOff[s0 + 1] - d->nullOff[s0]);
+        std::vector<uint32_t> tmp = outs[s0];
+        std::sort(tmp.begin(), tmp.end());
+        words = 2 + 2 * nIn0 + (uint32_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+      }
+      const uint32_t at = (uint32_t)P.blocks.size() % 8;
+      if (words <= 8 && at + words > 8)
+        while (P.blocks.size() % 8) P.blocks.push_back(0);
+    }
     P.blockOff[g] = (uint32_t)P.blocks.size();
     const uint32_t s = P.origOf[g];
     if (s == 0xFFFFFFFFu) {

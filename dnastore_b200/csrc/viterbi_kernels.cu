@@ -139,6 +139,10 @@ struct Blocks {
     if (kBS) return lds32(aBase + wordOff * 4);
     return __ldg(gBase + wordOff);
   }
+  // start fetching a block that will be needed soon (global-memory tables only)
+  __device__ __forceinline__ void prefetch(uint32_t wordOff) const {
+    if (!kBS) asm volatile("prefetch.global.L1 [%0];" ::"l"(gBase + wordOff));
+  }
 };
 
 // A cell of column `aCol` (shared address of the column in THIS CTA) addressed by an edge word.
@@ -328,6 +332,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           for (uint32_t j = 0; j < k; ++j) tCol[j * M + i] = NEG;
         } else {
           const uint32_t off = lds32(c.aBoff + 4 * i);
+          if (i + nThreads < M) blk.prefetch(lds32(c.aBoff + 4 * (i + nThreads)));
           const uint2 h = blk.ld2(off);
           const uint32_t nE = hdrNEmit(h.x), mdl = hdrMdl(h.x);
           double t0 = NEG;
@@ -378,6 +383,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         // round 0, first sweep: every state once
         for (uint32_t g = warp; g < nGroups; g += nWarps) {
           const uint32_t i = 32 * g + lane;
+          if (i + 32 * nWarps < M) blk.prefetch(lds32(c.aBoff + 4 * (i + 32 * nWarps)));
           if (i < M) sent |= relaxState<kBS>(c, blk, i, aScur, sm + lay.flagRemote[0]);
         }
         __syncwarp();
@@ -420,7 +426,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                 }
                 __syncwarp();
                 __threadfence_block();  // cells written before these bits were set are visible from here on
-                for (uint32_t q = lane; q < n; q += 32) sent |= relaxState<kBS>(c, blk, myList[q], aScur, aRemoteOut);
+                for (uint32_t q = lane + 32; q < n; q += 32) blk.prefetch(lds32(c.aBoff + 4 * myList[q]));
+              for (uint32_t q = lane; q < n; q += 32) sent |= relaxState<kBS>(c, blk, myList[q], aScur, aRemoteOut);
                 __syncwarp();
                 if (lane == 0) redAddShared(c.aPending, -(int32_t)n);  // only now: the successors they woke are counted
                 if (dbgOn && tid == 0) dbgWork += n;
@@ -467,6 +474,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
       for (uint32_t i = tid; i < M; i += nThreads) {
         const uint32_t g = rank * M + i;
         const uint32_t off = lds32(c.aBoff + 4 * i);
+        if (i + nThreads < M) blk.prefetch(lds32(c.aBoff + 4 * (i + nThreads)));
         const uint2 h = blk.ld2(off);
         const uint32_t nE = hdrNEmit(h.x), nIn = hdrNIn(h.x), mdl = hdrMdl(h.x);
         const double sHere = ldsCell(aScur + 8 * i), dHere = ldsCell(c.aD + 8 * i);
