@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libdnastore_b200.so")
+lib_path = os.environ.get("DNAB_LIB") or os.path.join(_HERE, "libdnastore_b200.so")  # DNAB_LIB: A/B builds
 
 if not os.path.exists(lib_path):
     raise ImportError(
@@ -55,7 +55,7 @@ class ErrorFlags(C.Structure):
 
 class DecoderInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_states", "k", "local", "cluster_size", "states_per_cta", "threads_per_cta",
-                                          "smem_bytes_per_cta", "t_in_smem", "table_in_smem", "n_clusters", "sm_count")]
+                                          "smem_bytes_per_cta", "t_in_smem", "table_in_smem", "s_prev_in_smem", "n_clusters", "sm_count")]
 
 
 class DecoderStats(C.Structure):

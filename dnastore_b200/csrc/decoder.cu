@@ -50,7 +50,7 @@ struct DevBuf {
 };
 
 struct LaunchPlan {
-  uint32_t C = 0, M = 0, threads = 0, tInSmem = 0, blocksInSmem = 0, sliceWords = 0, smemBytes = 0, nClusters = 0;
+  uint32_t C = 0, M = 0, threads = 0, tInSmem = 0, blocksInSmem = 0, sPrevGlobal = 0, sliceWords = 0, smemBytes = 0, nClusters = 0;
   int32_t maxLen = -1;
 };
 
@@ -72,7 +72,8 @@ struct dnab_decoder {
   // user overrides
   uint32_t wantC = 0, wantThreads = 0, wantTMode = 0;  // tMode: 0 auto, 1 smem, 2 global
   uint32_t wantBlockMode = 0;   // transition table: 0 auto, 1 shared memory, 2 global memory
-  uint32_t wantPartition = 0;   // 0 DFS runs + degree sort, 1 index order + degree sort, 2 DFS runs, no sort
+  uint32_t wantSPrevMode = 0;   // S(pos-1): 0 auto, 1 shared memory, 2 global scratch
+  uint32_t wantPartition = 0;   // 0/1 index-order runs + in-degree sort (default), 2 DFS runs unsorted, 3 DFS chunks dealt round-robin + sort, 4 DFS runs + sort
   // device-resident structures for the current plan
   LaunchPlan plan;
   DevTables dev{};
@@ -80,7 +81,7 @@ struct dnab_decoder {
   DevBuf<uint8_t> dSymChar;
   // scratch
   DevBuf<uint8_t> dPred;
-  DevBuf<double> dTScratch, dPartVal, dCells;
+  DevBuf<double> dTScratch, dSScratch, dPartVal, dCells;
   DevBuf<uint32_t> dStart, dPartOrig, dPartG;
   DevBuf<unsigned long long> dDbg;
   bool debug = false;
@@ -101,9 +102,10 @@ struct dnab_decoder {
 
 namespace dnab {
 
-// Locality-preserving order of the states: depth-first preorder over the transition graph.
-// Cutting it into C equal runs keeps most transitions inside one CTA (85% on the BASELINE
-// config 2 machine against 56% for index order), which turns DSMEM gathers into local LDS.
+// Alternative order of the states: depth-first preorder over the transition graph.  Cutting it
+// into C equal runs keeps more transitions inside one CTA (85% on the BASELINE config 2 machine
+// against 56% for index order) but measured slower on B200 (more closure sweeps per round), so
+// index order is the default and this is selectable (dnab_decoder_configure_ex).
 static std::vector<uint32_t> dfsOrder(const dnab_decoder* d) {
   const uint32_t N = d->nStates;
   std::vector<uint32_t> outOff(N + 1, 0), outDst;
@@ -158,9 +160,10 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
   const uint32_t M = (N + C - 1) / C, Np = C * M;
   P.C = C;
   P.M = M;
-  // 1. CTA assignment: equal runs of the DFS order (identity order for a single CTA)
+  // 1. CTA assignment: equal runs of the reference's state order (default) or of a DFS order
   std::vector<uint32_t> order;
-  if (C > 1 && d->wantPartition != 1)
+  const bool useDfs = d->wantPartition >= 2;
+  if (C > 1 && useDfs)
     order = dfsOrder(d);
   else {
     order.resize(N);
@@ -171,9 +174,24 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
   auto inDeg = [&](uint32_t s) { return (d->emitOff[s + 1] - d->emitOff[s]) + (d->nullOff[s + 1] - d->nullOff[s]); };
   P.origOf.assign(Np, 0xFFFFFFFFu);
   P.newOf.assign(N, 0);
+  // partition mode 3: the DFS order is cut into 8*C chunks dealt round-robin to the CTAs, trading some
+  // locality for CTAs that are busy for equally long inside a closure round
+  std::vector<std::vector<uint32_t>> dealt(C);
+  if (d->wantPartition == 3 && C > 1) {
+    const uint32_t chunk = std::max<uint32_t>(32, (N + 8 * C - 1) / (8 * C));
+    uint32_t r = 0;
+    for (uint32_t lo = 0; lo < N;) {
+      while (dealt[r].size() >= M) r = (r + 1) % C;  // a CTA never takes more than M states
+      const uint32_t hi = std::min<uint32_t>(std::min(N, lo + chunk), lo + (M - (uint32_t)dealt[r].size()));
+      dealt[r].insert(dealt[r].end(), order.begin() + lo, order.begin() + hi);
+      lo = hi;
+      r = (r + 1) % C;
+    }
+  }
   for (uint32_t r = 0; r < C; ++r) {
     const uint32_t lo = std::min(N, r * M), hi = std::min(N, (r + 1) * M);
     std::vector<uint32_t> mine(order.begin() + lo, order.begin() + hi);
+    if (d->wantPartition == 3 && C > 1) mine = dealt[r];
     if (d->wantPartition != 2)
       std::stable_sort(mine.begin(), mine.end(), [&](uint32_t a, uint32_t b) { return inDeg(a) > inDeg(b); });
     for (uint32_t j = 0; j < mine.size(); ++j) {
@@ -243,11 +261,11 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
       for (uint32_t dg : o) P.blocks.push_back((dg % M) | ((dg / M) << 20) | (dg / M != rank ? kEdgeRemote : 0u));
     }
     if (P.blocks.size() & 1) P.blocks.push_back(0);
-    if ((g + 1) % M == 0) {
-      P.sliceOff[rank + 1] = (uint32_t)P.blocks.size();
-      P.maxSliceWords = std::max(P.maxSliceWords, P.sliceOff[rank + 1] - P.sliceOff[rank]);
-    }
+    if ((g + 1) % M == 0) P.sliceOff[rank + 1] = (uint32_t)P.blocks.size();
   }
+  // slice r ends where slice r+1 begins (after that slice's sector alignment): size the shared-memory
+  // copy from the final offsets
+  for (uint32_t r = 0; r < C; ++r) P.maxSliceWords = std::max(P.maxSliceWords, P.sliceOff[r + 1] - P.sliceOff[r]);
   return DNAB_OK;
 }
 
@@ -259,30 +277,38 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
   // columns and the CTA's slice of the transition table in shared memory when they fit too.
   LaunchPlan best;
   Partition P;
-  const uint32_t cands[] = {1, 2, 4, 8, 16};
+  // more reads in flight beats more SMs per read (measured), so the smallest feasible cluster wins;
+  // any size up to 16 is allowed, not only powers of two
+  std::vector<uint32_t> cands = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16};
+  if (d->wantC >= 1 && d->wantC <= (uint32_t)kMaxCluster) cands = {d->wantC};  // any size, not only powers of two
   for (uint32_t C : cands) {
-    if (d->wantC && C != d->wantC) continue;
     const uint32_t M = (N + C - 1) / C;
     if (M > 65535) continue;  // 16-bit local indices in the out-edge words
-    if (makeLayout(M, k, 0, 0, (uint32_t)planLen).total > d->smemOptin) continue;
+    if (makeLayout(M, k, 0, 0, (uint32_t)planLen, d->wantSPrevMode == 1 ? 0 : 1).total > d->smemOptin) continue;
     int rc = buildPartition(d, C, P);
     if (rc != DNAB_OK) return rc;
-    // options in order of preference: (T,blocks) in smem, blocks only, T only, neither
+    // options in order of preference: S(pos-1) in shared memory before global scratch; within that
+    // (T,blocks) in smem, blocks only, T only, neither
     const uint32_t opts[4][2] = {{1, 1}, {0, 1}, {1, 0}, {0, 0}};
-    for (const auto& o : opts) {
-      const uint32_t tIn = (k == 0) ? 0 : o[0], bIn = o[1];
-      if (d->wantTMode == 1 && k && !tIn) continue;
-      if (d->wantTMode == 2 && tIn) continue;
-      if (d->wantBlockMode == 1 && !bIn) continue;
-      if (d->wantBlockMode == 2 && bIn) continue;
-      const uint32_t smem = makeLayout(M, k, tIn, bIn ? P.maxSliceWords : 0, (uint32_t)planLen).total;
-      if (smem <= d->smemOptin) {
-        best.C = C;
-        best.M = M;
-        best.tInSmem = tIn;
-        best.blocksInSmem = bIn;
-        best.smemBytes = smem;
-        break;
+    for (uint32_t sg = 0; sg < 2 && !best.C; ++sg) {
+      if (d->wantSPrevMode == 1 && sg) continue;
+      if (d->wantSPrevMode == 2 && !sg) continue;
+      for (const auto& o : opts) {
+        const uint32_t tIn = (k == 0) ? 0 : o[0], bIn = o[1];
+        if (d->wantTMode == 1 && k && !tIn) continue;
+        if (d->wantTMode == 2 && tIn) continue;
+        if (d->wantBlockMode == 1 && !bIn) continue;
+        if (d->wantBlockMode == 2 && bIn) continue;
+        const uint32_t smem = makeLayout(M, k, tIn, bIn ? P.maxSliceWords : 0, (uint32_t)planLen, sg).total;
+        if (smem <= d->smemOptin) {
+          best.C = C;
+          best.M = M;
+          best.tInSmem = tIn;
+          best.blocksInSmem = bIn;
+          best.sPrevGlobal = sg;
+          best.smemBytes = smem;
+          break;
+        }
       }
     }
     if (best.C) break;
@@ -292,7 +318,10 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
                  " states need more shared memory than a 16-CTA cluster has (or the requested configuration is infeasible)");
     return DNAB_EINVAL;
   }
-  uint32_t threads = d->wantThreads ? d->wantThreads : std::min<uint32_t>(512, std::max<uint32_t>(128, (best.M + 31) / 32 * 32));
+  // small slices: few threads per CTA so that several CTAs (reads) share an SM; large slices: more warps
+  // to overlap the latency-bound per-state chains (measured on B200)
+  uint32_t threads = d->wantThreads ? d->wantThreads
+                     : best.M <= 1024 ? 128 : best.M <= 2048 ? 256 : best.M <= 6000 ? 512 : 768;
   threads = std::min<uint32_t>(1024, (threads + 31) / 32 * 32);
   best.threads = threads;
   best.maxLen = planLen;
@@ -317,6 +346,7 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
   t.endG = P.newOf[N - 1];
   t.tInSmem = best.tInSmem;
   t.blocksInSmem = best.blocksInSmem;
+  t.sPrevGlobal = best.sPrevGlobal;
   t.blocks = d->dBlocks.p;
   t.blockOff = d->dBlockOff.p;
   t.sliceOff = d->dSliceOff.p;
@@ -339,6 +369,7 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
   }
   best.nClusters = (uint32_t)nClusters;
   if (!best.tInSmem && k) CUDA_TRY(d->dTScratch.ensure((size_t)nClusters * C * k * M));
+  if (best.sPrevGlobal) CUDA_TRY(d->dSScratch.ensure((size_t)nClusters * 2 * C * M));
   d->plan = best;
   return DNAB_OK;
 }
@@ -371,7 +402,7 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
     const int64_t n = std::min(chunk, nReads - at);
     FillArgs fa{};
     fa.lay = makeLayout(d->plan.M, d->k, d->plan.tInSmem, d->plan.blocksInSmem ? d->plan.sliceWords : 0,
-                        (uint32_t)d->plan.maxLen);
+                        (uint32_t)d->plan.maxLen, d->plan.sPrevGlobal);
     fa.nReads = n;
     fa.maxLen = maxLen;
     fa.packed = dPacked;
@@ -379,6 +410,7 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
     fa.readLen = dReadLen + at;
     fa.pred = d->dPred.p;
     fa.tScratch = d->dTScratch.p;
+    fa.sScratch = d->dSScratch.p;
     fa.loglike = dLoglike + at;
     fa.startState = d->dStart.p;
     fa.partVal = d->dPartVal.p;
@@ -542,7 +574,8 @@ int dnab_decoder_configure(dnab_decoder* d, uint32_t cluster_size, uint32_t thre
 
 int dnab_decoder_configure_ex(dnab_decoder* d, uint32_t block_table_mode, uint32_t partition_mode) {
   if (!d) return DNAB_EINVAL;
-  d->wantBlockMode = block_table_mode;
+  d->wantBlockMode = block_table_mode % 10;
+  d->wantSPrevMode = block_table_mode / 10;  // tens digit: S(pos-1) placement (0 auto, 1 shared, 2 global)
   d->wantPartition = partition_mode;
   d->plan = LaunchPlan();
   return DNAB_OK;
@@ -563,6 +596,7 @@ int dnab_decoder_get_info(const dnab_decoder* dc, dnab_decoder_info* info) {
   info->smem_bytes_per_cta = d->plan.smemBytes;
   info->t_in_smem = d->plan.tInSmem;
   info->table_in_smem = d->plan.blocksInSmem;
+  info->s_prev_in_smem = d->plan.sPrevGlobal ? 0 : 1;
   info->n_clusters = d->plan.nClusters;
   info->sm_count = (uint32_t)d->smCount;
   return DNAB_OK;

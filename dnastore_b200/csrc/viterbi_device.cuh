@@ -54,6 +54,7 @@ struct DevTables {
   uint32_t endG;      // padded-space index of the reference's last state
   uint32_t tInSmem;   // T columns in shared memory (else in global scratch)
   uint32_t blocksInSmem;  // every CTA keeps its slice of the state blocks in shared memory
+  uint32_t sPrevGlobal;   // the previous column S(pos-1) lives in global scratch (L2) instead of shared memory
   const uint32_t* blocks;     // state blocks; the blocks of one CTA's slice are contiguous
   const uint32_t* blockOff;   // [Np] word offset of each state's block
   const uint32_t* sliceOff;   // [C+1] word offset where each rank's slice of `blocks` begins

@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   volatile uint32_t* ctl = reinterpret_cast<volatile uint32_t*>(smem + lay.ctl);
   uint32_t* boff = reinterpret_cast<uint32_t*>(smem + lay.boff);
   uint8_t* seqS = smem + lay.seq;
+  double* sG = tb.sPrevGlobal ? args.sScratch + (size_t)clusterId * 2 * Np : nullptr;
   double* tCol = tb.tInSmem ? reinterpret_cast<double*>(smem + lay.tBuf)
                             : args.tScratch + ((size_t)clusterId * C + rank) * (size_t)k * M;
 
@@ -318,6 +319,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
     for (int32_t pos = 0; pos <= L; ++pos) {
       const uint32_t cur = pos & 1, prev = cur ^ 1;
       const uint32_t aScur = sm + (cur ? lay.sBuf[1] : lay.sBuf[0]), aSprev = sm + (prev ? lay.sBuf[1] : lay.sBuf[0]);
+      // when S(pos-1) lives in global scratch: the cluster's two S columns, indexed by padded state
+      const double* sPrevG = sG + (size_t)prev * Np;
+      double* sCurG = sG + (size_t)cur * Np;
+      const uint32_t M8 = M * 8;
       const uint32_t x = pos > 0 ? (seqS[(pos - 1) >> 2] >> (2 * ((pos - 1) & 3))) & 3u : 0u;
       const uint32_t x8 = x * 8;
 
@@ -341,8 +346,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             const bool two = j + 1 < nE;
             const uint2 e0 = blk.ld2(off + 2 + 2 * j);
             const uint2 e1 = two ? blk.ld2(off + 4 + 2 * j) : e0;
-            const double v0 = ldEdgeFinal(aSprev, e0.x);
-            const double v1 = two ? ldEdgeFinal(aSprev, e1.x) : NEG;
+            double v0, v1 = NEG;
+            if (tb.sPrevGlobal) {  // plain coherent loads: the column was published before the last cluster barrier
+              v0 = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(sPrevG) + edgeRank(e0.x) * M8 + edgeOff(e0.x));
+              if (two) v1 = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(sPrevG) + edgeRank(e1.x) * M8 + edgeOff(e1.x));
+            } else {
+              v0 = ldEdgeFinal(aSprev, e0.x);
+              if (two) v1 = ldEdgeFinal(aSprev, e1.x);
+            }
             const double c0 = ((v0 + ldsTab(c.aSym + edgeSymOff(e0.y))) + c.noGap) + ldsTab(c.aSub + edgeSubOff(e0.y) + x8);
             const double c1 = ((v1 + ldsTab(c.aSym + edgeSymOff(e1.y))) + c.noGap) + ldsTab(c.aSub + edgeSubOff(e1.y) + x8);
             s = dmax(s, c0);
@@ -478,6 +489,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         const uint2 h = blk.ld2(off);
         const uint32_t nE = hdrNEmit(h.x), nIn = hdrNIn(h.x), mdl = hdrMdl(h.x);
         const double sHere = ldsCell(aScur + 8 * i), dHere = ldsCell(c.aD + 8 * i);
+        if (tb.sPrevGlobal) sCurG[g] = sHere;  // publish the converged column for the next position
         const double parked = (mdl > 0 && pos > 0) ? tCol[(mdl - 1) * M + i] : NEG;  // T(state,pos-1,0)+sub
 
         double best = NEG, bestD = NEG;
@@ -487,7 +499,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           const double vs = ldEdgeRacing(aScur, ew.x), vd = ldEdgeRacing(c.aD, ew.x);
           if (e < nE) {
             if (pos > 0) {
-              const double v = ldEdgeFinal(aSprev, ew.x) + ldsTab(c.aTsE + edgeTsEOff(ew.y) + x8);
+              const double vp = tb.sPrevGlobal
+                                    ? *reinterpret_cast<const double*>(reinterpret_cast<const char*>(sPrevG) + edgeRank(ew.x) * M8 + edgeOff(ew.x))
+                                    : ldEdgeFinal(aSprev, ew.x);
+              const double v = vp + ldsTab(c.aTsE + edgeTsEOff(ew.y) + x8);
               if (v > best) {
                 best = v;
                 idx = e;

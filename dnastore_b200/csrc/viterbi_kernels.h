@@ -40,7 +40,8 @@ struct SmemLayout {
   uint32_t total;
 };
 
-inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t blockSliceWords, uint32_t maxLen) {
+inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t blockSliceWords, uint32_t maxLen,
+                             uint32_t sPrevGlobal = 0) {
   SmemLayout L;
   uint32_t at = 0;
   auto take = [&](uint32_t bytes) {
@@ -49,7 +50,7 @@ inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t 
     return here;
   };
   L.sBuf[0] = take(M * 8);
-  L.sBuf[1] = take(M * 8);
+  L.sBuf[1] = sPrevGlobal ? L.sBuf[0] : take(M * 8);  // one S column is enough when S(pos-1) is in global scratch
   L.dBuf = take(M * 8);
   L.tBuf = tInSmem ? take(k * M * 8) : 0;
   L.boff = take(M * 4);
@@ -80,6 +81,7 @@ struct FillArgs {
   const int32_t* readLen;    // [nReads]
   uint8_t* pred;             // [nReads][maxLen+1][k+2][Np] predecessor records, 1 byte per DP cell
   double* tScratch;          // [nClusters*C][k][M] T columns when they do not fit in shared memory
+  double* sScratch;          // [nClusters][2][Np] S columns of the last two positions when sPrevGlobal
   double* loglike;           // [nReads] (global mode; local mode: written by the traceback kernel)
   uint32_t* startState;      // [nReads] traceback start (padded index), global mode
   double* partVal;           // [nReads][C] local mode: per-CTA best final S ...

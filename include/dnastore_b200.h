@@ -112,6 +112,7 @@ typedef struct dnab_decoder_info {
   uint32_t smem_bytes_per_cta;
   uint32_t t_in_smem;        /* 1: duplication (T) columns live in shared memory, 0: in global scratch */
   uint32_t table_in_smem;    /* 1: each CTA keeps its slice of the transition table in shared memory */
+  uint32_t s_prev_in_smem;   /* 1: the previous column S(pos-1) is in shared memory, 0: in L2-resident global scratch */
   uint32_t n_clusters;       /* clusters resident at once = reads in flight */
   uint32_t sm_count;
 } dnab_decoder_info;
@@ -119,8 +120,10 @@ int dnab_decoder_get_info(const dnab_decoder* d, dnab_decoder_info* info);
 
 /* Tuning overrides (0 = automatic); must be set before the first batch. */
 int dnab_decoder_configure(dnab_decoder* d, uint32_t cluster_size, uint32_t threads_per_cta, uint32_t t_in_smem_mode);
-/* block_table_mode: 0 auto, 1 transition table in shared memory, 2 in global memory;
- * partition_mode: 0 locality-preserving (DFS) partition + in-degree sort, 1 index order + sort, 2 DFS, no sort. */
+/* block_table_mode: units digit 0 auto, 1 transition table in shared memory, 2 in global memory;
+ * tens digit 0 auto, 1 previous column S(pos-1) in shared memory, 2 in global scratch;
+ * partition_mode: 0/1 equal runs of the reference state order + in-degree sort inside a CTA (default),
+ * 2 runs of a depth-first order, unsorted, 3 DFS chunks dealt round-robin + sort, 4 DFS runs + sort. */
 int dnab_decoder_configure_ex(dnab_decoder* d, uint32_t block_table_mode, uint32_t partition_mode);
 
 /* Reads are packed 2 bits per base, A,C,G,T = 0..3 (src/kmer.h:11-13, src/fastseq.cpp:9-15),

@@ -60,6 +60,22 @@ def test_gpu_every_cluster_size(d, name, cluster):
         _check_against_golden(d, case, dict(cluster_size=cluster, t_in_smem_mode=tmode))
 
 
+@pytest.mark.parametrize("cluster,table_mode,partition", [(3, 20, 0), (6, 20, 4), (8, 22, 3), (2, 21, 2), (1, 20, 0), (5, 12, 4)])
+@pytest.mark.parametrize("name", ["l4c4_local_mixed", "cfg3_global_indels", "cfg4_global_dels"])
+def test_gpu_memory_placements_and_partitions(d, name, cluster, table_mode, partition):
+    """S(pos-1) in global scratch, transition table in shared / global memory, odd cluster sizes and
+    every partition policy: none of it may change a bit."""
+    case = util.golden_case(name)
+    if cluster == 1 and util.compiled_for_case(case).t.n_states > 4000:
+        pytest.skip("does not fit one CTA")
+    try:
+        _check_against_golden(d, case, dict(cluster_size=cluster, table_mode=table_mode, partition_mode=partition))
+    except d.DnabError as e:
+        if "does not fit" in str(e):
+            pytest.skip("requested placement does not fit this machine")
+        raise
+
+
 @pytest.mark.parametrize("threads", [32, 96, 256, 1024])
 def test_gpu_every_block_size(d, threads):
     _check_against_golden(d, util.golden_case("l4c4_global_mixed"), dict(threads_per_cta=threads))
