@@ -63,6 +63,45 @@ def mutate(seq, rng, sub_rate=0.0, iv_ratio=10.0, dup_rate=0.0, max_dup=1, del_r
     return "".join(s).upper()
 
 
+def mutate_aligned(seq, rng, sub_rate=0.0, iv_ratio=10.0, dup_rate=0.0, max_dup=1, del_rate=0.0, max_del=1):
+    """Same simulator as mutate(), but keeps the pairwise alignment (errdecode.pl tracks it in
+    @origpos, :271-273, and prints it as Stockholm, :320-340): returns (original row, observed row),
+    gapped with '-' and of equal length."""
+    cols = [[c.upper(), c.lower()] for c in seq]  # [original base or '-', observed base (lower = untouched)]
+
+    def observed():
+        return [i for i, c in enumerate(cols) if c[1] != "-"]
+
+    def coords(maxsize):
+        obs = observed()
+        n = len(obs)
+        size = int(rng.random() * (min(n, maxsize) + 1 - 1)) + 1
+        pos = int(rng.random() * (n + 1 - size))
+        return obs[pos:pos + size]
+
+    n0 = len(observed())
+    for _ in range(_round_half_up(dup_rate * n0)):
+        seg = coords(max_dup)
+        if not seg or any(cols[i][1].isupper() for i in seg):
+            continue
+        ins = [["-", cols[i][1].upper()] for i in seg]
+        at = seg[-1] + 1
+        cols[at:at] = ins
+    for _ in range(_round_half_up(sub_rate * len(observed()))):
+        seg = coords(1)
+        if not seg:
+            continue
+        i = seg[0]
+        base = cols[i][1].lower()
+        cols[i][1] = (_TRANSVERSION[base][int(rng.random() * 2)] if rng.random() < 1.0 / (1.0 + iv_ratio)
+                      else _TRANSITION[base])
+    for _ in range(_round_half_up(del_rate * len(observed()))):
+        for i in coords(max_del):
+            cols[i][1] = "-"
+    cols = [c for c in cols if not (c[0] == "-" and c[1] == "-")]
+    return "".join(c[0] for c in cols), "".join(c[1].upper() for c in cols)
+
+
 def mutate_subs_batch(seqs, rng, sub_rate=0.01, iv_ratio=10.0):
     """Vectorised substitution-only mutation of many reads (BASELINE config 2 / 5):
     round(sub_rate*len) substitutions per read at uniform positions (with replacement,

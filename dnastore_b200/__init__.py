@@ -16,6 +16,12 @@ from ._capi import (  # noqa: F401
     lib,
     lib_path,
     pack_reads,
+    MutatorParams,
+    MutatorCounts,
+    PairDb,
+    pairhmm_fb_batch,
+    expected_counts,
+    baum_welch,
     READ_OK,
     READ_NO_DECODING,
     READ_OVERFLOW,
@@ -23,6 +29,7 @@ from ._capi import (  # noqa: F401
 )
 
 __all__ = [
-    "DnabError", "Machine", "ErrorFlags", "Compiled", "Decoder", "Tables", "lib", "lib_path", "pack_reads",
+    "DnabError", "Machine", "ErrorFlags", "Compiled", "Decoder", "Tables", "lib", "lib_path", "pack_reads", "MutatorParams", "MutatorCounts", "PairDb",
+    "pairhmm_fb_batch", "expected_counts", "baum_welch",
     "READ_OK", "READ_NO_DECODING", "READ_OVERFLOW", "READ_TRACEBACK_FAILED",
 ]

@@ -64,6 +64,51 @@ class DecoderStats(C.Structure):
                 ("timed_fill_ms", C.c_double), ("timed_traceback_ms", C.c_double), ("timed_fill_launches", C.c_uint64)]
 
 
+class MutatorParams(C.Structure):
+    """struct dnab_mutator_params (reference MutatorParams, src/mutator.h:9-31)."""
+    _fields_ = [("p_del_open", C.c_double), ("p_del_extend", C.c_double), ("p_tan_dup", C.c_double),
+                ("p_transition", C.c_double), ("p_transversion", C.c_double), ("p_len", C.c_double * 16),
+                ("max_dup_len", C.c_int32), ("local", C.c_int32)]
+
+    @classmethod
+    def from_flags(cls, flags):
+        p = cls()
+        lib.dnab_mutator_params_from_flags(C.byref(flags), C.byref(p))
+        return p
+
+    def probs(self):
+        return np.array([self.p_del_open, self.p_del_extend, self.p_tan_dup, self.p_transition, self.p_transversion])
+
+    def plen(self):
+        return np.array(list(self.p_len)[:self.max_dup_len])
+
+    def to_json(self):
+        ptr = lib.dnab_mutator_params_json(C.byref(self))
+        try:
+            return C.string_at(ptr).decode()
+        finally:
+            lib.dnab_free(ptr)
+
+
+class MutatorCounts(C.Structure):
+    """struct dnab_mutator_counts (reference MutatorCounts, src/mutator.h:43-67)."""
+    _fields_ = [("n_del_open", C.c_double), ("n_tan_dup", C.c_double), ("n_no_gap", C.c_double),
+                ("n_del_extend", C.c_double), ("n_del_end", C.c_double), ("n_len", C.c_double * 16),
+                ("n_sub", C.c_double * 16), ("max_dup_len", C.c_int32), ("reserved", C.c_int32)]
+
+    def flat(self):
+        """[nDelOpen, nTanDup, nNoGap, nDelExtend, nDelEnd, nLen[k], nSub[16]] -- the oracle's order."""
+        return np.array([self.n_del_open, self.n_tan_dup, self.n_no_gap, self.n_del_extend, self.n_del_end]
+                        + list(self.n_len)[:self.max_dup_len] + list(self.n_sub))
+
+    def to_json(self):
+        ptr = lib.dnab_mutator_counts_json(C.byref(self))
+        try:
+            return C.string_at(ptr).decode()
+        finally:
+            lib.dnab_free(ptr)
+
+
 def _sig(name, restype, *argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -103,6 +148,25 @@ _sig("dnab_pack_reads", C.c_int, C.c_char_p, _vp, C.c_int64, _vp, _vp, _vp)
 _sig("dnab_viterbi_batch", C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp)
 _sig("dnab_viterbi_batch_device", C.c_int, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp)
 _sig("dnab_viterbi_cells", C.c_int, _vp, _vp, C.c_int32, _vp, _vp)
+_sig("dnab_mutator_params_from_flags", None, C.POINTER(ErrorFlags), C.POINTER(MutatorParams))
+_sig("dnab_mutator_params_json", _vp, C.POINTER(MutatorParams))
+_sig("dnab_mutator_counts_json", _vp, C.POINTER(MutatorCounts))
+_sig("dnab_lse_table", C.POINTER(C.c_double), C.POINTER(C.c_int32))
+_sig("dnab_pair_db_load", _vp, C.c_char_p)
+_sig("dnab_pair_db_count", C.c_int64, _vp)
+_sig("dnab_pair_db_in_len", C.c_int32, _vp, C.c_int64)
+_sig("dnab_pair_db_out_len", C.c_int32, _vp, C.c_int64)
+_sig("dnab_pair_db_in", C.POINTER(C.c_uint8), _vp, C.c_int64)
+_sig("dnab_pair_db_out", C.POINTER(C.c_uint8), _vp, C.c_int64)
+_sig("dnab_pair_db_env_a", C.POINTER(C.c_int32), _vp, C.c_int64)
+_sig("dnab_pair_db_env_b", C.POINTER(C.c_int32), _vp, C.c_int64)
+_sig("dnab_pair_db_free", None, _vp)
+_sig("dnab_pairhmm_fb_batch", C.c_int, C.c_int, C.POINTER(MutatorParams), C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp,
+     _vp, _vp, _vp, C.POINTER(C.c_double))
+_sig("dnab_expected_counts", C.c_int, C.c_int, C.POINTER(MutatorParams), _vp, C.c_int, C.POINTER(MutatorCounts),
+     C.POINTER(C.c_double))
+_sig("dnab_baum_welch", C.c_int, C.c_int, C.POINTER(MutatorParams), _vp, C.c_int, C.POINTER(MutatorParams),
+     C.POINTER(C.c_int32))
 _sig("dnab_decode_fasta", _vp, _vp, C.c_char_p)
 _sig("dnab_decoded_count", C.c_int64, _vp)
 _sig("dnab_decoded_name", C.c_char_p, _vp, C.c_int64)
@@ -228,6 +292,77 @@ class Compiled:
         if getattr(self, "_h", None):
             lib.dnab_compiled_free(self._h)
             self._h = None
+
+
+class PairDb:
+    """Database of 2-row Stockholm alignments prepared for the pair-HMM lattice."""
+
+    def __init__(self, path):
+        h = lib.dnab_pair_db_load(os.fspath(path).encode())
+        if not h:
+            raise _err()
+        self._h = h
+
+    def __len__(self):
+        return lib.dnab_pair_db_count(self._h)
+
+    def alignment(self, i):
+        """(in tokens, out tokens, env_a, env_b) as numpy arrays."""
+        n_in, n_out = lib.dnab_pair_db_in_len(self._h, i), lib.dnab_pair_db_out_len(self._h, i)
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dtype=dt)
+        return (arr(lib.dnab_pair_db_in(self._h, i), n_in, np.uint8), arr(lib.dnab_pair_db_out(self._h, i), n_out, np.uint8),
+                arr(lib.dnab_pair_db_env_a(self._h, i), n_in + 1, np.int32),
+                arr(lib.dnab_pair_db_env_b(self._h, i), n_out + 1, np.int32))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.dnab_pair_db_free(self._h)
+            self._h = None
+
+
+def pairhmm_fb_batch(params, aligns, strict=False, device=0):
+    """aligns: list of (in_tok, out_tok, env_a, env_b). Returns (fwd_ll, back_ll, [MutatorCounts], kernel_ms)."""
+    n = len(aligns)
+    in_off = np.zeros(n + 1, dtype=np.int64)
+    out_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(a[0]) for a in aligns], out=in_off[1:])
+    np.cumsum([len(a[1]) for a in aligns], out=out_off[1:])
+    cat = lambda k, dt: np.ascontiguousarray(np.concatenate([a[k] for a in aligns]).astype(dt)) if n else np.zeros(1, dtype=dt)
+    in_tok, out_tok, env_a, env_b = cat(0, np.uint8), cat(1, np.uint8), cat(2, np.int32), cat(3, np.int32)
+    if len(in_tok) == 0:
+        in_tok = np.zeros(1, dtype=np.uint8)
+    if len(out_tok) == 0:
+        out_tok = np.zeros(1, dtype=np.uint8)
+    fwd = np.zeros(n, dtype=np.float64)
+    back = np.zeros(n, dtype=np.float64)
+    counts = (MutatorCounts * max(n, 1))()
+    ms = C.c_double(0)
+    rc = lib.dnab_pairhmm_fb_batch(int(device), C.byref(params), int(bool(strict)), n, _ptr(in_tok), _ptr(in_off), _ptr(out_tok),
+                                   _ptr(out_off), _ptr(env_a), _ptr(env_b), _ptr(fwd), _ptr(back),
+                                   C.cast(counts, _vp), C.byref(ms))
+    if rc:
+        raise _err(rc)
+    return fwd, back, [counts[i] for i in range(n)], ms.value
+
+
+def expected_counts(params, db, strict=False, device=0):
+    total = MutatorCounts()
+    ll = C.c_double(0)
+    rc = lib.dnab_expected_counts(int(device), C.byref(params), db._h, int(bool(strict)), C.byref(total), C.byref(ll))
+    if rc:
+        raise _err(rc)
+    return total, ll.value
+
+
+def baum_welch(params, db, strict=False, device=0):
+    fitted = MutatorParams()
+    iters = C.c_int32(0)
+    rc = lib.dnab_baum_welch(int(device), C.byref(params), db._h, int(bool(strict)), C.byref(fitted), C.byref(iters))
+    if rc:
+        raise _err(rc)
+    return fitted, iters.value
 
 
 def pack_reads(reads):

@@ -12,6 +12,7 @@
 #include "capi_error.h"
 #include "host/fasta.h"
 #include "host/machine.h"
+#include "host/pairhmm.h"
 #include "host/tables.h"
 
 namespace dnab {
@@ -26,6 +27,9 @@ struct dnab_machine {
 };
 struct dnab_compiled {
   CompiledTables c;
+};
+struct dnab_pair_db {
+  std::vector<PairAlignment> aligns;
 };
 struct dnab_decoded_set {
   std::vector<std::string> names, seqs;
@@ -210,5 +214,157 @@ const char* dnab_decoded_seq(const dnab_decoded_set* s, int64_t i) { return s->s
 double dnab_decoded_loglike(const dnab_decoded_set* s, int64_t i) { return s->loglike[i]; }
 int32_t dnab_decoded_status(const dnab_decoded_set* s, int64_t i) { return s->status[i]; }
 void dnab_decoded_free(dnab_decoded_set* s) { delete s; }
+
+// ---- pair-HMM forward/backward ------------------------------------------------------------------
+static MutatorParams toParams(const dnab_mutator_params* p) {
+  MutatorParams m;
+  m.pDelOpen = p->p_del_open;
+  m.pDelExtend = p->p_del_extend;
+  m.pTanDup = p->p_tan_dup;
+  m.pTransition = p->p_transition;
+  m.pTransversion = p->p_transversion;
+  m.pLen.assign(p->p_len, p->p_len + p->max_dup_len);
+  m.local = p->local != 0;
+  return m;
+}
+static void fromParams(const MutatorParams& m, dnab_mutator_params* p) {
+  std::memset(p, 0, sizeof *p);
+  p->p_del_open = m.pDelOpen;
+  p->p_del_extend = m.pDelExtend;
+  p->p_tan_dup = m.pTanDup;
+  p->p_transition = m.pTransition;
+  p->p_transversion = m.pTransversion;
+  p->max_dup_len = (int32_t)m.maxDupLen();
+  for (size_t i = 0; i < m.pLen.size() && i < DNAB_MAX_DUP; ++i) p->p_len[i] = m.pLen[i];
+  p->local = m.local ? 1 : 0;
+}
+static void fromCounts(const MutatorCounts& m, dnab_mutator_counts* c) {
+  std::memset(c, 0, sizeof *c);
+  c->n_del_open = m.nDelOpen;
+  c->n_tan_dup = m.nTanDup;
+  c->n_no_gap = m.nNoGap;
+  c->n_del_extend = m.nDelExtend;
+  c->n_del_end = m.nDelEnd;
+  c->max_dup_len = (int32_t)m.nLen.size();
+  for (size_t i = 0; i < m.nLen.size() && i < DNAB_MAX_DUP; ++i) c->n_len[i] = m.nLen[i];
+  for (int i = 0; i < 16; ++i) c->n_sub[i] = m.nSub[i];
+}
+static MutatorCounts toCounts(const dnab_mutator_counts* c) {
+  MutatorCounts m((size_t)c->max_dup_len);
+  m.nDelOpen = c->n_del_open;
+  m.nTanDup = c->n_tan_dup;
+  m.nNoGap = c->n_no_gap;
+  m.nDelExtend = c->n_del_extend;
+  m.nDelEnd = c->n_del_end;
+  for (int i = 0; i < c->max_dup_len; ++i) m.nLen[i] = c->n_len[i];
+  for (int i = 0; i < 16; ++i) m.nSub[i] = c->n_sub[i];
+  return m;
+}
+static char* dupString(const std::string& s) {
+  char* out = (char*)std::malloc(s.size() + 1);
+  if (out) std::memcpy(out, s.c_str(), s.size() + 1);
+  return out;
+}
+
+void dnab_mutator_params_from_flags(const dnab_error_flags* f, dnab_mutator_params* out) {
+  if (!f || !out) return;
+  fromParams(MutatorParams::fromFlags(f->length, f->sub_prob, f->iv_ratio, f->dup_prob, f->del_open, f->del_ext,
+                                      f->global != 0), out);
+}
+char* dnab_mutator_params_json(const dnab_mutator_params* p) { return p ? dupString(toParams(p).asJSON()) : nullptr; }
+char* dnab_mutator_counts_json(const dnab_mutator_counts* c) { return c ? dupString(toCounts(c).asJSON()) : nullptr; }
+const double* dnab_lse_table(int32_t* n_entries) {
+  const std::vector<double>& t = logSumExpLookupTable();
+  if (n_entries) *n_entries = (int32_t)t.size();
+  return t.data();
+}
+
+dnab_pair_db* dnab_pair_db_load(const char* stockholm_path) {
+  if (!stockholm_path) return nullptr;
+  return guarded(
+      [&]() {
+        auto* db = new dnab_pair_db();
+        try {
+          for (const auto& s : readStockholmDatabase(stockholm_path)) db->aligns.push_back(makePairAlignment(s));
+        } catch (...) {
+          delete db;
+          throw;
+        }
+        return db;
+      },
+      (dnab_pair_db*)nullptr);
+}
+int64_t dnab_pair_db_count(const dnab_pair_db* db) { return db ? (int64_t)db->aligns.size() : 0; }
+int32_t dnab_pair_db_in_len(const dnab_pair_db* db, int64_t i) { return (int32_t)db->aligns[i].in.size(); }
+int32_t dnab_pair_db_out_len(const dnab_pair_db* db, int64_t i) { return (int32_t)db->aligns[i].out.size(); }
+const uint8_t* dnab_pair_db_in(const dnab_pair_db* db, int64_t i) { return db->aligns[i].in.data(); }
+const uint8_t* dnab_pair_db_out(const dnab_pair_db* db, int64_t i) { return db->aligns[i].out.data(); }
+const int32_t* dnab_pair_db_env_a(const dnab_pair_db* db, int64_t i) { return db->aligns[i].a.data(); }
+const int32_t* dnab_pair_db_env_b(const dnab_pair_db* db, int64_t i) { return db->aligns[i].b.data(); }
+void dnab_pair_db_free(dnab_pair_db* db) { delete db; }
+
+int dnab_pairhmm_fb_batch(int device, const dnab_mutator_params* p, int strict, int64_t n_align, const uint8_t* in_tok,
+                          const int64_t* in_off, const uint8_t* out_tok, const int64_t* out_off, const int32_t* env_a,
+                          const int32_t* env_b, double* fwd_ll, double* back_ll, dnab_mutator_counts* counts,
+                          double* kernel_ms) {
+  if (!p || n_align < 0 || p->max_dup_len < 0 || p->max_dup_len > DNAB_MAX_DUP) {
+    setLastError("dnab_pairhmm_fb_batch: bad argument");
+    return DNAB_EINVAL;
+  }
+  return guarded(
+      [&]() {
+        std::vector<PairAlignment> aligns((size_t)n_align);
+        for (int64_t i = 0; i < n_align; ++i) {
+          PairAlignment& a = aligns[(size_t)i];
+          a.in.assign(in_tok + in_off[i], in_tok + in_off[i + 1]);
+          a.out.assign(out_tok + out_off[i], out_tok + out_off[i + 1]);
+          a.a.assign(env_a + in_off[i] + i, env_a + in_off[i + 1] + i + 1);
+          a.b.assign(env_b + out_off[i] + i, env_b + out_off[i + 1] + i + 1);
+        }
+        std::vector<double> f, b;
+        std::vector<MutatorCounts> c;
+        if (!pairHmmFwdBackBatch(device, toParams(p), strict != 0, aligns, f, b, c, kernel_ms)) return (int)DNAB_ECUDA;
+        for (int64_t i = 0; i < n_align; ++i) {
+          if (fwd_ll) fwd_ll[i] = f[(size_t)i];
+          if (back_ll) back_ll[i] = b[(size_t)i];
+          if (counts) fromCounts(c[(size_t)i], &counts[i]);
+        }
+        return (int)DNAB_OK;
+      },
+      (int)DNAB_EINVAL);
+}
+
+int dnab_expected_counts(int device, const dnab_mutator_params* p, const dnab_pair_db* db, int strict,
+                         dnab_mutator_counts* total, double* loglike) {
+  if (!p || !db || !total || !loglike) return DNAB_EINVAL;
+  return guarded(
+      [&]() {
+        MutatorCounts t;
+        double ll = 0;
+        if (!expectedCounts(device, toParams(p), db->aligns, strict != 0, t, ll)) return (int)DNAB_ECUDA;
+        fromCounts(t, total);
+        *loglike = ll;
+        return (int)DNAB_OK;
+      },
+      (int)DNAB_EINVAL);
+}
+
+int dnab_baum_welch(int device, const dnab_mutator_params* init, const dnab_pair_db* db, int strict,
+                    dnab_mutator_params* fitted, int32_t* iterations) {
+  if (!init || !db || !fitted) return DNAB_EINVAL;
+  return guarded(
+      [&]() {
+        const MutatorParams start = toParams(init);
+        MutatorCounts prior(start.maxDupLen());
+        prior.initLaplace();
+        MutatorParams fit;
+        int iters = 0;
+        if (!baumWelchParams(device, start, prior, db->aligns, strict != 0, fit, &iters)) return (int)DNAB_ECUDA;
+        fromParams(fit, fitted);
+        if (iterations) *iterations = iters;
+        return (int)DNAB_OK;
+      },
+      (int)DNAB_EINVAL);
+}
 
 }  // extern "C"

@@ -72,6 +72,7 @@ struct dnab_decoder {
   // user overrides
   uint32_t wantC = 0, wantThreads = 0, wantTMode = 0;  // tMode: 0 auto, 1 smem, 2 global
   uint32_t wantBlockMode = 0;   // transition table: 0 auto, 1 shared memory, 2 global memory
+  uint32_t idleSleepNs = 100;
   uint32_t wantSPrevMode = 0;   // S(pos-1): 0 auto, 1 shared memory, 2 global scratch
   uint32_t wantPartition = 0;   // 0/1 index-order runs + in-degree sort (default), 2 DFS runs unsorted, 3 DFS chunks dealt round-robin + sort, 4 DFS runs + sort
   // device-resident structures for the current plan
@@ -404,6 +405,7 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
     fa.lay = makeLayout(d->plan.M, d->k, d->plan.tInSmem, d->plan.blocksInSmem ? d->plan.sliceWords : 0,
                         (uint32_t)d->plan.maxLen, d->plan.sPrevGlobal);
     fa.nReads = n;
+    fa.idleSleepNs = d->idleSleepNs;
     fa.maxLen = maxLen;
     fa.packed = dPacked;
     fa.byteOff = dByteOff + at;
@@ -567,7 +569,8 @@ int dnab_decoder_configure(dnab_decoder* d, uint32_t cluster_size, uint32_t thre
   if (!d) return DNAB_EINVAL;
   d->wantC = cluster_size;
   d->wantThreads = threads_per_cta;
-  d->wantTMode = t_in_smem_mode;
+  d->wantTMode = t_in_smem_mode % 10;
+  if (t_in_smem_mode >= 10) d->idleSleepNs = (t_in_smem_mode / 10) * 20;  // tuning hook: tens digit * 20 ns
   d->plan = LaunchPlan();
   return DNAB_OK;
 }

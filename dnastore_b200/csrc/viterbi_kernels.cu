@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
               if (++spins > (1u << 22)) __trap();  // never hang the GPU: a stuck closure is a bug
               // take this warp's dirty bits: lane j looks after the warp's j-th group (myGroups <= 32)
               uint32_t taken = 0;
+              bool didWork = false;
               for (uint32_t base = 0; base < myGroups; base += 32) {
                 const uint32_t j = base + lane;
                 const uint32_t aWord = c.aFlag + 4 * (warp + j * nWarps);
@@ -428,6 +429,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                 }
                 const uint32_t n = __shfl_sync(0xFFFFFFFFu, incl, 31);
                 if (n == 0) continue;
+                didWork = true;
                 uint32_t at = incl - cnt;
                 const uint32_t stateBase = 32 * (warp + j * nWarps);
                 while (taken) {
@@ -444,6 +446,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                 if (dbgOn && tid == 0) dbgWork += n;
               }
               if (dbgOn && tid == 0) dbgIters++;
+              // an idle warp backs off: spinning warps would steal issue slots from the warps that relax
+              if (!didWork) __nanosleep(args.idleSleepNs);
             }
           } while (__syncthreads_or(ldsVolatile32(c.aPending) != 0u));
           if (C == 1) break;

@@ -76,6 +76,7 @@ struct FillArgs {
   SmemLayout lay;
   int64_t nReads;
   int32_t maxLen;            // pred stride: every read owns (maxLen+1) columns of records
+  uint32_t idleSleepNs;      // back-off of a warp whose closure sweep found nothing to do
   const uint8_t* packed;     // 2-bit reads
   const int64_t* byteOff;    // [nReads]
   const int32_t* readLen;    // [nReads]

@@ -206,6 +206,72 @@ double dnab_decoded_loglike(const dnab_decoded_set* s, int64_t i);
 int32_t dnab_decoded_status(const dnab_decoded_set* s, int64_t i);
 void dnab_decoded_free(dnab_decoded_set* s);
 
+
+/* ------------------------------------------------------------------------
+ * Pair-HMM forward / backward / expected counts: the reference's
+ * only forward-backward, over the (original DNA x observed DNA) lattice of a 2-row
+ * alignment, used to train the error model (--error-counts / --fit-error).
+ *   ForwardMatrix / BackwardMatrix / FwdBackMatrix::counts   src/fwdback.cpp:43-188
+ *   expectedCounts / baumWelchParams                         src/fwdback.cpp:190-230
+ *   MutatorParams / MutatorCounts                            src/mutator.h:9-67
+ *   log_sum_exp (lookup table)                               src/logsumexp.h:19-86
+ * ---------------------------------------------------------------------- */
+#define DNAB_MAX_DUP 16
+
+typedef struct dnab_mutator_params {      /* MutatorParams, src/mutator.h:9-31 */
+  double p_del_open, p_del_extend, p_tan_dup, p_transition, p_transversion;
+  double p_len[DNAB_MAX_DUP];
+  int32_t max_dup_len;                    /* pLen.size() */
+  int32_t local;
+} dnab_mutator_params;
+
+typedef struct dnab_mutator_counts {      /* MutatorCounts, src/mutator.h:43-67 */
+  double n_del_open, n_tan_dup, n_no_gap, n_del_extend, n_del_end;
+  double n_len[DNAB_MAX_DUP];
+  double n_sub[16];                       /* nSub[original base * 4 + observed base] */
+  int32_t max_dup_len;
+  int32_t reserved;
+} dnab_mutator_counts;
+
+/* MutatorParams as the CLI builds it from its flags (t/dnastore.cpp:119-129). */
+void dnab_mutator_params_from_flags(const dnab_error_flags* f, dnab_mutator_params* out);
+char* dnab_mutator_params_json(const dnab_mutator_params* p);   /* MutatorParams::writeJSON text; dnab_free() it */
+char* dnab_mutator_counts_json(const dnab_mutator_counts* c);   /* MutatorCounts::writeJSON text; dnab_free() it */
+/* The log(1+exp(-x)) lookup table the device uses (100,001 entries, step 1e-4). */
+const double* dnab_lse_table(int32_t* n_entries);
+
+/* A database of 2-row Stockholm alignments prepared for the lattice (readStockholmDatabase,
+ * src/stockholm.cpp:154-167; Alignment + GuideAlignmentEnvelope, src/alignpath.cpp:189-204,237-265):
+ * tokens of both rows and the envelope coordinates a[0..inLen], b[0..outLen] with
+ * inRange(ip,op) <=> |a[ip]-b[op]| <= maxDistance (src/alignpath.h:48-53). */
+typedef struct dnab_pair_db dnab_pair_db;
+dnab_pair_db* dnab_pair_db_load(const char* stockholm_path);
+int64_t dnab_pair_db_count(const dnab_pair_db* db);
+int32_t dnab_pair_db_in_len(const dnab_pair_db* db, int64_t i);
+int32_t dnab_pair_db_out_len(const dnab_pair_db* db, int64_t i);
+const uint8_t* dnab_pair_db_in(const dnab_pair_db* db, int64_t i);     /* tokens 0..3 */
+const uint8_t* dnab_pair_db_out(const dnab_pair_db* db, int64_t i);
+const int32_t* dnab_pair_db_env_a(const dnab_pair_db* db, int64_t i);  /* in_len+1 entries */
+const int32_t* dnab_pair_db_env_b(const dnab_pair_db* db, int64_t i);  /* out_len+1 entries */
+void dnab_pair_db_free(dnab_pair_db* db);
+
+/* Forward, backward and expected counts of a batch of alignments on `device` (one GPU thread per
+ * alignment).  Alignment i: tokens in_tok[in_off[i]..in_off[i+1]), out_tok[out_off[i]..out_off[i+1]),
+ * envelope env_a[in_off[i]+i ..] (in_len+1 entries) and env_b[out_off[i]+i ..] (out_len+1 entries).
+ * strict != 0 <=> --strict-guides (maxDistance 0, else maxDupLen; src/fwdback.cpp:17).
+ * fwd_ll = ForwardMatrix::loglike, back_ll = BackwardMatrix::loglike (bit-identical to the
+ * reference: same lookup table, same operand order); counts[i] = FwdBackMatrix::counts(). */
+int dnab_pairhmm_fb_batch(int device, const dnab_mutator_params* p, int strict, int64_t n_align, const uint8_t* in_tok,
+                          const int64_t* in_off, const uint8_t* out_tok, const int64_t* out_off, const int32_t* env_a,
+                          const int32_t* env_b, double* fwd_ll, double* back_ll, dnab_mutator_counts* counts,
+                          double* kernel_ms);
+/* expectedCounts (src/fwdback.cpp:190-209): counts summed and log-likelihoods added in database order. */
+int dnab_expected_counts(int device, const dnab_mutator_params* p, const dnab_pair_db* db, int strict,
+                         dnab_mutator_counts* total, double* loglike);
+/* baumWelchParams (src/fwdback.cpp:211-230) with the Laplace prior the CLI uses (t/dnastore.cpp:137-139). */
+int dnab_baum_welch(int device, const dnab_mutator_params* init, const dnab_pair_db* db, int strict,
+                    dnab_mutator_params* fitted, int32_t* iterations);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,13 @@
 //   refdriver encode --machine M.json [--compose ...]   (payload symbol strings on stdin,
 //       one per line; one encoded DNA string per line on stdout)
 //   refdriver compose --machine M.json --compose ... --save out.json
+//   refdriver fb [-l N --sub p --iv r --dup p --delopen p --delext p] [--strict] --stk FILE
+//       pair-HMM forward/backward (FwdBackMatrix, fwdback.cpp:118-188) per alignment:
+//       idx \t fwd loglike (hexfloat) \t back loglike (hexfloat) \t counts (%.17g: nDelOpen nTanDup
+//       nNoGap nDelExtend nDelEnd, nLen[maxDupLen], nSub[16] row-major)
+//   refdriver fit  [...same flags...] [--strict] --stk FILE
+//       baumWelchParams with the Laplace prior the CLI uses (t/dnastore.cpp:135-140); prints the
+//       fitted parameters with %.17g
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,6 +46,7 @@
 #include "fastseq.h"
 #include "mutator.h"
 #include "viterbi.h"
+#include "fwdback.h"
 
 using namespace std;
 
@@ -56,7 +64,8 @@ int main(int argc, char** argv) {
     return 2;
   }
   const string mode = argv[1];
-  string machineFile, fasta, cellsFile, saveFile;
+  string machineFile, fasta, cellsFile, saveFile, stkFile;
+  bool strict = false;
   vector<string> comps;
   int len = 12;
   double sub = .01, iv = 10, dup = .001, delOpen = .001, delExt = .01;
@@ -82,6 +91,8 @@ int main(int argc, char** argv) {
     else if (a == "--delopen") delOpen = atof(next().c_str());
     else if (a == "--delext") delExt = atof(next().c_str());
     else if (a == "--global") global = true;
+    else if (a == "--strict") strict = true;
+    else if (a == "--stk") stkFile = next();
     else if (a == "--path") wantPath = true;
     else {
       cerr << "unknown argument " << a << endl;
@@ -90,6 +101,40 @@ int main(int argc, char** argv) {
   }
   logger.setVerbose(0);
   logger.colorOff();
+
+  if (mode == "fb" || mode == "fit") {
+    MutatorParams mut;  // exactly as t/dnastore.cpp:119-129
+    mut.initMaxDupLen(len / 2);
+    mut.pTanDup = dup;
+    mut.pDelOpen = delOpen;
+    mut.pDelExtend = delExt;
+    mut.pTransition = sub * iv / (1 + iv);
+    mut.pTransversion = sub / (1 + iv);
+    mut.local = !global;
+    const list<Stockholm> db = readStockholmDatabase(stkFile.c_str());
+    if (mode == "fit") {
+      MutatorCounts prior(mut);
+      prior.initLaplace();
+      const MutatorParams fit = baumWelchParams(mut, prior, db, strict);
+      printf("%.17g %.17g %.17g %.17g %.17g", fit.pDelOpen, fit.pDelExtend, fit.pTanDup, fit.pTransition, fit.pTransversion);
+      for (double p : fit.pLen) printf(" %.17g", p);
+      printf("\n");
+      return 0;
+    }
+    size_t idx = 0;
+    for (const auto& stock : db) {
+      const FwdBackMatrix fb(mut, stock, strict);
+      const MutatorCounts c = fb.counts();
+      printf("%zu\t%a\t%a\t%.17g %.17g %.17g %.17g %.17g", idx++, fb.fwd.loglike, fb.back.loglike, c.nDelOpen, c.nTanDup,
+             c.nNoGap, c.nDelExtend, c.nDelEnd);
+      for (double v : c.nLen) printf(" %.17g", v);
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) printf(" %.17g", c.nSub[i][j]);
+      printf("\n");
+    }
+    return 0;
+  }
+
   const Machine machine = loadMachine(machineFile, comps);
 
   if (mode == "compose") {
