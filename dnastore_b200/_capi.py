@@ -420,7 +420,7 @@ class Decoder:
     def debug_counters(self):
         out = np.zeros(16, dtype=np.uint64)
         lib.dnab_decoder_debug_counters(self._h, _ptr(out))
-        names = ["columns", "sweeps", "work_rank0", "cyc_emit", "cyc_closure", "cyc_pred", "rounds", "cyc_dense", "cyc_syncwait", "cyc_compact", "cyc_proc", "cyc_clusterwait"]
+        names = ["columns", "sweeps", "work_rank0", "cyc_emit", "cyc_closure", "cyc_pred", "rounds", "cyc_dense", "dirty_first", "cyc_compact", "cyc_proc", "cyc_clusterwait", "cyc_pushwait", "hops_t0"]
         return {n: int(v) for n, v in zip(names, out)}
 
     def reset_timing(self):

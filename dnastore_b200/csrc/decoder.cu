@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -51,6 +52,7 @@ struct DevBuf {
 
 struct LaunchPlan {
   uint32_t C = 0, M = 0, threads = 0, tInSmem = 0, blocksInSmem = 0, sPrevGlobal = 0, sliceWords = 0, smemBytes = 0, nClusters = 0;
+  uint32_t push = 0, outInSmem = 0, outBytes = 0, chunkBytes = 0, queueCap = 0;  // push kernel (viterbi_fill_push.cu)
   int32_t maxLen = -1;
 };
 
@@ -73,12 +75,15 @@ struct dnab_decoder {
   uint32_t wantC = 0, wantThreads = 0, wantTMode = 0;  // tMode: 0 auto, 1 smem, 2 global
   uint32_t wantBlockMode = 0;   // transition table: 0 auto, 1 shared memory, 2 global memory
   uint32_t idleSleepNs = 100;
+  uint32_t tailN = 128, tailHops = 64;  // push kernel: lockstep-chain mode (tuning: DNAB_TAIL_N / DNAB_TAIL_HOPS)
   uint32_t wantSPrevMode = 0;   // S(pos-1): 0 auto, 1 shared memory, 2 global scratch
+  uint32_t wantKernel = 0;      // 0 push kernel (viterbi_fill_push.cu), 1 pull kernel (viterbi_kernels.cu)
   uint32_t wantPartition = 0;   // 0/1 index-order runs + in-degree sort (default), 2 DFS runs unsorted, 3 DFS chunks dealt round-robin + sort, 4 DFS runs + sort
   // device-resident structures for the current plan
   LaunchPlan plan;
   DevTables dev{};
   DevBuf<uint32_t> dBlocks, dBlockOff, dSliceOff, dOrigId;
+  DevBuf<uint32_t> dInChunks, dInChunkOff, dOutTable, dOutSliceOff;
   DevBuf<uint8_t> dSymChar;
   // scratch
   DevBuf<uint8_t> dPred;
@@ -270,10 +275,242 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
   return DNAB_OK;
 }
 
+// Tables of the push kernel for a given partition and CTA size (formats: viterbi_device.cuh).
+struct PushTables {
+  uint32_t chunkStates = 0, nChunks = 0, maxChunkBytes = 0, maxOutBytes = 0;
+  std::vector<uint32_t> inChunks, inChunkOff, outTable, outSliceOff;
+};
+
+static int buildPushTables(const dnab_decoder* d, const Partition& P, uint32_t chunkStates, PushTables& T) {
+  const uint32_t threads = chunkStates;  // (states per chunk = kPushStatesPerThread * threads per CTA)
+  const uint32_t N = d->nStates, k = d->k, C = P.C, M = P.M, Np = C * M;
+  std::vector<std::vector<uint32_t>> outs(Np);  // out-edge words, "other CTA" bit added below
+  std::vector<char> hasNullOut(N, 0);
+  for (uint32_t s = 0; s < N; ++s) {
+    const uint32_t dg = P.newOf[s];
+    for (uint32_t e = d->emitOff[s]; e < d->emitOff[s + 1]; ++e)
+      outs[P.newOf[d->emitSrc[e]]].push_back(peMake(dg % M, dg / M, false, d->emitSym[e], 1));
+    for (uint32_t e = d->nullOff[s]; e < d->nullOff[s + 1]; ++e) {
+      outs[P.newOf[d->nullSrc[e]]].push_back(peMake(dg % M, dg / M, false, d->nullSym[e], 0));
+      hasNullOut[d->nullSrc[e]] = 1;
+    }
+  }
+  T.chunkStates = threads;
+  T.nChunks = (M + threads - 1) / threads;
+  T.inChunks.clear();
+  T.inChunkOff.assign((size_t)C * (T.nChunks + 1), 0);
+  T.maxChunkBytes = 0;
+  const uint32_t offWords = (threads + 1 + 1) / 2;
+  for (uint32_t r = 0; r < C; ++r) {
+    for (uint32_t j = 0; j < T.nChunks; ++j) {
+      const uint32_t start = (uint32_t)T.inChunks.size();  // multiple of 4 words
+      T.inChunkOff[(size_t)r * (T.nChunks + 1) + j] = start;
+      T.inChunks.resize(start + offWords, 0);
+      std::vector<uint16_t> recOff(threads + 1, 0);
+      uint32_t at = 0;
+      for (uint32_t t = 0; t < threads; ++t) {
+        recOff[t] = (uint16_t)at;
+        const uint32_t i = j * threads + t;
+        if (i >= M) continue;
+        const uint32_t s = P.origOf[r * M + i];
+        if (s == 0xFFFFFFFFu) {
+          T.inChunks.push_back(kInPad << 7);
+          at += 1;
+          continue;
+        }
+        const uint32_t nE = d->emitOff[s + 1] - d->emitOff[s], nN = d->nullOff[s + 1] - d->nullOff[s];
+        uint32_t h = nE | ((nE + nN) << 7) | ((uint32_t)d->mdl[s] << 15) | ((uint32_t)hasNullOut[s] << 30);
+        for (uint32_t i2 = 0; i2 < d->mdl[s]; ++i2) h |= (uint32_t)(d->ctx[(size_t)s * k + i2] & 3u) << (18 + 2 * i2);
+        T.inChunks.push_back(h);
+        auto pushIn = [&](uint32_t src, uint32_t sym, uint32_t base) {
+          const uint32_t sg = P.newOf[src];
+          T.inChunks.push_back(peMake(sg % M, sg / M, sg / M != r, sym, base));
+        };
+        for (uint32_t e = d->emitOff[s]; e < d->emitOff[s + 1]; ++e) pushIn(d->emitSrc[e], d->emitSym[e], d->emitBase[e]);
+        for (uint32_t e = d->nullOff[s]; e < d->nullOff[s + 1]; ++e) pushIn(d->nullSrc[e], d->nullSym[e], 0);
+        at += 1 + nE + nN;
+        if (at > 65535) {
+          setLastError("in-table chunk exceeds 16-bit record offsets; use fewer threads per CTA");
+          return DNAB_EINVAL;
+        }
+      }
+      recOff[threads] = (uint16_t)at;
+      std::memcpy(&T.inChunks[start], recOff.data(), (threads + 1) * sizeof(uint16_t));
+      while (T.inChunks.size() % 4) T.inChunks.push_back(0);
+      T.maxChunkBytes = std::max<uint32_t>(T.maxChunkBytes, ((uint32_t)T.inChunks.size() - start) * 4);
+    }
+    T.inChunkOff[(size_t)r * (T.nChunks + 1) + T.nChunks] = (uint32_t)T.inChunks.size();
+  }
+  T.outTable.clear();
+  T.outSliceOff.assign(C + 1, 0);
+  T.maxOutBytes = 0;
+  const uint32_t outOffWords = (M + 1 + 1) / 2;
+  for (uint32_t r = 0; r < C; ++r) {
+    const uint32_t start = (uint32_t)T.outTable.size();
+    T.outSliceOff[r] = start;
+    T.outTable.resize(start + outOffWords, 0);
+    std::vector<uint16_t> off(M + 1, 0);
+    uint32_t at = 0;
+    for (uint32_t i = 0; i < M; ++i) {
+      off[i] = (uint16_t)at;
+      for (uint32_t w : outs[r * M + i]) {
+        T.outTable.push_back(peRank(w) != r ? (w | (1u << 20)) : w);
+        ++at;
+      }
+      if (at > 65535) {
+        setLastError("out-table of one CTA exceeds 16-bit offsets; use a larger cluster");
+        return DNAB_EINVAL;
+      }
+    }
+    off[M] = (uint16_t)at;
+    std::memcpy(&T.outTable[start], off.data(), (M + 1) * sizeof(uint16_t));
+    T.maxOutBytes = std::max<uint32_t>(T.maxOutBytes, ((uint32_t)T.outTable.size() - start) * 4);
+  }
+  T.outSliceOff[C] = (uint32_t)T.outTable.size();
+  return DNAB_OK;
+}
+
+// Threads per CTA of the push kernel: a dense pass takes ceil(M / (kPushStatesPerThread * threads)) steps, so
+// the count is chosen to fill the last step (7,779 states: 5 steps of 2 x 800 rather than 6 of 2 x 768).
+static uint32_t pushThreads(const dnab_decoder* d, uint32_t M) {
+  if (d->wantThreads) return std::min<uint32_t>(1024, (d->wantThreads + 31) / 32 * 32);
+  const uint32_t target = M <= 1024 ? 128 : M <= 2048 ? 256 : M <= 6000 ? 512 : 800;
+  const uint32_t perStep = kPushStatesPerThread * target;
+  const uint32_t steps = (M + perStep - 1) / perStep;
+  const uint32_t threads = ((M + kPushStatesPerThread * steps - 1) / (kPushStatesPerThread * steps) + 31) / 32 * 32;
+  return std::max<uint32_t>(32, std::min<uint32_t>(1024, threads));
+}
+
+static int buildPlanPush(dnab_decoder* d, int32_t planLen) {
+  const uint32_t N = d->nStates, k = d->k;
+  LaunchPlan best;
+  Partition P;
+  PushTables T;
+  std::vector<uint32_t> cands = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16};
+  if (d->wantC >= 1 && d->wantC <= (uint32_t)kMaxCluster) cands = {d->wantC};
+  // Preference: the smallest cluster whose CTAs hold S, D and the out-table in shared memory (more reads
+  // in flight beats more SMs per read); then S(pos-1) and the T columns when they fit too.  A machine
+  // too large for that keeps its out-table in global memory (second sweep over the candidates).
+  for (uint32_t needOut = 1; needOut + 1 > 0 && !best.C; --needOut) {
+    if (d->wantBlockMode == 2 && needOut) continue;
+    if (d->wantBlockMode == 1 && !needOut) break;
+    for (uint32_t C : cands) {
+      const uint32_t M = (N + C - 1) / C;
+      if (M > 65535) continue;
+      const uint32_t threads = pushThreads(d, M);
+      if (makePushLayout(M, k, 0, 0, 0, 64, 1, (uint32_t)planLen, 1024).total > d->smemOptin) continue;
+      int rc = buildPartition(d, C, P);
+      if (rc != DNAB_OK) return rc;
+      rc = buildPushTables(d, P, threads * kPushStatesPerThread, T);
+      if (rc != DNAB_OK) {
+        if (d->wantC) return rc;
+        continue;
+      }
+      // (S(pos-1) in smem, T in smem, full-size level queue); a short queue defers states to the next level
+      const uint32_t opts[6][3] = {{1, 1, 1}, {1, 0, 1}, {0, 1, 1}, {0, 0, 1}, {0, 1, 0}, {0, 0, 0}};
+      for (const auto& o : opts) {
+        const uint32_t sIn = o[0], tIn = (k == 0) ? 0 : o[1];
+        const uint32_t qCap = o[2] ? M : std::max<uint32_t>(1024, M / 4);
+        if (d->wantSPrevMode == 1 && !sIn) continue;
+        if (d->wantSPrevMode == 2 && sIn) continue;
+        if (d->wantTMode == 1 && k && !tIn) continue;
+        if (d->wantTMode == 2 && tIn) continue;
+        const uint32_t smem =
+            makePushLayout(M, k, tIn, sIn, needOut ? T.maxOutBytes : 0, T.maxChunkBytes, T.nChunks, (uint32_t)planLen, qCap).total;
+        if (smem <= d->smemOptin) {
+          best.C = C;
+          best.M = M;
+          best.threads = threads;
+          best.tInSmem = tIn;
+          best.sPrevGlobal = sIn ? 0 : 1;
+          best.outInSmem = needOut;
+          best.outBytes = needOut ? T.maxOutBytes : 0;
+          best.chunkBytes = T.maxChunkBytes;
+          best.queueCap = qCap;
+          best.smemBytes = smem;
+          best.push = 1;
+          break;
+        }
+      }
+      if (best.C) break;
+    }
+    if (!needOut) break;
+  }
+  if (!best.C) {
+    setLastError("machine does not fit: " + std::to_string(N) +
+                 " states need more shared memory than a 16-CTA cluster has (or the requested configuration is infeasible)");
+    return DNAB_EINVAL;
+  }
+  best.maxLen = planLen;
+  const uint32_t C = best.C, M = best.M;
+  P.blocks.resize(P.blocks.size() + 8, 0);
+  T.inChunks.resize(T.inChunks.size() + 4, 0);
+  T.outTable.resize(T.outTable.size() + 4, 0);
+  CUDA_TRY(d->dBlocks.upload(P.blocks));  // the traceback kernel decodes records against the state blocks
+  CUDA_TRY(d->dBlockOff.upload(P.blockOff));
+  CUDA_TRY(d->dSliceOff.upload(P.sliceOff));
+  CUDA_TRY(d->dOrigId.upload(P.origOf));
+  CUDA_TRY(d->dSymChar.upload(d->symChar));
+  CUDA_TRY(d->dInChunks.upload(T.inChunks));
+  CUDA_TRY(d->dInChunkOff.upload(T.inChunkOff));
+  CUDA_TRY(d->dOutTable.upload(T.outTable));
+  CUDA_TRY(d->dOutSliceOff.upload(T.outSliceOff));
+
+  DevTables& t = d->dev;
+  t = DevTables{};
+  t.nStates = N;
+  t.M = M;
+  t.C = C;
+  t.k = k;
+  t.local = d->local;
+  t.nSyms = (uint32_t)d->symChar.size();
+  t.startG = P.newOf[0];
+  t.endG = P.newOf[N - 1];
+  t.tInSmem = best.tInSmem;
+  t.blocksInSmem = 0;
+  t.sPrevGlobal = best.sPrevGlobal;
+  t.sPrevInSmem = best.sPrevGlobal ? 0 : 1;
+  t.outInSmem = best.outInSmem;
+  t.chunkStates = T.chunkStates;
+  t.nChunks = T.nChunks;
+  t.maxChunkBytes = T.maxChunkBytes;
+  t.maxOutBytes = T.maxOutBytes;
+  t.blocks = d->dBlocks.p;
+  t.blockOff = d->dBlockOff.p;
+  t.sliceOff = d->dSliceOff.p;
+  t.origId = d->dOrigId.p;
+  t.symChar = d->dSymChar.p;
+  t.inChunks = d->dInChunks.p;
+  t.inChunkOff = d->dInChunkOff.p;
+  t.outTable = d->dOutTable.p;
+  t.outSliceOff = d->dOutSliceOff.p;
+  for (int i = 0; i < kMaxSyms; ++i) t.symScore[i] = i < (int)d->symScore.size() ? d->symScore[i] : 0.;
+  std::memcpy(t.sub, d->sub, sizeof t.sub);
+  std::memcpy(t.len, d->len, sizeof t.len);
+  t.noGap = d->noGap;
+  t.delOpen = d->delOpen;
+  t.delExtend = d->delExtend;
+  t.delEnd = d->delEnd;
+  t.tanDup = d->tanDup;
+
+  int nClusters = 0;
+  CUDA_TRY(queryMaxClustersPush(t, best.threads, best.smemBytes, &nClusters));
+  if (nClusters < 1) {
+    setLastError("no cluster of size " + std::to_string(C) + " can be resident on this device");
+    return DNAB_ECUDA;
+  }
+  best.nClusters = (uint32_t)nClusters;
+  if (!best.tInSmem && k) CUDA_TRY(d->dTScratch.ensure((size_t)nClusters * C * k * M));
+  if (best.sPrevGlobal) CUDA_TRY(d->dSScratch.ensure((size_t)nClusters * 2 * C * M));
+  d->plan = best;
+  return DNAB_OK;
+}
+
 static int buildPlan(dnab_decoder* d, int32_t maxLen) {
   if (d->plan.maxLen >= maxLen && d->plan.C) return DNAB_OK;
   const uint32_t N = d->nStates, k = d->k;
   const int32_t planLen = std::max(maxLen, 1024);
+  if (d->wantKernel == 0) return buildPlanPush(d, planLen);
   // Preference: the smallest cluster that holds the three live columns; within it, keep the T
   // columns and the CTA's slice of the transition table in shared memory when they fit too.
   LaunchPlan best;
@@ -402,10 +639,16 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
   for (int64_t at = 0; at < nReads; at += chunk) {
     const int64_t n = std::min(chunk, nReads - at);
     FillArgs fa{};
-    fa.lay = makeLayout(d->plan.M, d->k, d->plan.tInSmem, d->plan.blocksInSmem ? d->plan.sliceWords : 0,
-                        (uint32_t)d->plan.maxLen, d->plan.sPrevGlobal);
+    if (d->plan.push)
+      fa.play = makePushLayout(d->plan.M, d->k, d->plan.tInSmem, d->plan.sPrevGlobal ? 0 : 1, d->plan.outBytes,
+                               d->plan.chunkBytes, d->dev.nChunks, (uint32_t)d->plan.maxLen, d->plan.queueCap);
+    else
+      fa.lay = makeLayout(d->plan.M, d->k, d->plan.tInSmem, d->plan.blocksInSmem ? d->plan.sliceWords : 0,
+                          (uint32_t)d->plan.maxLen, d->plan.sPrevGlobal);
     fa.nReads = n;
     fa.idleSleepNs = d->idleSleepNs;
+    fa.tailN = std::min<uint32_t>(d->tailN, d->plan.threads);
+    fa.tailHops = d->tailHops;
     fa.maxLen = maxLen;
     fa.packed = dPacked;
     fa.byteOff = dByteOff + at;
@@ -436,7 +679,10 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
     }
     const bool rec = timeIt || pooled;
     if (rec) CUDA_TRY(cudaEventRecord(e0, stream));
-    CUDA_TRY(launchFill(d->dev, fa, nClusters, d->plan.threads, d->plan.smemBytes, stream));
+    if (d->plan.push)
+      CUDA_TRY(launchFillPush(d->dev, fa, nClusters, d->plan.threads, d->plan.smemBytes, stream));
+    else
+      CUDA_TRY(launchFill(d->dev, fa, nClusters, d->plan.threads, d->plan.smemBytes, stream));
     if (rec) CUDA_TRY(cudaEventRecord(e1, stream));
     TracebackArgs ta{};
     ta.nReads = n;
@@ -496,6 +742,8 @@ dnab_decoder* dnab_decoder_create(const dnab_tables* t, int device) {
     delete d;
     return nullptr;
   }
+  if (const char* e = getenv("DNAB_TAIL_N")) d->tailN = (uint32_t)atoi(e);
+  if (const char* e = getenv("DNAB_TAIL_HOPS")) d->tailHops = (uint32_t)atoi(e);
   d->smCount = prop.multiProcessorCount;
   d->smemOptin = prop.sharedMemPerBlockOptin;
   size_t freeB = 0, totalB = 0;
@@ -579,7 +827,8 @@ int dnab_decoder_configure_ex(dnab_decoder* d, uint32_t block_table_mode, uint32
   if (!d) return DNAB_EINVAL;
   d->wantBlockMode = block_table_mode % 10;
   d->wantSPrevMode = block_table_mode / 10;  // tens digit: S(pos-1) placement (0 auto, 1 shared, 2 global)
-  d->wantPartition = partition_mode;
+  d->wantPartition = partition_mode % 10;
+  d->wantKernel = partition_mode / 10;  // tens digit: 0 push kernel (default), 1 pull kernel
   d->plan = LaunchPlan();
   return DNAB_OK;
 }
@@ -598,7 +847,7 @@ int dnab_decoder_get_info(const dnab_decoder* dc, dnab_decoder_info* info) {
   info->threads_per_cta = d->plan.threads;
   info->smem_bytes_per_cta = d->plan.smemBytes;
   info->t_in_smem = d->plan.tInSmem;
-  info->table_in_smem = d->plan.blocksInSmem;
+  info->table_in_smem = d->plan.push ? d->plan.outInSmem : d->plan.blocksInSmem;
   info->s_prev_in_smem = d->plan.sPrevGlobal ? 0 : 1;
   info->n_clusters = d->plan.nClusters;
   info->sm_count = (uint32_t)d->smCount;

@@ -1,0 +1,885 @@
+// viterbiFillPushKernel: the ViterbiMatrix fill (reference src/viterbi.cpp:62-176) for a batch of
+// reads, one thread-block cluster per read, with the within-column closure done PUSH style.
+//
+// Why a second fill kernel.  The first one (viterbi_kernels.cu) relaxes dirty states PULL style: a hop
+// of a propagation chain costs two transition-table accesses (the state's incoming list, then its
+// outgoing list to wake successors) that miss L1 (cluster barriers flush it), plus a bitmap /
+// compaction / pending-counter protocol: ~3,000 cycles per hop measured on B200, and a column of the
+// BASELINE config-2 machine has chains of 17-46 hops.  Here
+//   * the closure is the reference's own phase-2 loop body (src/viterbi.cpp:118-158): a state whose S
+//     or D grew pushes max(D+delExtend, S+delOpen)+score into D(dest) over emitting transitions and
+//     D+score / S+score over null ones, with a compare-and-swap max on the destination cell (a failed
+//     push costs one shared-memory load).  max(a,b)+c == max(a+c,b+c) in IEEE arithmetic and every
+//     within-column weight is <= 0, so any schedule reaches the reference's least fixed point bit for
+//     bit; a hop needs one table access: the pusher's outgoing list;
+//   * that out-table is compact (one word per transition) and RESIDENT in shared memory;
+//   * the incoming lists, needed only by the three dense passes that walk the states in order
+//     (emission step, first closure pass, predecessor pass), are STREAMED through one shared-memory
+//     staging buffer in chunks: every thread fetches its 16-byte pieces of the NEXT chunk into registers
+//     (coalesced 128-bit loads) before it works on the current one and stores them after a CTA barrier,
+//     so the L2 latency of the table is hidden behind a whole step of the pass; each thread handles
+//     kU states per step with their loads interleaved (the passes are latency-, not issue-bound);
+//   * the push closure is level-synchronous and breadth first (the order that keeps re-relaxation
+//     low): per level the dirty bitmap is compacted into a queue, the queued states push, one CTA
+//     barrier; in a cluster, peers are relaxed directly through distributed shared memory (ld /
+//     atom.cas / red.or .shared::cluster) and ONE cluster barrier per level makes the flags they set
+//     visible; a thin frontier (the long tail of a column) is followed in lockstep chains by the lanes
+//     of a warp without any barrier.
+// Everything else -- the emission step, the predecessor records evaluated with the TRACEBACK's own
+// floating-point association and candidate order (src/viterbi.cpp:251-286), duplication opens, the
+// record layout read by viterbiTracebackKernel -- is as in viterbi_kernels.cu.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "viterbi_kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace dnab {
+namespace {
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double negInf() { return __longlong_as_double(0xFFF0000000000000LL); }
+// std::max(a,b) of the reference: keeps a on ties
+__device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }
+
+// constant tables / staged table chunks: plain loads
+__device__ __forceinline__ double ldsTab(uint32_t a) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+// DP cells: volatile, every relaxation re-reads them
+__device__ __forceinline__ double ldsCell(uint32_t a) {
+  double v;
+  asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void stsCell(uint32_t a, double v) {
+  asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ldsVolatile32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void redOrShared(uint32_t a, uint32_t v) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atomExchShared(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t atomAddShared(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+  asm volatile("st.volatile.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ uint32_t mapToRank(uint32_t localAddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(localAddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ double ldPeer(uint32_t clusterAddr) {
+  double v;
+  asm volatile("ld.relaxed.cluster.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(clusterAddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stPeerU32(uint32_t localAddr, uint32_t rank, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapToRank(localAddr, rank)), "r"(v) : "memory");
+}
+
+// cell <- max(cell, v) on a cell of THIS CTA; true when the cell grew.  A failed push is one load.
+__device__ __forceinline__ bool casMaxLocal(uint32_t a, double v, double old) {
+  while (v > old) {
+    const unsigned long long assumed = (unsigned long long)__double_as_longlong(old);
+    unsigned long long prev;
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;"
+                 : "=l"(prev)
+                 : "r"(a), "l"(assumed), "l"((unsigned long long)__double_as_longlong(v))
+                 : "memory");
+    if (prev == assumed) return true;
+    old = __longlong_as_double((long long)prev);
+  }
+  return false;
+}
+// the same on a cell of a peer CTA, through distributed shared memory
+__device__ __forceinline__ bool casMaxPeer(uint32_t clusterAddr, double v, double old) {
+  while (v > old) {
+    const unsigned long long assumed = (unsigned long long)__double_as_longlong(old);
+    unsigned long long prev;
+    asm volatile("atom.relaxed.cluster.shared::cluster.cas.b64 %0, [%1], %2, %3;"
+                 : "=l"(prev)
+                 : "r"(clusterAddr), "l"(assumed), "l"((unsigned long long)__double_as_longlong(v))
+                 : "memory");
+    if (prev == assumed) return true;
+    old = __longlong_as_double((long long)prev);
+  }
+  return false;
+}
+
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct Ctx {
+  uint32_t aS, aD, aFlag, aSym, aOutOff, aOutWords;
+  const uint16_t* gOutOff;   // out-table in global memory (when it does not fit in shared memory)
+  const uint32_t* gOutWords;
+  uint32_t outInSmem;
+  double delOpen, delExtend, delEnd;
+};
+
+constexpr uint32_t kNoState = 0xFFFFFFFFu;
+
+// One state's push (reference src/viterbi.cpp:118-158): ssrc = max(S, D+delEnd); over emitting
+// transitions max(D+delExtend, ssrc+delOpen)+score -> D(dest); over null ones D+score -> D(dest) and
+// ssrc+score -> S(dest).  A destination that grew must push in turn: the first such destination in
+// this CTA is RETURNED (the caller flags it or follows it), the others are flagged in the dirty
+// bitmap (this CTA's or a peer's) and `flagged` is set.
+// Loads that do not depend on each other are issued together: the chain is cells+offsets -> edge word
+// -> destination cells -> add/compare -> compare-and-swap (only when the destination grows).
+template <bool kCluster>
+__device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, bool& flagged) {
+  const uint32_t myS = c.aS + 8 * s, myD = c.aD + 8 * s;
+  uint32_t o0, o1;
+  if (c.outInSmem) {
+    o0 = lds16(c.aOutOff + 2 * s);
+    o1 = lds16(c.aOutOff + 2 * s + 2);
+  } else {
+    o0 = __ldg(c.gOutOff + s);
+    o1 = __ldg(c.gOutOff + s + 1);
+  }
+  const double dv = ldsCell(myD);
+  double sv = ldsCell(myS);
+  {  // ssrc = max(S, D + delEnd) (src/viterbi.cpp:121-122)
+    const double viaD = dv + c.delEnd;
+    if (viaD > sv) {
+      casMaxLocal(myS, viaD, sv);
+      sv = viaD;
+    }
+  }
+  const double m = dmax(dv + c.delExtend, sv + c.delOpen);  // src/viterbi.cpp:124
+  uint32_t next = kNoState;
+  for (uint32_t e = o0; e < o1; ++e) {
+    const uint32_t w = c.outInSmem ? lds32(c.aOutWords + 4 * e) : __ldg(c.gOutWords + e);
+    const uint32_t l = peLocal(w);
+    const uint32_t dS = c.aS + 8 * l, dD = c.aD + 8 * l;
+    const bool emit = peIsEmit(w) != 0;
+    const double sc = ldsTab(c.aSym + 8 * peSym(w));
+    const double candD = (emit ? m : dv) + sc;  // src/viterbi.cpp:125 / :139
+    const double candS = sv + sc;               // src/viterbi.cpp:148 (null transitions only)
+    if (!kCluster || !peRemote(w)) {
+      const double oldD = ldsCell(dD);
+      const double oldS = emit ? candS : ldsCell(dS);
+      bool grew = false;
+      if (candD > oldD) grew = casMaxLocal(dD, candD, oldD);
+      if (candS > oldS) grew |= casMaxLocal(dS, candS, oldS);
+      if (grew) {
+        if (next == kNoState)
+          next = l;
+        else {  // no fence: the flag is consumed only after the next CTA barrier
+          redOrShared(c.aFlag + 4 * (l >> 5), 1u << (l & 31));
+          flagged = true;
+        }
+      }
+    } else {
+      const uint32_t r = peRank(w);
+      const uint32_t pD = mapToRank(dD, r), pS = mapToRank(dS, r);
+      const double oldD = ldPeer(pD);
+      const double oldS = emit ? candS : ldPeer(pS);
+      bool grew = false;
+      if (candD > oldD) grew = casMaxPeer(pD, candD, oldD);
+      if (candS > oldS) grew |= casMaxPeer(pS, candS, oldS);
+      if (grew) {
+        // the compare-and-swap has returned, i.e. it was performed at the peer, before this is issued;
+        // the peer consumes the flag after the next cluster barrier
+        asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(mapToRank(c.aFlag + 4 * (l >> 5), r)),
+                     "r"(1u << (l & 31))
+                     : "memory");
+        flagged = true;
+      }
+    }
+  }
+  return next;
+}
+
+}  // namespace
+
+template <int kMaxThreads, int kMinBlocks, bool kCluster>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
+    viterbiFillPushKernel(const __grid_constant__ DevTables tb, const __grid_constant__ FillArgs args) {
+  constexpr int kU = kPushStatesPerThread;  // states per thread and step of a dense pass
+  constexpr int kV = 2;                     // 16-byte pieces of the next chunk staged in registers per thread
+  extern __shared__ __align__(128) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t C = kCluster ? tb.C : 1u, M = tb.M, k = tb.k;
+  const uint32_t rank = kCluster ? cluster.block_rank() : 0;
+  const uint32_t clusterId = blockIdx.x / C;
+  const uint32_t nClusters = gridDim.x / C;
+  const uint32_t tid = threadIdx.x, nThreads = blockDim.x;
+  const uint32_t lane = tid & 31;
+  const uint32_t Np = C * M;
+  const double NEG = negInf();
+  const PushLayout& lay = args.play;
+  const uint32_t sm = smemAddr(smem);
+  const bool sPrevSmem = tb.sPrevInSmem != 0;
+
+  const uint32_t aD = sm + lay.dBuf, aFlag = sm + lay.flag, aSym = sm + lay.symScore, aSub = sm + lay.sub;
+  const uint32_t aTsE = sm + lay.tsE, aExt = sm + lay.tsDext, aOpen = sm + lay.tsDopen;
+  const uint32_t aBuf = sm + lay.chunk, aChunkOff = sm + lay.chunkOff;
+  const double noGap = tb.noGap, delOpen = tb.delOpen, delExtend = tb.delExtend, delEnd = tb.delEnd;
+
+  double* symScore = reinterpret_cast<double*>(smem + lay.symScore);
+  double* tsE = reinterpret_cast<double*>(smem + lay.tsE);
+  double* tsDext = reinterpret_cast<double*>(smem + lay.tsDext);
+  double* tsDopen = reinterpret_cast<double*>(smem + lay.tsDopen);
+  double* subS = reinterpret_cast<double*>(smem + lay.sub);
+  double* tsT = reinterpret_cast<double*>(smem + lay.tsT);
+  double* lenS = reinterpret_cast<double*>(smem + lay.len);
+  volatile uint32_t* ctl = reinterpret_cast<volatile uint32_t*>(smem + lay.ctl);
+  uint8_t* seqS = smem + lay.seq;
+  double* sG = sPrevSmem ? nullptr : args.sScratch + (size_t)clusterId * 2 * Np;
+  double* tCol = tb.tInSmem ? reinterpret_cast<double*>(smem + lay.tBuf)
+                            : args.tScratch + ((size_t)clusterId * C + rank) * (size_t)k * M;
+
+  // ---- read-independent set-up ----
+  for (uint32_t s = tid; s < kMaxSyms; s += nThreads) {
+    const double sc = s < tb.nSyms ? tb.symScore[s] : NEG;
+    symScore[s] = sc;
+    tsDext[s] = sc + tb.delExtend;
+    tsDopen[s] = sc + tb.delOpen;
+  }
+  for (uint32_t j = tid; j < 16; j += nThreads) subS[j] = tb.sub[j];
+  for (uint32_t j = tid; j < 8; j += nThreads) {
+    lenS[j] = j < k ? tb.len[j] : NEG;
+    tsT[j] = j < k ? tb.tanDup + tb.len[j] : NEG;
+  }
+  auto buildTsE = [&]() {  // [(base*32+sym)*4 + observed] = (score+noGap)+sub[base][observed]
+    for (uint32_t j = tid; j < 512; j += nThreads) {
+      const uint32_t x = j & 3, sym = (j >> 2) & 31, base = j >> 7;
+      tsE[j] = sym < tb.nSyms ? (tb.symScore[sym] + tb.noGap) + tb.sub[base * 4 + x] : NEG;
+    }
+  };
+  buildTsE();
+  const uint32_t outOffBytes = (((M + 1) * 2) + 3) & ~3u;
+  const uint32_t* gOut = tb.outTable + __ldg(&tb.outSliceOff[rank]);
+  if (tb.outInSmem) {
+    const uint32_t nW = __ldg(&tb.outSliceOff[rank + 1]) - __ldg(&tb.outSliceOff[rank]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + lay.outTab);
+    for (uint32_t j = tid; j < nW; j += nThreads) dst[j] = __ldg(gOut + j);
+  }
+  const uint32_t nChunks = tb.nChunks;
+  {
+    uint32_t* co = reinterpret_cast<uint32_t*>(smem + lay.chunkOff);
+    for (uint32_t j = tid; j <= nChunks; j += nThreads) co[j] = __ldg(&tb.inChunkOff[rank * (nChunks + 1) + j]);
+  }
+  for (uint32_t j = tid; j < 64; j += nThreads) ctl[j] = 0;
+  {
+    uint32_t* fl = reinterpret_cast<uint32_t*>(smem + lay.flag);
+    for (uint32_t j = tid; j < (M + 31) / 32; j += nThreads) fl[j] = 0;
+  }
+  Ctx c;
+  c.aD = aD;
+  c.aFlag = aFlag;
+  c.aSym = aSym;
+  c.aOutOff = sm + lay.outTab;
+  c.aOutWords = sm + lay.outTab + outOffBytes;
+  c.gOutOff = reinterpret_cast<const uint16_t*>(gOut);
+  c.gOutWords = gOut + outOffBytes / 4;
+  c.outInSmem = tb.outInSmem;
+  c.delOpen = delOpen;
+  c.delExtend = delExtend;
+  c.delEnd = delEnd;
+  __syncthreads();
+
+  // ---- the streamed in-table: chunk `nextChunk` is fetched into registers while the current one is used
+  const uint4* gChunks = reinterpret_cast<const uint4*>(tb.inChunks);
+  const uint32_t chunkStates = tb.chunkStates;                      // = kU * nThreads
+  const uint32_t recBase = ((chunkStates + 1) * 2 + 3) & ~3u;       // records start after the u16 offsets
+  uint32_t nextChunk = 0, stageVec0 = 0, stageN = 0;
+  uint4 stage[kV];
+  auto prefetch = [&]() {
+    const uint32_t o0 = lds32(aChunkOff + 4 * nextChunk), o1 = lds32(aChunkOff + 4 * nextChunk + 4);
+    stageVec0 = o0 >> 2;
+    stageN = (o1 - o0) >> 2;
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+      const uint32_t idx = v * nThreads + tid;
+      stage[v] = idx < stageN ? __ldg(gChunks + stageVec0 + idx) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  auto commit = [&]() {
+    __syncthreads();  // every thread is done with the current chunk (and with this step of the pass)
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+      const uint32_t idx = v * nThreads + tid;
+      if (idx < stageN) sts128(aBuf + 16 * idx, stage[v]);
+    }
+    for (uint32_t idx = kV * nThreads + tid; idx < stageN; idx += nThreads)  // oversized chunk: unstaged remainder
+      sts128(aBuf + 16 * idx, __ldg(gChunks + stageVec0 + idx));
+    __syncthreads();
+    nextChunk = nextChunk + 1 == nChunks ? 0 : nextChunk + 1;
+  };
+  prefetch();
+  commit();  // chunk 0 is in the buffer; nextChunk = 1 (or 0 again for a one-chunk slice)
+
+  auto clusterBarrier = [&]() {
+    if (kCluster)
+      cluster.sync();
+    else
+      __syncthreads();
+  };
+  clusterBarrier();  // every CTA's flags exist before a peer can touch them
+
+  unsigned long long dbgLevels = 0, dbgRounds = 0, dbgTE = 0, dbgTC = 0, dbgTP = 0, dbgTB = 0, dbgCols = 0, dbgWork = 0,
+                     dbgClusterWait = 0, dbgDirty = 0, dbgScan = 0, dbgPush = 0, dbgPushWait = 0, dbgHops = 0;
+  const bool dbgOn = args.dbg != nullptr;
+
+  for (int64_t read = clusterId; read < args.nReads; read += nClusters) {
+    const int32_t L = args.readLen[read];
+    {  // stage the packed read
+      const uint8_t* src = args.packed + args.byteOff[read];
+      const uint32_t nVec = ((uint32_t)(L + 3) / 4 + 15) / 16;
+      for (uint32_t v = tid; v < nVec; v += nThreads)
+        reinterpret_cast<uint4*>(seqS)[v] = __ldg(reinterpret_cast<const uint4*>(src) + v);
+    }
+    uint8_t* predRead = args.pred + (size_t)read * (size_t)(args.maxLen + 1) * (k + 2) * Np;
+    __syncthreads();
+
+    for (int32_t pos = 0; pos <= L; ++pos) {
+      const uint32_t cur = pos & 1, prev = cur ^ 1;
+      const uint32_t aScur = sm + (sPrevSmem ? (cur ? lay.sBuf[1] : lay.sBuf[0]) : lay.sBuf[0]);
+      const uint32_t aSprev = sm + (sPrevSmem ? (prev ? lay.sBuf[1] : lay.sBuf[0]) : lay.sBuf[0]);
+      const double* sPrevG = sG + (size_t)prev * Np;  // (only dereferenced when !sPrevSmem)
+      double* sCurG = sG + (size_t)cur * Np;
+      const uint32_t x = pos > 0 ? (seqS[(pos - 1) >> 2] >> (2 * ((pos - 1) & 3))) & 3u : 0u;
+      c.aS = aScur;
+
+      // S(pos-1) of the source named by an in-edge word
+      auto loadPrev = [&](uint32_t w) -> double {
+        if (!sPrevSmem) return sPrevG[peRank(w) * M + peLocal(w)];
+        const uint32_t a = aSprev + 8 * peLocal(w);
+        return (kCluster && peRemote(w)) ? ldPeer(mapToRank(a, peRank(w))) : ldsCell(a);
+      };
+      auto loadCell = [&](uint32_t aCol, uint32_t w) -> double {
+        const uint32_t a = aCol + 8 * peLocal(w);
+        return (kCluster && peRemote(w)) ? ldPeer(mapToRank(a, peRank(w))) : ldsCell(a);
+      };
+      // record of slot u of this thread in the staged chunk, and its header (padding header when out of range)
+      auto recOf = [&](uint32_t u) -> uint32_t { return aBuf + recBase + 4 * lds16(aBuf + 2 * (u * nThreads + tid)); };
+
+      long long tc0 = dbgOn ? clock64() : 0;
+      // ---- (1) emission step: S0 from the previous column, T shift (src/viterbi.cpp:92-106) ----
+      for (uint32_t j = 0; j < nChunks; ++j) {
+        prefetch();
+        uint32_t i[kU], rec[kU], h[kU];
+        double s[kU], t0[kU];
+        uint32_t maxE = 0;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          i[u] = j * chunkStates + u * nThreads + tid;
+          rec[u] = recOf(u);
+          h[u] = i[u] < M ? lds32(rec[u]) : (kInPad << 7);
+          s[u] = NEG;
+          t0[u] = NEG;
+          if (pos > 0) {
+            if (inMdl(h[u]) > 0) t0[u] = tCol[i[u]];
+            maxE = max(maxE, inNEmit(h[u]));
+          }
+        }
+        if (pos == 0) {
+#pragma unroll
+          for (int u = 0; u < kU; ++u)
+            if (i[u] < M) {
+              const bool real = inNIn(h[u]) != kInPad;
+              s[u] = (real && (tb.local || rank * M + i[u] == tb.startG)) ? 0.0 : NEG;  // src/viterbi.cpp:75-79
+              for (uint32_t t = 0; t < k; ++t) tCol[t * M + i[u]] = NEG;
+            }
+        } else {
+          for (uint32_t e = 0; e < maxE; ++e) {
+            uint32_t w[kU];
+            double v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) w[u] = e < inNEmit(h[u]) ? lds32(rec[u] + 4 + 4 * e) : 0u;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) v[u] = e < inNEmit(h[u]) ? loadPrev(w[u]) : NEG;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+              const double cand = ((v[u] + ldsTab(aSym + 8 * peSym(w[u]))) + noGap) + ldsTab(aSub + 8 * (peBase(w[u]) * 4 + x));
+              if (e < inNEmit(h[u])) s[u] = dmax(s[u], cand);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const uint32_t mdl = inMdl(h[u]);
+            if (mdl > 0) {
+              const double t2s = t0[u] + subS[inCtx(h[u], 0) * 4 + x];
+              s[u] = dmax(s[u], t2s);
+              for (uint32_t t = 0; t + 1 < mdl; ++t)
+                tCol[t * M + i[u]] = tCol[(t + 1) * M + i[u]] + subS[inCtx(h[u], t + 1) * 4 + x];
+              tCol[(mdl - 1) * M + i[u]] = t2s;  // slot mdl-1 is free until step (4): park the T->S candidate there
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (i[u] < M) {
+            stsCell(aScur + 8 * i[u], s[u]);
+            stsCell(aD + 8 * i[u], NEG);
+          }
+        commit();
+      }
+      clusterBarrier();  // S0 of every CTA is complete before a peer reads it
+      long long tc1 = dbgOn ? clock64() : 0;
+
+      // ---- (2a) closure, first pass, PULL over the streamed in-table (src/viterbi.cpp:97-99,110-159).
+      // Successors may have read S0(d) / D = -inf or the new values (racy, benign); a state is flagged
+      // when its new values can still raise a successor above what S0 / -inf already gave it.
+      for (uint32_t j = 0; j < nChunks; ++j) {
+        prefetch();
+        uint32_t i[kU], rec[kU], h[kU], nIn[kU];
+        double s0[kU], newS[kU], newD[kU];
+        uint32_t maxIn = 0;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          i[u] = j * chunkStates + u * nThreads + tid;
+          rec[u] = recOf(u);
+          h[u] = i[u] < M ? lds32(rec[u]) : (kInPad << 7);
+          nIn[u] = inNIn(h[u]) == kInPad ? 0u : inNIn(h[u]);
+          maxIn = max(maxIn, nIn[u]);
+          s0[u] = i[u] < M ? ldsCell(aScur + 8 * i[u]) : NEG;
+          newS[u] = s0[u];
+          newD[u] = NEG;
+        }
+        for (uint32_t e = 0; e < maxIn; ++e) {
+          uint32_t w[kU];
+          double ss[kU], ds[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) w[u] = e < nIn[u] ? lds32(rec[u] + 4 + 4 * e) : 0u;
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            ss[u] = e < nIn[u] ? loadCell(aScur, w[u]) : NEG;
+            ds[u] = e < nIn[u] ? loadCell(aD, w[u]) : NEG;
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const double sc = ldsTab(aSym + 8 * peSym(w[u]));
+            if (e < inNEmit(h[u]))
+              newD[u] = dmax(newD[u], dmax(ds[u] + delExtend, ss[u] + delOpen) + sc);
+            else if (e < nIn[u]) {
+              newD[u] = dmax(newD[u], ds[u] + sc);
+              newS[u] = dmax(newS[u], ss[u] + sc);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          bool dirty = false;
+          if (i[u] < M) {
+            newS[u] = dmax(newS[u], newD[u] + delEnd);
+            if (newD[u] > NEG) stsCell(aD + 8 * i[u], newD[u]);
+            if (newS[u] > s0[u]) stsCell(aScur + 8 * i[u], newS[u]);
+            dirty = (newS[u] > s0[u]) || (newD[u] + delExtend > s0[u] + delOpen) || (inHasNullOut(h[u]) && newD[u] > NEG);
+          }
+          const uint32_t mask = __ballot_sync(0xFFFFFFFFu, dirty);
+          if (lane == 0 && i[u] < M) {
+            sts32(aFlag + 4 * (i[u] >> 5), mask);
+            if (dbgOn) dbgDirty += __popc(mask);
+          }
+        }
+        commit();
+      }
+      clusterBarrier();  // no peer pushes into this CTA's cells while its first pass still stores them
+      long long tc1b = dbgOn ? clock64() : 0;
+
+      // ---- (2b) closure, PUSH levels.  Per level: the set bits of the dirty bitmap are taken and
+      // compacted into a CTA-wide queue (one lane per bitmap word, one shared-memory atomic per warp);
+      // after a CTA barrier every thread pushes the queued states, one state per thread and step, so
+      // that all lanes of a warp work whatever the shape of the frontier; a destination that grew is
+      // flagged (this CTA's bitmap or a peer's) for the next level.  The level ends with a barrier of
+      // the CTA -- of the cluster when there are peers, which also makes the flags they set visible --
+      // and the closure ends when a level flagged nothing anywhere.
+      {
+        const uint32_t nWords = (M + 31) / 32, cap = lay.queueCap;
+        const uint32_t aQueue = sm + lay.queue, aTail = sm + lay.ctl;  // ctl[0], ctl[1]: queue tails, by level parity
+        for (uint32_t levels = 0;; ++levels) {
+          const uint32_t par = levels & 1;
+          const long long tl0 = dbgOn ? clock64() : 0;
+          bool flagged = false;
+          for (uint32_t base = 0; base < nWords; base += nThreads) {
+            const uint32_t wi = base + tid;
+            const uint32_t aWord = aFlag + 4 * wi;
+            uint32_t taken = (wi < nWords && ldsVolatile32(aWord)) ? atomExchShared(aWord, 0u) : 0u;
+            const uint32_t cnt = __popc(taken);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (uint32_t dlt = 1; dlt < 32; dlt <<= 1) {
+              const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, dlt);
+              if (lane >= dlt) incl += up;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (total == 0) continue;  // warp-uniform
+            uint32_t wbase = 0;
+            if (lane == 31) wbase = atomAddShared(aTail + 4 * par, total);
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+            uint32_t at = wbase + incl - cnt, putBack = 0;
+            while (taken) {
+              const uint32_t bit = __ffs(taken) - 1;
+              taken &= taken - 1;
+              if (at < cap)
+                sts16(aQueue + 2 * at, 32 * wi + bit);
+              else
+                putBack |= 1u << bit;  // queue full: the state waits for the next level
+              ++at;
+            }
+            if (putBack) {
+              redOrShared(aWord, putBack);
+              flagged = true;
+            }
+          }
+          __syncthreads();  // queue complete; every cell stored before the bits were set is visible
+          const long long tl1 = dbgOn ? clock64() : 0;
+          uint32_t n = ldsVolatile32(aTail + 4 * par);
+          if (n > cap) n = cap;
+          if (dbgOn && tid == 0) ++dbgLevels;
+          if (levels > (1u << 22)) __trap();  // never hang the GPU: a closure that does not settle is a bug
+          if (tid == 0) sts32(aTail + 4 * (par ^ 1), 0u);  // the other tail is idle until the next scan
+          if (n > args.tailN) {
+            // wide frontier: one hop per level, breadth first
+            for (uint32_t q = tid; q < n; q += nThreads) {
+              const uint32_t nx = pushState<kCluster>(c, lds16(aQueue + 2 * q), flagged);
+              if (nx != kNoState) {
+                redOrShared(aFlag + 4 * (nx >> 5), 1u << (nx & 31));
+                flagged = true;
+              }
+            }
+          } else if (n > 0) {
+            // thin frontier (the long tail of a column's closure): at most one state per thread, and the
+            // lanes of a warp follow their chains in LOCKSTEP -- still breadth first, but a hop now
+            // costs one dependent chain of shared-memory accesses instead of a scan and two barriers.
+            // Fan-out beyond one successor per state goes through the bitmap as usual.
+            uint32_t s = tid < n ? lds16(aQueue + 2 * tid) : kNoState;
+            for (uint32_t hop = 0; hop < args.tailHops; ++hop) {
+              if (__ballot_sync(0xFFFFFFFFu, s != kNoState) == 0u) break;
+              if (s != kNoState) s = pushState<kCluster>(c, s, flagged);
+              if (dbgOn && tid == 0) ++dbgHops;
+            }
+            if (s != kNoState) {  // hop budget spent
+              redOrShared(aFlag + 4 * (s >> 5), 1u << (s & 31));
+              flagged = true;
+            }
+          }
+          if (dbgOn && tid == 0) dbgWork += n;
+          const long long tl2 = dbgOn ? clock64() : 0;
+          const uint32_t anyFlagged = (uint32_t)__syncthreads_or(flagged ? 1 : 0);  // every push of this level has set its flags
+          uint32_t tot = anyFlagged;
+          if (kCluster) {
+            if (tid < C) stPeerU32(sm + lay.ctl + (16 + par * kMaxCluster + rank) * 4, tid, anyFlagged);
+            cluster.sync();
+            tot = 0;
+            for (uint32_t r = 0; r < C; ++r) tot |= ctl[16 + par * kMaxCluster + r];
+          }
+          if (dbgOn && tid == 0) {
+            const long long tl3 = clock64();
+            dbgScan += tl1 - tl0;
+            dbgPush += tl2 - tl1;
+            dbgPushWait += tl3 - tl2;
+          }
+          if (!tot) break;
+        }
+      }
+      long long tc2 = dbgOn ? clock64() : 0;
+
+      // ---- (3) predecessor records with the traceback's arithmetic (src/viterbi.cpp:251-286)
+      //      (4) duplication opens (src/viterbi.cpp:161-168) ----
+      uint8_t* predCol = predRead + (size_t)pos * (k + 2) * Np;
+      for (uint32_t j = 0; j < nChunks; ++j) {
+        prefetch();
+        uint32_t i[kU], rec[kU], h[kU], nIn[kU], idx[kU], idxD[kU];
+        double sHere[kU], dHere[kU], parked[kU], best[kU], bestD[kU];
+        uint32_t maxIn = 0;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          i[u] = j * chunkStates + u * nThreads + tid;
+          rec[u] = recOf(u);
+          h[u] = i[u] < M ? lds32(rec[u]) : (kInPad << 7);
+          nIn[u] = inNIn(h[u]) == kInPad ? 0u : inNIn(h[u]);
+          maxIn = max(maxIn, nIn[u]);
+          const uint32_t mdl = inMdl(h[u]);
+          sHere[u] = i[u] < M ? ldsCell(aScur + 8 * i[u]) : NEG;
+          dHere[u] = i[u] < M ? ldsCell(aD + 8 * i[u]) : NEG;
+          parked[u] = (mdl > 0 && pos > 0) ? tCol[(mdl - 1) * M + i[u]] : NEG;  // T(state,pos-1,0)+sub
+          best[u] = NEG;
+          bestD[u] = NEG;
+          idx[u] = kNoPred;
+          idxD[u] = kNoPred;
+        }
+        for (uint32_t e = 0; e < maxIn; ++e) {
+          uint32_t w[kU];
+          double vs[kU], vd[kU], vp[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) w[u] = e < nIn[u] ? lds32(rec[u] + 4 + 4 * e) : 0u;
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            vs[u] = e < nIn[u] ? loadCell(aScur, w[u]) : NEG;
+            vd[u] = e < nIn[u] ? loadCell(aD, w[u]) : NEG;
+            vp[u] = (pos > 0 && e < inNEmit(h[u])) ? loadPrev(w[u]) : NEG;
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const uint32_t nE = inNEmit(h[u]);
+            const uint32_t sym8 = 8 * peSym(w[u]);
+            if (e < nE) {
+              if (pos > 0) {
+                const double v = vp[u] + ldsTab(aTsE + 8 * ((((w[u] >> 21) & 0x7Fu) << 2) + x));
+                if (v > best[u]) {
+                  best[u] = v;
+                  idx[u] = e;
+                }
+              }
+              const double ve = vd[u] + ldsTab(aExt + sym8);
+              if (ve > bestD[u]) {
+                bestD[u] = ve;
+                idxD[u] = 2 * e;
+              }
+              const double vo = vs[u] + ldsTab(aOpen + sym8);
+              if (vo > bestD[u]) {
+                bestD[u] = vo;
+                idxD[u] = 2 * e + 1;
+              }
+            } else if (e < nIn[u]) {
+              const double sc = ldsTab(aSym + sym8);
+              const double v = vs[u] + sc;
+              if (v > best[u]) {
+                best[u] = v;
+                idx[u] = e;
+              }
+              const double vn = vd[u] + sc;
+              if (vn > bestD[u]) {
+                bestD[u] = vn;
+                idxD[u] = nE + e;  // = 2*nE + (e - nE)
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (i[u] < M) {
+            const uint32_t g = rank * M + i[u];
+            const bool real = inNIn(h[u]) != kInPad;
+            const uint32_t mdl = inMdl(h[u]);
+            if (!sPrevSmem) sCurG[g] = sHere[u];  // publish the converged column for the next position
+            {
+              const double v = dHere[u] + delEnd;
+              if (v > best[u]) {
+                best[u] = v;
+                idx[u] = nIn[u];
+              }
+            }
+            if (mdl > 0 && pos > 0 && parked[u] > best[u]) {
+              best[u] = parked[u];
+              idx[u] = nIn[u] + 1;
+            }
+            if (tb.local && pos == 0) {
+              const uint32_t a = aScur + (tb.startG % M) * 8, r = tb.startG / M;
+              const double v = ((!kCluster || r == rank) ? ldsCell(a) : ldPeer(mapToRank(a, r))) + 0.0;
+              if (v > best[u]) {
+                best[u] = v;
+                idx[u] = nIn[u] + 2;
+              }
+            }
+            predCol[g] = (uint8_t)(real ? idx[u] : kNoPred);
+            predCol[Np + g] = (uint8_t)(real ? idxD[u] : kNoPred);
+            for (uint32_t t = 0; t < k; ++t) {
+              uint32_t idxT = kNoPred;
+              if (pos > 0 && t < mdl) {
+                const double shifted = (t + 1 < mdl) ? tCol[t * M + i[u]] : NEG;
+                if (t + 1 < mdl && shifted > NEG) idxT = 0;
+                if (sHere[u] + tsT[t] > shifted) idxT = 1;
+                tCol[t * M + i[u]] = dmax(shifted, (sHere[u] + tb.tanDup) + lenS[t]);  // (4)
+              }
+              predCol[(size_t)(2 + t) * Np + g] = (uint8_t)idxT;
+            }
+            if (args.cells && read == 0 && real) {
+              double* cell = args.cells + ((size_t)pos * tb.nStates + __ldg(&tb.origId[g])) * (k + 2);
+              cell[0] = sHere[u];
+              cell[1] = dHere[u];
+              for (uint32_t t = 0; t < k; ++t) cell[2 + t] = (pos > 0 && t < mdl) ? tCol[t * M + i[u]] : NEG;
+            }
+          }
+        commit();
+      }
+      clusterBarrier();
+      if (dbgOn && tid == 0) {
+        const long long tc3 = clock64();
+        dbgTE += tc1 - tc0;
+        dbgTB += tc1b - tc1;
+        dbgTC += tc2 - tc1;
+        dbgTP += tc3 - tc2;
+        dbgCols++;
+      }
+    }
+
+    // ---- end of read: log-likelihood and traceback start (src/viterbi.cpp:171-173, 239-245) ----
+    {
+      const double* sLast = reinterpret_cast<const double*>(smem + ((sPrevSmem && (L & 1)) ? lay.sBuf[1] : lay.sBuf[0]));
+      if (!tb.local) {
+        if (rank == tb.endG / M && tid == 0) {
+          args.loglike[read] = sLast[tb.endG % M];
+          args.startState[read] = tb.endG;
+        }
+        __syncthreads();
+      } else {
+        // first strict maximum in REFERENCE state order: max value, then smallest original index
+        double bv = NEG;
+        uint32_t bo = 0xFFFFFFFFu, bg = 0;
+        for (uint32_t i = tid; i < M; i += nThreads) {
+          const uint32_t g = rank * M + i;
+          const uint32_t o = __ldg(&tb.origId[g]);
+          if (o == 0xFFFFFFFFu) continue;
+          const double v = sLast[i];
+          if (v > bv || (v == bv && o < bo)) {
+            bv = v;
+            bo = o;
+            bg = g;
+          }
+        }
+        for (int sh = 16; sh > 0; sh >>= 1) {
+          const double ov = __shfl_down_sync(0xFFFFFFFFu, bv, sh);
+          const uint32_t oo = __shfl_down_sync(0xFFFFFFFFu, bo, sh);
+          const uint32_t og = __shfl_down_sync(0xFFFFFFFFu, bg, sh);
+          if (ov > bv || (ov == bv && oo < bo)) {
+            bv = ov;
+            bo = oo;
+            bg = og;
+          }
+        }
+        __syncthreads();
+        // reduction scratch: the tsE table (rebuilt below) is free between reads
+        double* rv = tsE;
+        uint32_t* ro = reinterpret_cast<uint32_t*>(tsE + 32);
+        if (lane == 0) {
+          rv[tid >> 5] = bv;
+          ro[2 * (tid >> 5)] = bo;
+          ro[2 * (tid >> 5) + 1] = bg;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          const uint32_t nw = (nThreads + 31) / 32;
+          for (uint32_t w = 1; w < nw; ++w)
+            if (rv[w] > bv || (rv[w] == bv && ro[2 * w] < bo)) {
+              bv = rv[w];
+              bo = ro[2 * w];
+              bg = ro[2 * w + 1];
+            }
+          args.partVal[read * C + rank] = bv;
+          args.partOrig[read * C + rank] = bo;
+          args.partG[read * C + rank] = bg;
+        }
+        __syncthreads();
+        buildTsE();
+        __syncthreads();
+      }
+    }
+  }
+  if (dbgOn && rank == 0) {
+    if (lane == 0 && dbgDirty) atomicAdd(&args.dbg[8], dbgDirty);
+    if (tid == 0) {
+      atomicAdd(&args.dbg[0], dbgCols);
+      atomicAdd(&args.dbg[1], dbgLevels);
+      atomicAdd(&args.dbg[2], dbgWork);
+      atomicAdd(&args.dbg[3], dbgTE);
+      atomicAdd(&args.dbg[4], dbgTC);
+      atomicAdd(&args.dbg[5], dbgTP);
+      atomicAdd(&args.dbg[6], dbgRounds);
+      atomicAdd(&args.dbg[7], dbgTB);
+      atomicAdd(&args.dbg[11], dbgClusterWait);
+      atomicAdd(&args.dbg[9], dbgScan);
+      atomicAdd(&args.dbg[10], dbgPush);
+      atomicAdd(&args.dbg[12], dbgPushWait);
+      atomicAdd(&args.dbg[13], dbgHops);
+    }
+  }
+  clusterBarrier();  // no CTA may exit while a peer can still touch its shared memory
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+typedef void (*PushKernelPtr)(const DevTables, const FillArgs);
+template <bool kCluster>
+static PushKernelPtr pickPushKernelT(uint32_t threads) {
+  if (threads > 800) return viterbiFillPushKernel<1024, 1, kCluster>;  // 64 registers/thread
+  if (threads > 640) return viterbiFillPushKernel<800, 1, kCluster>;   // 80
+  if (threads > 512) return viterbiFillPushKernel<640, 1, kCluster>;   // 96
+  if (threads > 256) return viterbiFillPushKernel<512, 1, kCluster>;   // 128
+  return viterbiFillPushKernel<256, 2, kCluster>;                      // 128
+}
+static PushKernelPtr pickPushKernel(const DevTables& tb, uint32_t threads) {
+  return tb.C > 1 ? pickPushKernelT<true>(threads) : pickPushKernelT<false>(threads);
+}
+
+static cudaError_t prepPush(PushKernelPtr kern, const DevTables& tb, uint32_t smemBytes) {
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+  if (err != cudaSuccess) return err;
+  if (tb.C > 8) err = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return err;
+}
+
+static void pushClusterConfig(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, const DevTables& tb, uint32_t nClusters,
+                              uint32_t threads, uint32_t smemBytes, cudaStream_t stream) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(nClusters * tb.C);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smemBytes;
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = tb.C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+}
+
+cudaError_t launchFillPush(const DevTables& tb, const FillArgs& args, uint32_t nClusters, uint32_t threads,
+                           uint32_t smemBytes, cudaStream_t stream) {
+  PushKernelPtr kern = pickPushKernel(tb, threads);
+  cudaError_t err = prepPush(kern, tb, smemBytes);
+  if (err != cudaSuccess) return err;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  pushClusterConfig(cfg, attr, tb, nClusters, threads, smemBytes, stream);
+  return cudaLaunchKernelEx(&cfg, kern, tb, args);
+}
+
+cudaError_t queryMaxClustersPush(const DevTables& tb, uint32_t threads, uint32_t smemBytes, int* nClusters) {
+  PushKernelPtr kern = pickPushKernel(tb, threads);
+  cudaError_t err = prepPush(kern, tb, smemBytes);
+  if (err != cudaSuccess) return err;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  pushClusterConfig(cfg, attr, tb, 1, threads, smemBytes, nullptr);
+  return cudaOccupancyMaxActiveClusters(nClusters, kern, &cfg);
+}
+
+}  // namespace dnab

@@ -72,11 +72,75 @@ inline SmemLayout makeLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t 
   return L;
 }
 
+// ---------------------------------------------------------------------------
+// shared-memory carve-up of the push kernel (viterbi_fill_push.cu); identical in every CTA of
+// a cluster.  S and D are the only columns that must be in shared memory; S(pos-1), the T
+// columns and the out-table join them when they fit.
+// ---------------------------------------------------------------------------
+struct PushLayout {
+  uint32_t sBuf[2];    // S(pos) / S(pos-1); one buffer only when S(pos-1) lives in global scratch
+  uint32_t dBuf;       // D(pos)
+  uint32_t tBuf;       // k*M doubles, only if tInSmem
+  uint32_t outTab;     // the CTA's out-table, only if outInSmem
+  uint32_t chunk;      // staging buffer of the streamed in-table (one chunk)
+  uint32_t chunkOff;   // [nChunks+1] u32: word offsets of this CTA's chunks in the global in-table
+  uint32_t flag;       // [ceil(M/32)] u32 dirty bitmap: the state must push to its successors
+  uint32_t queue;      // [queueCap] u16: the dirty states of the current closure level, compacted
+  uint32_t queueCap;
+  uint32_t tsE;        // [4 bases][32 syms][4 observed] (score+noGap)+sub, traceback association (src/viterbi.cpp:255)
+  uint32_t symScore;   // [kMaxSyms]
+  uint32_t tsDext;     // [kMaxSyms] score+delExtend (src/viterbi.cpp:272)
+  uint32_t tsDopen;    // [kMaxSyms] score+delOpen   (src/viterbi.cpp:273)
+  uint32_t sub;        // [16]
+  uint32_t tsT;        // [8] tanDup+len[i]          (src/viterbi.cpp:286)
+  uint32_t len;        // [8]
+  uint32_t ctl;        // 64 u32 control words: [16..47] sent[2][kMaxCluster]
+  uint32_t seq;        // packed read
+  uint32_t total;
+};
+
+constexpr int kPushStatesPerThread = 2;  // states a thread handles per step of a dense pass (interleaved loads)
+
+inline PushLayout makePushLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t sPrevInSmem, uint32_t outBytes,
+                                 uint32_t chunkBytes, uint32_t nChunks, uint32_t maxLen, uint32_t queueCap = 0) {
+  PushLayout L;
+  uint32_t at = 0;
+  auto take = [&](uint32_t bytes) {
+    const uint32_t here = at;
+    at += (bytes + 15u) & ~15u;
+    return here;
+  };
+  L.sBuf[0] = take(M * 8);
+  L.sBuf[1] = sPrevInSmem ? take(M * 8) : L.sBuf[0];
+  L.dBuf = take(M * 8);
+  L.tBuf = tInSmem ? take(k * M * 8) : 0;
+  L.outTab = outBytes ? take(outBytes) : 0;
+  L.chunk = take(chunkBytes);
+  L.chunkOff = take((nChunks + 1) * 4);
+  L.flag = take(((M + 31) / 32) * 4);
+  L.queueCap = queueCap ? queueCap : M;  // M entries never overflow; a smaller queue defers states to the next level
+  L.queue = take(L.queueCap * 2);
+  L.tsE = take(4 * 32 * 4 * 8);
+  L.symScore = take(kMaxSyms * 8);
+  L.tsDext = take(kMaxSyms * 8);
+  L.tsDopen = take(kMaxSyms * 8);
+  L.sub = take(16 * 8);
+  L.tsT = take(8 * 8);
+  L.len = take(8 * 8);
+  L.ctl = take(64 * 4);
+  L.seq = take((maxLen + 3) / 4 + 16);
+  L.total = at;
+  return L;
+}
+
 struct FillArgs {
   SmemLayout lay;
+  PushLayout play;           // push kernel
   int64_t nReads;
   int32_t maxLen;            // pred stride: every read owns (maxLen+1) columns of records
   uint32_t idleSleepNs;      // back-off of a warp whose closure sweep found nothing to do
+  uint32_t tailN;            // push kernel: a closure level with at most this many dirty states (<= threads) runs in lockstep-chain mode
+  uint32_t tailHops;         // push kernel: hop budget of one lockstep-chain episode
   const uint8_t* packed;     // 2-bit reads
   const int64_t* byteOff;    // [nReads]
   const int32_t* readLen;    // [nReads]
@@ -114,6 +178,10 @@ struct TracebackArgs {
 cudaError_t queryMaxClusters(const DevTables& tb, uint32_t threads, uint32_t smemBytes, int* nClusters);
 cudaError_t launchFill(const DevTables& tb, const FillArgs& args, uint32_t nClusters, uint32_t threads,
                        uint32_t smemBytes, cudaStream_t stream);
+// push kernel (viterbi_fill_push.cu)
+cudaError_t queryMaxClustersPush(const DevTables& tb, uint32_t threads, uint32_t smemBytes, int* nClusters);
+cudaError_t launchFillPush(const DevTables& tb, const FillArgs& args, uint32_t nClusters, uint32_t threads,
+                           uint32_t smemBytes, cudaStream_t stream);
 cudaError_t launchTraceback(const DevTables& tb, const TracebackArgs& args, cudaStream_t stream);
 
 }  // namespace dnab

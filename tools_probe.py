@@ -16,5 +16,5 @@ out = dec.viterbi(reads)
 st = dec.stats(); dc = dec.debug_counters(); info = dec.info()
 cols = max(dc['columns'], 1)
 print(json.dumps(dict(fill_ms=round(st['last_fill_ms'],2), cfg=cfg, info=info, tb_ms=st['last_traceback_ms'], reads=n,
-      per_column=dict(local_iters=dc['sweeps'] / cols, rounds=dc['rounds'] / cols, work_rank0=dc['work_rank0'] / cols, cyc_emit=dc['cyc_emit'] / cols,
+      per_column=dict(local_iters=dc['sweeps'] / cols, rounds=dc['rounds'] / cols, work_rank0=dc['work_rank0'] / cols, dirty_first=dc['dirty_first'] / cols, hops_t0=dc['hops_t0'] / cols, cyc_emit=dc['cyc_emit'] / cols,
                       cyc_closure=dc['cyc_closure'] / cols, cyc_pred=dc['cyc_pred'] / cols, **{k: dc[k] / cols for k in dc if k.startswith('cyc_') and k not in ('cyc_emit','cyc_closure','cyc_pred')}))))
