@@ -75,7 +75,8 @@ struct dnab_decoder {
   uint32_t wantC = 0, wantThreads = 0, wantTMode = 0;  // tMode: 0 auto, 1 smem, 2 global
   uint32_t wantBlockMode = 0;   // transition table: 0 auto, 1 shared memory, 2 global memory
   uint32_t idleSleepNs = 100;
-  uint32_t tailN = 128, tailHops = 64;  // push kernel: lockstep-chain mode (tuning: DNAB_TAIL_N / DNAB_TAIL_HOPS)
+  uint32_t tRecompute = 1;
+  uint32_t tailN = 0, tailHops = 64;  // push kernel: lockstep-chain mode (tuning: DNAB_TAIL_N / DNAB_TAIL_HOPS)
   uint32_t wantSPrevMode = 0;   // S(pos-1): 0 auto, 1 shared memory, 2 global scratch
   uint32_t wantKernel = 0;      // 0 push kernel (viterbi_fill_push.cu), 1 pull kernel (viterbi_kernels.cu)
   uint32_t wantPartition = 0;   // 0/1 index-order runs + in-degree sort (default), 2 DFS runs unsorted, 3 DFS chunks dealt round-robin + sort, 4 DFS runs + sort
@@ -89,7 +90,7 @@ struct dnab_decoder {
   DevBuf<uint8_t> dPred;
   DevBuf<double> dTScratch, dSScratch, dPartVal, dCells;
   DevBuf<uint32_t> dStart, dPartOrig, dPartG;
-  DevBuf<unsigned long long> dDbg;
+  DevBuf<unsigned long long> dDbg, dNextRead;
   bool debug = false;
   // staging for the host-buffer path
   DevBuf<uint8_t> dPacked;
@@ -168,7 +169,8 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
   P.M = M;
   // 1. CTA assignment: equal runs of the reference's state order (default) or of a DFS order
   std::vector<uint32_t> order;
-  const bool useDfs = d->wantPartition >= 2;
+  const uint32_t partMode = d->wantPartition ? d->wantPartition : (d->wantKernel == 0 ? 3u : 1u);
+  const bool useDfs = partMode >= 2;
   if (C > 1 && useDfs)
     order = dfsOrder(d);
   else {
@@ -183,7 +185,7 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
   // partition mode 3: the DFS order is cut into 8*C chunks dealt round-robin to the CTAs, trading some
   // locality for CTAs that are busy for equally long inside a closure round
   std::vector<std::vector<uint32_t>> dealt(C);
-  if (d->wantPartition == 3 && C > 1) {
+  if (partMode == 3 && C > 1) {
     const uint32_t chunk = std::max<uint32_t>(32, (N + 8 * C - 1) / (8 * C));
     uint32_t r = 0;
     for (uint32_t lo = 0; lo < N;) {
@@ -197,8 +199,8 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
   for (uint32_t r = 0; r < C; ++r) {
     const uint32_t lo = std::min(N, r * M), hi = std::min(N, (r + 1) * M);
     std::vector<uint32_t> mine(order.begin() + lo, order.begin() + hi);
-    if (d->wantPartition == 3 && C > 1) mine = dealt[r];
-    if (d->wantPartition != 2)
+    if (partMode == 3 && C > 1) mine = dealt[r];
+    if (partMode != 2)
       std::stable_sort(mine.begin(), mine.end(), [&](uint32_t a, uint32_t b) { return inDeg(a) > inDeg(b); });
     for (uint32_t j = 0; j < mine.size(); ++j) {
       P.origOf[r * M + j] = mine[j];
@@ -388,53 +390,52 @@ static int buildPlanPush(dnab_decoder* d, int32_t planLen) {
   PushTables T;
   std::vector<uint32_t> cands = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16};
   if (d->wantC >= 1 && d->wantC <= (uint32_t)kMaxCluster) cands = {d->wantC};
-  // Preference: the smallest cluster whose CTAs hold S, D and the out-table in shared memory (more reads
-  // in flight beats more SMs per read); then S(pos-1) and the T columns when they fit too.  A machine
-  // too large for that keeps its out-table in global memory (second sweep over the candidates).
-  for (uint32_t needOut = 1; needOut + 1 > 0 && !best.C; --needOut) {
-    if (d->wantBlockMode == 2 && needOut) continue;
-    if (d->wantBlockMode == 1 && !needOut) break;
-    for (uint32_t C : cands) {
-      const uint32_t M = (N + C - 1) / C;
-      if (M > 65535) continue;
-      const uint32_t threads = pushThreads(d, M);
-      if (makePushLayout(M, k, 0, 0, 0, 64, 1, (uint32_t)planLen, 1024).total > d->smemOptin) continue;
-      int rc = buildPartition(d, C, P);
-      if (rc != DNAB_OK) return rc;
-      rc = buildPushTables(d, P, threads * kPushStatesPerThread, T);
-      if (rc != DNAB_OK) {
-        if (d->wantC) return rc;
-        continue;
-      }
-      // (S(pos-1) in smem, T in smem, full-size level queue); a short queue defers states to the next level
-      const uint32_t opts[6][3] = {{1, 1, 1}, {1, 0, 1}, {0, 1, 1}, {0, 0, 1}, {0, 1, 0}, {0, 0, 0}};
-      for (const auto& o : opts) {
-        const uint32_t sIn = o[0], tIn = (k == 0) ? 0 : o[1];
-        const uint32_t qCap = o[2] ? M : std::max<uint32_t>(1024, M / 4);
-        if (d->wantSPrevMode == 1 && !sIn) continue;
-        if (d->wantSPrevMode == 2 && sIn) continue;
-        if (d->wantTMode == 1 && k && !tIn) continue;
-        if (d->wantTMode == 2 && tIn) continue;
-        const uint32_t smem =
-            makePushLayout(M, k, tIn, sIn, needOut ? T.maxOutBytes : 0, T.maxChunkBytes, T.nChunks, (uint32_t)planLen, qCap).total;
-        if (smem <= d->smemOptin) {
-          best.C = C;
-          best.M = M;
-          best.threads = threads;
-          best.tInSmem = tIn;
-          best.sPrevGlobal = sIn ? 0 : 1;
-          best.outInSmem = needOut;
-          best.outBytes = needOut ? T.maxOutBytes : 0;
-          best.chunkBytes = T.maxChunkBytes;
-          best.queueCap = qCap;
-          best.smemBytes = smem;
-          best.push = 1;
-          break;
-        }
-      }
-      if (best.C) break;
+  // Preference: the smallest cluster whose CTAs hold S and D (more reads in flight beats more SMs per
+  // read, and fewer transitions cross CTAs); within it the out-table, then S(pos-1), then the T columns
+  // join them in shared memory when they fit.  Measured on B200 with the BASELINE config-2 machine:
+  // 4 CTAs per read with the out-table in L2 decode 11% more reads per second than 6 CTAs per read
+  // with the out-table in shared memory.
+  for (uint32_t C : cands) {
+    const uint32_t M = (N + C - 1) / C;
+    if (M > 65535) continue;
+    const uint32_t threads = pushThreads(d, M);
+    if (makePushLayout(M, k, 0, 0, 0, 64, 1, (uint32_t)planLen, 1024).total > d->smemOptin) continue;
+    int rc = buildPartition(d, C, P);
+    if (rc != DNAB_OK) return rc;
+    rc = buildPushTables(d, P, threads * kPushStatesPerThread, T);
+    if (rc != DNAB_OK) {
+      if (d->wantC) return rc;
+      continue;
     }
-    if (!needOut) break;
+    // (out-table in smem, S(pos-1) in smem, T in smem, full-size level queue); a short queue defers states to the next level
+    const uint32_t opts[8][4] = {{1, 1, 1, 1}, {1, 1, 0, 1}, {1, 0, 1, 1}, {1, 0, 0, 1}, {1, 0, 0, 0}, {0, 0, 1, 1}, {0, 0, 0, 1}, {0, 0, 0, 0}};
+    for (const auto& o : opts) {
+      const uint32_t needOut = o[0], sIn = o[1], tIn = (k == 0) ? 0 : o[2];
+      const uint32_t qCap = o[3] ? M : std::max<uint32_t>(1024, M / 4);
+      if (d->wantBlockMode == 1 && !needOut) continue;
+      if (d->wantBlockMode == 2 && needOut) continue;
+      if (d->wantSPrevMode == 1 && !sIn) continue;
+      if (d->wantSPrevMode == 2 && sIn) continue;
+      if (d->wantTMode == 1 && k && !tIn) continue;
+      if (d->wantTMode == 2 && tIn) continue;
+      const uint32_t smem =
+          makePushLayout(M, k, tIn, sIn, needOut ? T.maxOutBytes : 0, T.maxChunkBytes, T.nChunks, (uint32_t)planLen, qCap).total;
+      if (smem <= d->smemOptin) {
+        best.C = C;
+        best.M = M;
+        best.threads = threads;
+        best.tInSmem = tIn;
+        best.sPrevGlobal = sIn ? 0 : 1;
+        best.outInSmem = needOut;
+        best.outBytes = needOut ? T.maxOutBytes : 0;
+        best.chunkBytes = T.maxChunkBytes;
+        best.queueCap = qCap;
+        best.smemBytes = smem;
+        best.push = 1;
+        break;
+      }
+    }
+    if (best.C) break;
   }
   if (!best.C) {
     setLastError("machine does not fit: " + std::to_string(N) +
@@ -649,6 +650,7 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
     fa.idleSleepNs = d->idleSleepNs;
     fa.tailN = std::min<uint32_t>(d->tailN, d->plan.threads);
     fa.tailHops = d->tailHops;
+    fa.tRecompute = d->tRecompute;
     fa.maxLen = maxLen;
     fa.packed = dPacked;
     fa.byteOff = dByteOff + at;
@@ -679,6 +681,11 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
     }
     const bool rec = timeIt || pooled;
     if (rec) CUDA_TRY(cudaEventRecord(e0, stream));
+    if (d->plan.push) {
+      CUDA_TRY(d->dNextRead.ensure(1));
+      CUDA_TRY(cudaMemsetAsync(d->dNextRead.p, 0, sizeof(unsigned long long), stream));
+      fa.nextRead = d->dNextRead.p;
+    }
     if (d->plan.push)
       CUDA_TRY(launchFillPush(d->dev, fa, nClusters, d->plan.threads, d->plan.smemBytes, stream));
     else
@@ -744,6 +751,7 @@ dnab_decoder* dnab_decoder_create(const dnab_tables* t, int device) {
   }
   if (const char* e = getenv("DNAB_TAIL_N")) d->tailN = (uint32_t)atoi(e);
   if (const char* e = getenv("DNAB_TAIL_HOPS")) d->tailHops = (uint32_t)atoi(e);
+  if (const char* e = getenv("DNAB_T_RECOMPUTE")) d->tRecompute = (uint32_t)atoi(e);
   d->smCount = prop.multiProcessorCount;
   d->smemOptin = prop.sharedMemPerBlockOptin;
   size_t freeB = 0, totalB = 0;

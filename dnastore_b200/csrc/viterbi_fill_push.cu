@@ -159,7 +159,7 @@ constexpr uint32_t kNoState = 0xFFFFFFFFu;
 // Loads that do not depend on each other are issued together: the chain is cells+offsets -> edge word
 // -> destination cells -> add/compare -> compare-and-swap (only when the destination grows).
 template <bool kCluster>
-__device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, bool& flagged) {
+__device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, bool& flagged, bool& sent) {
   const uint32_t myS = c.aS + 8 * s, myD = c.aD + 8 * s;
   uint32_t o0, o1;
   if (c.outInSmem) {
@@ -216,7 +216,7 @@ __device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, bool& fl
         asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(mapToRank(c.aFlag + 4 * (l >> 5), r)),
                      "r"(1u << (l & 31))
                      : "memory");
-        flagged = true;
+        sent = true;
       }
     }
   }
@@ -235,7 +235,6 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   const uint32_t C = kCluster ? tb.C : 1u, M = tb.M, k = tb.k;
   const uint32_t rank = kCluster ? cluster.block_rank() : 0;
   const uint32_t clusterId = blockIdx.x / C;
-  const uint32_t nClusters = gridDim.x / C;
   const uint32_t tid = threadIdx.x, nThreads = blockDim.x;
   const uint32_t lane = tid & 31;
   const uint32_t Np = C * M;
@@ -243,6 +242,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   const PushLayout& lay = args.play;
   const uint32_t sm = smemAddr(smem);
   const bool sPrevSmem = tb.sPrevInSmem != 0;
+  const bool tRecompute = !sPrevSmem && tb.k <= 2 && args.tRecompute;
 
   const uint32_t aD = sm + lay.dBuf, aFlag = sm + lay.flag, aSym = sm + lay.symScore, aSub = sm + lay.sub;
   const uint32_t aTsE = sm + lay.tsE, aExt = sm + lay.tsDext, aOpen = sm + lay.tsDopen;
@@ -355,7 +355,28 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                      dbgClusterWait = 0, dbgDirty = 0, dbgScan = 0, dbgPush = 0, dbgPushWait = 0, dbgHops = 0;
   const bool dbgOn = args.dbg != nullptr;
 
-  for (int64_t read = clusterId; read < args.nReads; read += nClusters) {
+  // Reads are handed out dynamically (one global counter, fetched by rank 0 and broadcast through
+  // distributed shared memory): reads differ in length, and a static stride leaves the clusters that
+  // drew short reads idle at the end of the launch.
+  auto nextRead = [&]() -> int64_t {
+    if (rank == 0 && tid == 0) {
+      const unsigned long long r = atomicAdd(args.nextRead, 1ull);
+      for (uint32_t p = 0; p < C; ++p) {
+        if (kCluster) {
+          stPeerU32(sm + lay.ctl + 8 * 4, p, (uint32_t)r);
+          stPeerU32(sm + lay.ctl + 9 * 4, p, (uint32_t)(r >> 32));
+        } else {
+          ctl[8] = (uint32_t)r;
+          ctl[9] = (uint32_t)(r >> 32);
+        }
+      }
+    }
+    clusterBarrier();
+    const int64_t r = (int64_t)(((unsigned long long)ctl[9] << 32) | ctl[8]);
+    clusterBarrier();  // everyone has read the slot before rank 0 may overwrite it
+    return r;
+  };
+  for (int64_t read = nextRead(); read < args.nReads; read = nextRead()) {
     const int32_t L = args.readLen[read];
     {  // stage the packed read
       const uint8_t* src = args.packed + args.byteOff[read];
@@ -388,6 +409,26 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
       // record of slot u of this thread in the staged chunk, and its header (padding header when out of range)
       auto recOf = [&](uint32_t u) -> uint32_t { return aBuf + recBase + 4 * lds16(aBuf + 2 * (u * nThreads + tid)); };
 
+      // Duplication cells without storing them (k <= 2, S columns published in global scratch): T(p,1) =
+      // (S(p)+tanDup)+len[1] and T(p,0) = max(T(p-1,1)+sub[ctx1][x_p], (S(p)+tanDup)+len[0]) are functions of
+      // the state's own S(p), S(p-1) (src/viterbi.cpp:105-106,161-168), so T(pos-1,0) and T(pos-1,1) are
+      // re-derived from S(pos-1), S(pos-2) with the reference's own operations instead of being kept
+      // in L2-resident scratch (4 fewer 8-byte global accesses per state in each of the two passes).
+      const uint32_t xPrev = pos > 1 ? (seqS[(pos - 2) >> 2] >> (2 * ((pos - 2) & 3))) & 3u : 0u;
+      auto dupPrev = [&](uint32_t h, double s1, double s2, double& tPrev0, double& tPrev1) {
+        const uint32_t mdl = inMdl(h);
+        tPrev0 = NEG;
+        tPrev1 = NEG;
+        if (pos < 2 || mdl == 0) return;  // T(0,.) = -inf: duplications open from column 1 on
+        if (mdl == 1) {
+          tPrev0 = (s1 + tb.tanDup) + lenS[0];
+          return;
+        }
+        tPrev1 = (s1 + tb.tanDup) + lenS[1];
+        const double shifted = pos >= 3 ? ((s2 + tb.tanDup) + lenS[1]) + subS[inCtx(h, 1) * 4 + xPrev] : NEG;
+        tPrev0 = dmax(shifted, (s1 + tb.tanDup) + lenS[0]);
+      };
+
       long long tc0 = dbgOn ? clock64() : 0;
       // ---- (1) emission step: S0 from the previous column, T shift (src/viterbi.cpp:92-106) ----
       for (uint32_t j = 0; j < nChunks; ++j) {
@@ -403,7 +444,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           s[u] = NEG;
           t0[u] = NEG;
           if (pos > 0) {
-            if (inMdl(h[u]) > 0) t0[u] = tCol[i[u]];
+            if (inMdl(h[u]) > 0) {
+              if (tRecompute) {
+                double t1;
+                dupPrev(h[u], ldsCell(aScur + 8 * i[u]), sCurG[rank * M + i[u]], t0[u], t1);  // S(pos-1) is still in place
+              } else
+                t0[u] = tCol[i[u]];
+            }
             maxE = max(maxE, inNEmit(h[u]));
           }
         }
@@ -413,7 +460,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             if (i[u] < M) {
               const bool real = inNIn(h[u]) != kInPad;
               s[u] = (real && (tb.local || rank * M + i[u] == tb.startG)) ? 0.0 : NEG;  // src/viterbi.cpp:75-79
-              for (uint32_t t = 0; t < k; ++t) tCol[t * M + i[u]] = NEG;
+              if (!tRecompute)
+                for (uint32_t t = 0; t < k; ++t) tCol[t * M + i[u]] = NEG;
             }
         } else {
           for (uint32_t e = 0; e < maxE; ++e) {
@@ -435,9 +483,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             if (mdl > 0) {
               const double t2s = t0[u] + subS[inCtx(h[u], 0) * 4 + x];
               s[u] = dmax(s[u], t2s);
-              for (uint32_t t = 0; t + 1 < mdl; ++t)
-                tCol[t * M + i[u]] = tCol[(t + 1) * M + i[u]] + subS[inCtx(h[u], t + 1) * 4 + x];
-              tCol[(mdl - 1) * M + i[u]] = t2s;  // slot mdl-1 is free until step (4): park the T->S candidate there
+              if (!tRecompute) {
+                for (uint32_t t = 0; t + 1 < mdl; ++t)
+                  tCol[t * M + i[u]] = tCol[(t + 1) * M + i[u]] + subS[inCtx(h[u], t + 1) * 4 + x];
+                tCol[(mdl - 1) * M + i[u]] = t2s;  // slot mdl-1 is free until step (4): park the T->S candidate there
+              }
             }
           }
         }
@@ -516,17 +566,21 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
       // compacted into a CTA-wide queue (one lane per bitmap word, one shared-memory atomic per warp);
       // after a CTA barrier every thread pushes the queued states, one state per thread and step, so
       // that all lanes of a warp work whatever the shape of the frontier; a destination that grew is
-      // flagged (this CTA's bitmap or a peer's) for the next level.  The level ends with a barrier of
-      // the CTA -- of the cluster when there are peers, which also makes the flags they set visible --
-      // and the closure ends when a level flagged nothing anywhere.
+      // flagged (this CTA's bitmap or a peer's) for the next level.  A level ends with a CTA barrier;
+      // when the CTA is quiet it meets the cluster, and the closure ends when nothing crossed CTAs
+      // since the last meeting (a per-level cluster barrier measured slower: every level then waits
+      // for the slowest CTA).
       {
         const uint32_t nWords = (M + 31) / 32, cap = lay.queueCap;
         const uint32_t aQueue = sm + lay.queue, aTail = sm + lay.ctl;  // ctl[0], ctl[1]: queue tails, by level parity
+        uint32_t round = 0;
+        bool sent = false;
         for (uint32_t levels = 0;; ++levels) {
           const uint32_t par = levels & 1;
           const long long tl0 = dbgOn ? clock64() : 0;
           bool flagged = false;
           for (uint32_t base = 0; base < nWords; base += nThreads) {
+            if (base + (tid & ~31u) >= nWords) break;  // warp-uniform: this warp has no bitmap word to scan
             const uint32_t wi = base + tid;
             const uint32_t aWord = aFlag + 4 * wi;
             uint32_t taken = (wi < nWords && ldsVolatile32(aWord)) ? atomExchShared(aWord, 0u) : 0u;
@@ -567,7 +621,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           if (n > args.tailN) {
             // wide frontier: one hop per level, breadth first
             for (uint32_t q = tid; q < n; q += nThreads) {
-              const uint32_t nx = pushState<kCluster>(c, lds16(aQueue + 2 * q), flagged);
+              const uint32_t nx = pushState<kCluster>(c, lds16(aQueue + 2 * q), flagged, sent);
               if (nx != kNoState) {
                 redOrShared(aFlag + 4 * (nx >> 5), 1u << (nx & 31));
                 flagged = true;
@@ -581,7 +635,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             uint32_t s = tid < n ? lds16(aQueue + 2 * tid) : kNoState;
             for (uint32_t hop = 0; hop < args.tailHops; ++hop) {
               if (__ballot_sync(0xFFFFFFFFu, s != kNoState) == 0u) break;
-              if (s != kNoState) s = pushState<kCluster>(c, s, flagged);
+              if (s != kNoState) s = pushState<kCluster>(c, s, flagged, sent);
               if (dbgOn && tid == 0) ++dbgHops;
             }
             if (s != kNoState) {  // hop budget spent
@@ -592,19 +646,25 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           if (dbgOn && tid == 0) dbgWork += n;
           const long long tl2 = dbgOn ? clock64() : 0;
           const uint32_t anyFlagged = (uint32_t)__syncthreads_or(flagged ? 1 : 0);  // every push of this level has set its flags
-          uint32_t tot = anyFlagged;
-          if (kCluster) {
-            if (tid < C) stPeerU32(sm + lay.ctl + (16 + par * kMaxCluster + rank) * 4, tid, anyFlagged);
-            cluster.sync();
-            tot = 0;
-            for (uint32_t r = 0; r < C; ++r) tot |= ctl[16 + par * kMaxCluster + r];
-          }
           if (dbgOn && tid == 0) {
             const long long tl3 = clock64();
             dbgScan += tl1 - tl0;
             dbgPush += tl2 - tl1;
             dbgPushWait += tl3 - tl2;
           }
+          if (anyFlagged) continue;  // this CTA is not quiet yet
+          if (!kCluster) break;
+          // locally quiet: meet the cluster; another round if anything crossed CTAs since the last meeting
+          const long long tcb = dbgOn ? clock64() : 0;
+          const uint32_t anySent = (uint32_t)__syncthreads_or(sent ? 1 : 0);
+          sent = false;
+          if (tid < C) stPeerU32(sm + lay.ctl + (16 + (round & 1) * kMaxCluster + rank) * 4, tid, anySent);
+          cluster.sync();
+          if (dbgOn && tid == 0) dbgClusterWait += clock64() - tcb;
+          uint32_t tot = 0;
+          for (uint32_t r = 0; r < C; ++r) tot |= ctl[16 + (round & 1) * kMaxCluster + r];
+          ++round;
+          if (dbgOn && tid == 0 && tot) ++dbgRounds;
           if (!tot) break;
         }
       }
@@ -616,7 +676,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
       for (uint32_t j = 0; j < nChunks; ++j) {
         prefetch();
         uint32_t i[kU], rec[kU], h[kU], nIn[kU], idx[kU], idxD[kU];
-        double sHere[kU], dHere[kU], parked[kU], best[kU], bestD[kU];
+        double sHere[kU], dHere[kU], parked[kU], tPrev1[kU], best[kU], bestD[kU];
         uint32_t maxIn = 0;
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
@@ -628,7 +688,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           const uint32_t mdl = inMdl(h[u]);
           sHere[u] = i[u] < M ? ldsCell(aScur + 8 * i[u]) : NEG;
           dHere[u] = i[u] < M ? ldsCell(aD + 8 * i[u]) : NEG;
-          parked[u] = (mdl > 0 && pos > 0) ? tCol[(mdl - 1) * M + i[u]] : NEG;  // T(state,pos-1,0)+sub
+          tPrev1[u] = NEG;
+          if (tRecompute) {
+            double tPrev0 = NEG;
+            if (i[u] < M && mdl > 0 && pos > 0) dupPrev(h[u], sPrevG[rank * M + i[u]], sCurG[rank * M + i[u]], tPrev0, tPrev1[u]);
+            parked[u] = (mdl > 0 && pos > 0) ? tPrev0 + subS[inCtx(h[u], 0) * 4 + x] : NEG;
+          } else
+            parked[u] = (mdl > 0 && pos > 0) ? tCol[(mdl - 1) * M + i[u]] : NEG;  // T(state,pos-1,0)+sub
           best[u] = NEG;
           bestD[u] = NEG;
           idx[u] = kNoPred;
@@ -710,21 +776,26 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             }
             predCol[g] = (uint8_t)(real ? idx[u] : kNoPred);
             predCol[Np + g] = (uint8_t)(real ? idxD[u] : kNoPred);
-            for (uint32_t t = 0; t < k; ++t) {
-              uint32_t idxT = kNoPred;
-              if (pos > 0 && t < mdl) {
-                const double shifted = (t + 1 < mdl) ? tCol[t * M + i[u]] : NEG;
-                if (t + 1 < mdl && shifted > NEG) idxT = 0;
-                if (sHere[u] + tsT[t] > shifted) idxT = 1;
-                tCol[t * M + i[u]] = dmax(shifted, (sHere[u] + tb.tanDup) + lenS[t]);  // (4)
-              }
-              predCol[(size_t)(2 + t) * Np + g] = (uint8_t)idxT;
-            }
-            if (args.cells && read == 0 && real) {
-              double* cell = args.cells + ((size_t)pos * tb.nStates + __ldg(&tb.origId[g])) * (k + 2);
+            double* cell = (args.cells && read == 0 && real)
+                               ? args.cells + ((size_t)pos * tb.nStates + __ldg(&tb.origId[g])) * (k + 2)
+                               : nullptr;
+            if (cell) {
               cell[0] = sHere[u];
               cell[1] = dHere[u];
-              for (uint32_t t = 0; t < k; ++t) cell[2 + t] = (pos > 0 && t < mdl) ? tCol[t * M + i[u]] : NEG;
+            }
+            for (uint32_t t = 0; t < k; ++t) {
+              uint32_t idxT = kNoPred;
+              double tNow = NEG;
+              if (pos > 0 && t < mdl) {
+                double shifted = NEG;
+                if (t + 1 < mdl) shifted = tRecompute ? tPrev1[u] + subS[inCtx(h[u], 1) * 4 + x] : tCol[t * M + i[u]];
+                if (t + 1 < mdl && shifted > NEG) idxT = 0;
+                if (sHere[u] + tsT[t] > shifted) idxT = 1;
+                tNow = dmax(shifted, (sHere[u] + tb.tanDup) + lenS[t]);  // (4)
+                if (!tRecompute) tCol[t * M + i[u]] = tNow;
+              }
+              predCol[(size_t)(2 + t) * Np + g] = (uint8_t)idxT;
+              if (cell) cell[2 + t] = tNow;
             }
           }
         commit();

@@ -141,6 +141,7 @@ struct FillArgs {
   uint32_t idleSleepNs;      // back-off of a warp whose closure sweep found nothing to do
   uint32_t tailN;            // push kernel: a closure level with at most this many dirty states (<= threads) runs in lockstep-chain mode
   uint32_t tailHops;         // push kernel: hop budget of one lockstep-chain episode
+  uint32_t tRecompute;       // push kernel: re-derive the duplication cells from S(pos-1), S(pos-2) (k <= 2) instead of storing them
   const uint8_t* packed;     // 2-bit reads
   const int64_t* byteOff;    // [nReads]
   const int32_t* readLen;    // [nReads]
@@ -154,6 +155,7 @@ struct FillArgs {
   uint32_t* partG;           //             ... and padded index
   double* cells;             // optional debug dump of read 0: [(L+1)][nStates][k+2]
   unsigned long long* dbg;   // optional [16] profiling counters (see dnab_decoder_debug_counters)
+  unsigned long long* nextRead;  // push kernel: the next read to hand to a cluster (zeroed before every launch)
 };
 
 struct TracebackArgs {

@@ -76,6 +76,23 @@ def test_gpu_memory_placements_and_partitions(d, name, cluster, table_mode, part
         raise
 
 
+@pytest.mark.parametrize("name", ["l4c4_global_mixed", "l4c4_local_mixed", "cfg2_global_subs", "cfg3_global_indels", "cfg4_global_dels"])
+def test_gpu_pull_kernel_same_bits(d, name):
+    """The first fill kernel (pull-style closure, viterbi_kernels.cu; partition_mode tens digit 1) stays
+    selectable and must give the same bits as the push kernel that is now the default."""
+    _check_against_golden(d, util.golden_case(name), dict(partition_mode=10))
+
+
+@pytest.mark.parametrize("env", [dict(DNAB_TAIL_N="64", DNAB_TAIL_HOPS="8"), dict(DNAB_T_RECOMPUTE="0")])
+@pytest.mark.parametrize("name", ["l4c4_global_mixed", "cfg3_global_indels", "cfg2_global_subs"])
+def test_gpu_push_kernel_tuning_knobs_same_bits(d, name, env, monkeypatch):
+    """Lockstep-chain mode for thin frontiers and stored (not re-derived) duplication cells are
+    schedule / placement choices of the push kernel: no bit may change."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _check_against_golden(d, util.golden_case(name))
+
+
 @pytest.mark.parametrize("threads", [32, 96, 256, 1024])
 def test_gpu_every_block_size(d, threads):
     _check_against_golden(d, util.golden_case("l4c4_global_mixed"), dict(threads_per_cta=threads))
