@@ -10,7 +10,7 @@ synthetic reads per GPU; reads are independent, so ranks shard the batch with no
             the launching stream, barrier + synchronize on both sides, max over ranks)
   e2e       the same metric through the C-ABI host-buffer call dnab_viterbi_batch (pinned host
             buffers, H2D of reads and D2H of decoded strings / log-likelihoods inside the timed region)
-  roofline  HBM roofline of the dominant kernel (viterbiFillKernel): algorithmic bytes
+  roofline  HBM roofline of the dominant kernel (viterbiFillPushKernel): algorithmic bytes
             = 1 B per DP cell + ceil(L/4) + |decoded| + 8 per read / its CUDA-event time
   cpu_baseline  the reference's own CPU decoder (oracle/_ref/dnastore when it was built, else the
             oracle port) on a bounded sample of the same reads, one core, decoded strings compared
@@ -362,6 +362,15 @@ def main():
         algo_bytes = my_cells + sum(int(np.sum((batches[b][3].astype(np.int64) + 3) // 4)) for b in range(args.warmup, n_batches)) \
             + int(dec_len_last.sum()) * args.steps + 8 * my_reads
         achieved = algo_bytes / (st["timed_fill_ms"] * 1e-3) / 1e9
+        fill_kernel = "viterbiFillKernel" if args.partition >= 10 else "viterbiFillPushKernel"
+        # DRAM traffic of one launch: measured once with `ncu --set full` (profiles/), scaled to this launch
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_fill_traffic.json")
+        if os.path.exists(tp) and args.workload == "cfg2":
+            tj = json.load(open(tp))
+            if tj.get("kernel") == fill_kernel:
+                traffic = tj["dram_over_algorithmic"] * algo_bytes / fl
+                traffic_src = tj["capture"]
         # CPU baseline on a bounded sample of the last batch: one core, decoded strings must match the GPU's
         cpu = None
         if args.cpu_sample > 0:
@@ -389,8 +398,9 @@ def main():
             e2e=dict(value=tot_e2e_cells / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      steps=e2e_steps, reads_per_sec=rps * e2e_steps * world / e2e_s),
             gpu_launches=int(tot_launches),
-            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
-                          kernel="viterbiFillKernel", launches=fl, avg_launch_ms=st["timed_fill_ms"] / fl,
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                          traffic=traffic, traffic_source=traffic_src,
+                          kernel=fill_kernel, launches=fl, avg_launch_ms=st["timed_fill_ms"] / fl,
                           peak_source=peak_src, algorithmic_bytes_per_launch=algo_bytes / fl,
                           fill_share_of_step=fill_ms / elapsed_ms, traceback_share_of_step=tb_ms / elapsed_ms),
             cpu_baseline=cpu, clocks=clocks)
