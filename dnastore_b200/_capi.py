@@ -148,6 +148,7 @@ _sig("dnab_pack_reads", C.c_int, C.c_char_p, _vp, C.c_int64, _vp, _vp, _vp)
 _sig("dnab_viterbi_batch", C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp)
 _sig("dnab_viterbi_batch_device", C.c_int, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp)
 _sig("dnab_viterbi_cells", C.c_int, _vp, _vp, C.c_int32, _vp, _vp)
+_sig("dnab_forward_batch", C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp)
 _sig("dnab_mutator_params_from_flags", None, C.POINTER(ErrorFlags), C.POINTER(MutatorParams))
 _sig("dnab_mutator_params_json", _vp, C.POINTER(MutatorParams))
 _sig("dnab_mutator_counts_json", _vp, C.POINTER(MutatorCounts))
@@ -468,6 +469,25 @@ class Decoder:
         if rc:
             raise _err(rc)
         return ll.value, cells
+
+    def forward(self, reads, max_sweeps=0, want_cells=False):
+        """Forward (sum-product) log-likelihoods over the machine lattice (not in the
+        reference, specified by oracle/forward_oracle.c). Returns dict(loglike, sweeps, status[, cells of read 0])."""
+        packed, byte_off, read_len = pack_reads(reads)
+        n = len(read_len)
+        t = self._compiled.t
+        ll = np.zeros(n, dtype=np.float64)
+        sweeps = np.zeros(n, dtype=np.int64)
+        status = np.zeros(n, dtype=np.int32)
+        cells = np.zeros((int(read_len[0]) + 1, t.n_states, t.k + 2), dtype=np.float64) if (want_cells and n) else None
+        rc = lib.dnab_forward_batch(self._h, n, _ptr(packed), _ptr(byte_off), _ptr(read_len), int(max_sweeps), _ptr(ll),
+                                    _ptr(sweeps), _ptr(status), _ptr(cells) if cells is not None else None)
+        if rc:
+            raise _err(rc)
+        out = dict(loglike=ll, sweeps=sweeps, status=status)
+        if cells is not None:
+            out["cells"] = cells
+        return out
 
     def viterbi_device(self, n_reads, max_read_len, d_packed, d_byte_off, d_read_len, d_loglike, d_decoded, decoded_stride,
                        d_decoded_len, d_status, stream=0):

@@ -91,6 +91,12 @@ struct dnab_decoder {
   DevBuf<double> dTScratch, dSScratch, dPartVal, dCells;
   DevBuf<uint32_t> dStart, dPartOrig, dPartG;
   DevBuf<unsigned long long> dDbg, dNextRead;
+  // forward kernel (forward_kernels.cu): CSR tables in reference order, uploaded on first use
+  bool fwdReady = false;
+  DevBuf<uint32_t> dFwdEmitOff, dFwdEmitSrc, dFwdNullOff, dFwdNullSrc;
+  DevBuf<uint8_t> dFwdEmitMeta, dFwdNullSym, dFwdCtx, dFwdMdl;
+  DevBuf<double> dFwdLse, dFwdScratch;
+  DevBuf<long long> dFwdSweeps;
   bool debug = false;
   // staging for the host-buffer path
   DevBuf<uint8_t> dPacked;
@@ -994,6 +1000,113 @@ int dnab_viterbi_batch(dnab_decoder* d, int64_t n_reads, const uint8_t* packed, 
                        int32_t* decoded_len, int32_t* status, int32_t* path, int32_t path_stride, int32_t* path_len) {
   return viterbiHost(d, n_reads, packed, read_byte_off, read_len, loglike, decoded, decoded_stride, decoded_len, status,
                      path, path_stride, path_len, nullptr);
+}
+
+int dnab_forward_batch(dnab_decoder* d, int64_t n, const uint8_t* packed, const int64_t* byteOff, const int32_t* readLen,
+                       int32_t maxSweeps, double* loglike, int64_t* sweeps, int32_t* status, double* cells) {
+  if (!d || n < 0 || !loglike) {
+    setLastError("dnab_forward_batch: bad argument");
+    return DNAB_EINVAL;
+  }
+  if (n == 0) return DNAB_OK;
+  CUDA_TRY(cudaSetDevice(d->device));
+  const uint32_t N = d->nStates, k = d->k;
+  if (!d->fwdReady) {
+    std::vector<uint8_t> meta(d->emitSym.size());
+    for (size_t e = 0; e < meta.size(); ++e) meta[e] = (uint8_t)(d->emitSym[e] | (d->emitBase[e] << 5));
+    int32_t nLse = 0;
+    const double* lseHost = dnab_lse_table(&nLse);
+    std::vector<double> lseV(lseHost, lseHost + nLse);
+    lseV.push_back(0.);  // lseUnary reads table[n+1]
+    CUDA_TRY(d->dFwdEmitOff.upload(d->emitOff));
+    CUDA_TRY(d->dFwdEmitSrc.upload(d->emitSrc));
+    CUDA_TRY(d->dFwdEmitMeta.upload(meta));
+    CUDA_TRY(d->dFwdNullOff.upload(d->nullOff));
+    CUDA_TRY(d->dFwdNullSrc.upload(d->nullSrc));
+    CUDA_TRY(d->dFwdNullSym.upload(d->nullSym));
+    CUDA_TRY(d->dFwdCtx.upload(d->ctx));
+    CUDA_TRY(d->dFwdMdl.upload(d->mdl));
+    CUDA_TRY(d->dFwdLse.upload(lseV));
+    d->fwdReady = true;
+  }
+  int32_t maxLen = 0;
+  size_t packedBytes = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    maxLen = std::max(maxLen, readLen[r]);
+    packedBytes = std::max<size_t>(packedBytes, (size_t)byteOff[r] + ((((size_t)readLen[r] + 3) / 4 + 15) & ~(size_t)15));
+  }
+  if (maxLen > 16000) {
+    setLastError("dnab_forward_batch: reads longer than 16000 bases are not supported");
+    return DNAB_EINVAL;
+  }
+  packedBytes = std::max<size_t>(packedBytes, 16);
+  const uint32_t nBlocks = (uint32_t)std::min<int64_t>(n, d->smCount);
+  CUDA_TRY(d->dPacked.ensure(packedBytes));
+  CUDA_TRY(d->dByteOff.ensure((size_t)n));
+  CUDA_TRY(d->dReadLen.ensure((size_t)n));
+  CUDA_TRY(d->dLoglike.ensure((size_t)n));
+  CUDA_TRY(d->dStatus.ensure((size_t)n));
+  CUDA_TRY(d->dFwdSweeps.ensure((size_t)n));
+  CUDA_TRY(d->dFwdScratch.ensure((size_t)nBlocks * (6 + 2 * k) * N));
+  CUDA_TRY(d->dNextRead.ensure(1));
+  size_t cellCount = 0;
+  if (cells) {
+    cellCount = (size_t)(readLen[0] + 1) * N * (k + 2);
+    CUDA_TRY(d->dCells.ensure(cellCount));
+  }
+  cudaStream_t stream = nullptr;
+  CUDA_TRY(cudaMemcpyAsync(d->dPacked.p, packed, packedBytes, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(d->dByteOff.p, byteOff, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(d->dReadLen.p, readLen, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemsetAsync(d->dNextRead.p, 0, sizeof(unsigned long long), stream));
+  ForwardTables ft{};
+  ft.nStates = N;
+  ft.k = k;
+  ft.local = d->local;
+  ft.nSyms = (uint32_t)d->symChar.size();
+  ft.emitOff = d->dFwdEmitOff.p;
+  ft.emitSrc = d->dFwdEmitSrc.p;
+  ft.emitMeta = d->dFwdEmitMeta.p;
+  ft.nullOff = d->dFwdNullOff.p;
+  ft.nullSrc = d->dFwdNullSrc.p;
+  ft.nullSym = d->dFwdNullSym.p;
+  ft.ctx = d->dFwdCtx.p;
+  ft.mdl = d->dFwdMdl.p;
+  ft.lseTable = d->dFwdLse.p;
+  for (int i = 0; i < kMaxSyms; ++i) ft.symScore[i] = i < (int)d->symScore.size() ? d->symScore[i] : 0.;
+  std::memcpy(ft.sub, d->sub, sizeof ft.sub);
+  std::memcpy(ft.len, d->len, sizeof ft.len);
+  ft.noGap = d->noGap;
+  ft.delOpen = d->delOpen;
+  ft.delExtend = d->delExtend;
+  ft.delEnd = d->delEnd;
+  ft.tanDup = d->tanDup;
+  ForwardArgs fa{};
+  fa.nReads = n;
+  fa.maxSweeps = maxSweeps > 0 ? maxSweeps : 4096;
+  fa.packed = d->dPacked.p;
+  fa.byteOff = d->dByteOff.p;
+  fa.readLen = d->dReadLen.p;
+  fa.scratch = d->dFwdScratch.p;
+  fa.loglike = d->dLoglike.p;
+  fa.sweeps = d->dFwdSweeps.p;
+  fa.status = d->dStatus.p;
+  fa.nextRead = d->dNextRead.p;
+  fa.cells = cells ? d->dCells.p : nullptr;
+  CUDA_TRY(cudaEventRecord(d->ev0, stream));
+  CUDA_TRY(launchForward(ft, fa, nBlocks, 1024, stream));
+  CUDA_TRY(cudaEventRecord(d->ev1, stream));
+  d->stats.kernel_launches += 1;
+  CUDA_TRY(cudaMemcpyAsync(loglike, d->dLoglike.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  std::vector<long long> sw(sweeps ? (size_t)n : 0);
+  if (sweeps) CUDA_TRY(cudaMemcpyAsync(sw.data(), d->dFwdSweeps.p, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, d->dStatus.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  if (cells) CUDA_TRY(cudaMemcpyAsync(cells, d->dCells.p, cellCount * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  for (size_t r = 0; r < sw.size(); ++r) sweeps[r] = (int64_t)sw[r];
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, d->ev0, d->ev1) == cudaSuccess) d->stats.last_fill_ms = ms;
+  return DNAB_OK;
 }
 
 int dnab_viterbi_cells(dnab_decoder* d, const uint8_t* packed, int32_t read_len, double* loglike, double* cells) {

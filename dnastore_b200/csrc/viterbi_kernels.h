@@ -177,6 +177,43 @@ struct TracebackArgs {
   int32_t* pathLen;
 };
 
+// ---------------------------------------------------------------------------
+// forward kernel (forward_kernels.cu): the destination-indexed CSR tables in reference order
+// ---------------------------------------------------------------------------
+struct ForwardTables {
+  uint32_t nStates, k, local, nSyms;
+  const uint32_t* emitOff;   // [N+1]
+  const uint32_t* emitSrc;   // [nEmit]
+  const uint8_t* emitMeta;   // [nEmit] symbol id | base << 5
+  const uint32_t* nullOff;   // [N+1]
+  const uint32_t* nullSrc;   // [nNull]
+  const uint8_t* nullSym;    // [nNull]
+  const uint8_t* ctx;        // [N*k]
+  const uint8_t* mdl;        // [N]
+  const double* lseTable;    // the reference's 100,001-entry log(1+exp(-x)) table (logsumexp.cpp:5-15)
+  double symScore[kMaxSyms];
+  double sub[16];
+  double len[kMaxK > 0 ? kMaxK : 1];
+  double noGap, delOpen, delExtend, delEnd, tanDup;
+};
+
+struct ForwardArgs {
+  int64_t nReads;
+  int32_t maxSweeps;
+  const uint8_t* packed;
+  const int64_t* byteOff;
+  const int32_t* readLen;
+  double* scratch;               // [nBlocks][(6+2k)*N]
+  double* loglike;               // [nReads]
+  long long* sweeps;             // [nReads] closure sweeps summed over the columns
+  int32_t* status;               // [nReads] 0 ok, 1 a closure did not settle within maxSweeps
+  unsigned long long* nextRead;  // zeroed before the launch
+  double* cells;                 // optional dump of read 0: [(L+1)][N][k+2]
+};
+
+cudaError_t launchForward(const ForwardTables& tb, const ForwardArgs& args, uint32_t nBlocks, uint32_t threads,
+                          cudaStream_t stream);
+
 cudaError_t queryMaxClusters(const DevTables& tb, uint32_t threads, uint32_t smemBytes, int* nClusters);
 cudaError_t launchFill(const DevTables& tb, const FillArgs& args, uint32_t nClusters, uint32_t threads,
                        uint32_t smemBytes, cudaStream_t stream);

@@ -168,6 +168,20 @@ int dnab_viterbi_batch_device(dnab_decoder* d, int64_t n_reads, int32_t max_read
  * (len+1)*n_states*(k+2) doubles (host memory). */
 int dnab_viterbi_cells(dnab_decoder* d, const uint8_t* packed, int32_t read_len, double* loglike, double* cells);
 
+/* Forward (sum-product) log-likelihood over the same machine-state x DNA-position lattice
+ * (SURVEY.md 8a-12).  NOT IN THE REFERENCE: the reference's only forward-backward is the pair-HMM
+ * of src/fwdback.cpp (dnab_pairhmm_fb_batch below).  Specified by analogy with ViterbiMatrix's fill
+ * (src/viterbi.cpp:62-176): every max becomes the reference's table-based log_sum_exp
+ * (src/logsumexp.h:19-74); the closure of a column is solved by synchronous sweeps that stop after
+ * the first sweep that changes no cell.  loglike = F_S(end, L) (global mode) or the log-sum over all
+ * states of F_S(., L) (local mode).  Host buffers; same packed-read format as dnab_viterbi_batch.
+ * sweeps[r] (optional) = closure sweeps summed over the columns of read r; status[r] = 0, or 1 when a
+ * closure did not settle within max_sweeps (0 = default 4096).  cells (optional, read 0 only):
+ * (len+1)*n_states*(k+2) doubles in the ViterbiMatrix layout. */
+int dnab_forward_batch(dnab_decoder* d, int64_t n_reads, const uint8_t* packed, const int64_t* read_byte_off,
+                       const int32_t* read_len, int32_t max_sweeps, double* loglike, int64_t* sweeps, int32_t* status,
+                       double* cells);
+
 /* Counters since creation: kernels launched by this library and DP cells filled. */
 typedef struct dnab_decoder_stats {
   uint64_t kernel_launches;

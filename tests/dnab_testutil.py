@@ -108,6 +108,28 @@ def oracle_viterbi(compiled, seq, want_cells=False, want_path=True):
                 path=path[:plen.value].tolist(), cells=cells)
 
 
+@functools.lru_cache(maxsize=None)
+def forward_oracle_lib():
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libforward_oracle.so"))
+    lib.dnab_oracle_forward.restype = C.c_int
+    lib.dnab_oracle_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_long), C.c_void_p]
+    return lib
+
+
+def oracle_forward(compiled, seq, want_cells=False, max_sweeps=4096):
+    """The forward specification (oracle/forward_oracle.c). Returns dict(rc, loglike, sweeps, cells)."""
+    t = compiled.t
+    tok = tokens(seq)
+    L = len(seq)
+    ll = C.c_double(0)
+    sw = C.c_long(0)
+    cells = np.zeros((L + 1, t.n_states, t.k + 2), dtype=np.float64) if want_cells else None
+    rc = forward_oracle_lib().dnab_oracle_forward(C.addressof(t), tok.ctypes.data, L, max_sweeps, C.byref(ll), C.byref(sw),
+                                                  cells.ctypes.data if want_cells else None)
+    return dict(rc=rc, loglike=ll.value, sweeps=sw.value, cells=cells)
+
+
 def hexf(x):
     """Canonical hex-float string of an fp64 (bit-exact comparisons; accepts C's %a output too)."""
     if isinstance(x, str):
