@@ -84,7 +84,8 @@ struct dnab_decoder {
   LaunchPlan plan;
   DevTables dev{};
   DevBuf<uint32_t> dBlocks, dBlockOff, dSliceOff, dOrigId;
-  DevBuf<uint32_t> dInChunks, dInChunkOff, dOutTable, dOutSliceOff;
+  DevBuf<uint32_t> dInChunks, dInChunkOff, dOutTable, dOutSliceOff, dOutOvf;
+  DevBuf<uint4> dOutSlots;
   DevBuf<uint8_t> dSymChar;
   // scratch
   DevBuf<uint8_t> dPred;
@@ -286,7 +287,8 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
 // Tables of the push kernel for a given partition and CTA size (formats: viterbi_device.cuh).
 struct PushTables {
   uint32_t chunkStates = 0, nChunks = 0, maxChunkBytes = 0, maxOutBytes = 0;
-  std::vector<uint32_t> inChunks, inChunkOff, outTable, outSliceOff;
+  std::vector<uint32_t> inChunks, inChunkOff, outTable, outSliceOff, outOvf;
+  std::vector<uint4> outSlots;
 };
 
 static int buildPushTables(const dnab_decoder* d, const Partition& P, uint32_t chunkStates, PushTables& T) {
@@ -375,6 +377,24 @@ static int buildPushTables(const dnab_decoder* d, const Partition& P, uint32_t c
     T.maxOutBytes = std::max<uint32_t>(T.maxOutBytes, ((uint32_t)T.outTable.size() - start) * 4);
   }
   T.outSliceOff[C] = (uint32_t)T.outTable.size();
+  // the same lists as 16-byte slots for the CTAs that read their out-table from L2
+  T.outSlots.assign(Np, make_uint4(0, 0, 0, 0));
+  T.outOvf.clear();
+  for (uint32_t g = 0; g < Np; ++g) {
+    std::vector<uint32_t> words;
+    for (uint32_t w : outs[g]) words.push_back(peRank(w) != g / M ? (w | (1u << 20)) : w);
+    uint4& slot = T.outSlots[g];
+    slot.x = (uint32_t)words.size();
+    if (words.size() <= 3) {
+      if (words.size() > 0) slot.y = words[0];
+      if (words.size() > 1) slot.z = words[1];
+      if (words.size() > 2) slot.w = words[2];
+    } else {
+      slot.y = (uint32_t)T.outOvf.size();
+      T.outOvf.insert(T.outOvf.end(), words.begin(), words.end());
+    }
+  }
+  T.outOvf.resize(T.outOvf.size() + 4, 0);
   return DNAB_OK;
 }
 
@@ -462,6 +482,8 @@ static int buildPlanPush(dnab_decoder* d, int32_t planLen) {
   CUDA_TRY(d->dInChunkOff.upload(T.inChunkOff));
   CUDA_TRY(d->dOutTable.upload(T.outTable));
   CUDA_TRY(d->dOutSliceOff.upload(T.outSliceOff));
+  CUDA_TRY(d->dOutSlots.upload(T.outSlots));
+  CUDA_TRY(d->dOutOvf.upload(T.outOvf));
 
   DevTables& t = d->dev;
   t = DevTables{};
@@ -491,6 +513,8 @@ static int buildPlanPush(dnab_decoder* d, int32_t planLen) {
   t.inChunkOff = d->dInChunkOff.p;
   t.outTable = d->dOutTable.p;
   t.outSliceOff = d->dOutSliceOff.p;
+  t.outSlots = d->dOutSlots.p;
+  t.outOvf = d->dOutOvf.p;
   for (int i = 0; i < kMaxSyms; ++i) t.symScore[i] = i < (int)d->symScore.size() ? d->symScore[i] : 0.;
   std::memcpy(t.sub, d->sub, sizeof t.sub);
   std::memcpy(t.len, d->len, sizeof t.len);

@@ -105,6 +105,9 @@ struct DevTables {
   uint32_t maxOutBytes;       // largest out-table of any rank
   const uint32_t* inChunks;   // all chunks of all ranks (16-byte aligned pieces)
   const uint32_t* inChunkOff; // [C][nChunks+1] word offset of each chunk in inChunks
+  const uint4* outSlots;      // [Np] 16-byte out-slots {nOut, e0, e1, e2} (or {nOut, overflow offset} when nOut > 3):
+                              // the out-table in the form read straight from L2 when it is not in shared memory
+  const uint32_t* outOvf;     // overflow edges of states with more than 3 outgoing transitions
   const uint32_t* outTable;   // all out-tables
   const uint32_t* outSliceOff;// [C+1] word offset of each rank's out-table in outTable
   double symScore[kMaxSyms];  // log(symProb) per id (0 for id 0)

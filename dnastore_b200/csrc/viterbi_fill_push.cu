@@ -143,8 +143,8 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
 
 struct Ctx {
   uint32_t aS, aD, aFlag, aSym, aOutOff, aOutWords;
-  const uint16_t* gOutOff;   // out-table in global memory (when it does not fit in shared memory)
-  const uint32_t* gOutWords;
+  const uint4* gOutSlots;    // this CTA's out-slots in global memory (when the table is not in shared memory)
+  const uint32_t* gOutOvf;
   uint32_t outInSmem;
   double delOpen, delExtend, delEnd;
 };
@@ -159,15 +159,15 @@ constexpr uint32_t kNoState = 0xFFFFFFFFu;
 // Loads that do not depend on each other are issued together: the chain is cells+offsets -> edge word
 // -> destination cells -> add/compare -> compare-and-swap (only when the destination grows).
 template <bool kCluster>
-__device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, bool& flagged, bool& sent) {
+__device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, uint4 slot, bool& flagged, bool& sent) {
   const uint32_t myS = c.aS + 8 * s, myD = c.aD + 8 * s;
-  uint32_t o0, o1;
+  uint32_t o0, o1;  // shared-memory table: edge range; L2 slots: 0 .. nOut
   if (c.outInSmem) {
     o0 = lds16(c.aOutOff + 2 * s);
     o1 = lds16(c.aOutOff + 2 * s + 2);
   } else {
-    o0 = __ldg(c.gOutOff + s);
-    o1 = __ldg(c.gOutOff + s + 1);
+    o0 = 0;
+    o1 = slot.x;
   }
   const double dv = ldsCell(myD);
   double sv = ldsCell(myS);
@@ -181,7 +181,13 @@ __device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, bool& fl
   const double m = dmax(dv + c.delExtend, sv + c.delOpen);  // src/viterbi.cpp:124
   uint32_t next = kNoState;
   for (uint32_t e = o0; e < o1; ++e) {
-    const uint32_t w = c.outInSmem ? lds32(c.aOutWords + 4 * e) : __ldg(c.gOutWords + e);
+    uint32_t w;
+    if (c.outInSmem)
+      w = lds32(c.aOutWords + 4 * e);
+    else if (o1 <= 3)
+      w = e == 0 ? slot.y : e == 1 ? slot.z : slot.w;
+    else
+      w = __ldg(c.gOutOvf + slot.y + e);
     const uint32_t l = peLocal(w);
     const uint32_t dS = c.aS + 8 * l, dD = c.aD + 8 * l;
     const bool emit = peIsEmit(w) != 0;
@@ -304,8 +310,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   c.aSym = aSym;
   c.aOutOff = sm + lay.outTab;
   c.aOutWords = sm + lay.outTab + outOffBytes;
-  c.gOutOff = reinterpret_cast<const uint16_t*>(gOut);
-  c.gOutWords = gOut + outOffBytes / 4;
+  c.gOutSlots = tb.outSlots + (size_t)rank * M;
+  c.gOutOvf = tb.outOvf;
   c.outInSmem = tb.outInSmem;
   c.delOpen = delOpen;
   c.delExtend = delExtend;
@@ -620,8 +626,16 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           if (tid == 0) sts32(aTail + 4 * (par ^ 1), 0u);  // the other tail is idle until the next scan
           if (n > args.tailN) {
             // wide frontier: one hop per level, breadth first
+            uint32_t sNext = tid < n ? lds16(aQueue + 2 * tid) : 0u;
+            uint4 slNext = (!c.outInSmem && tid < n) ? __ldg(c.gOutSlots + sNext) : make_uint4(0, 0, 0, 0);
             for (uint32_t q = tid; q < n; q += nThreads) {
-              const uint32_t nx = pushState<kCluster>(c, lds16(aQueue + 2 * q), flagged, sent);
+              const uint32_t sCur = sNext;
+              const uint4 slCur = slNext;
+              if (q + nThreads < n) {  // the next entry's slot travels while this one is pushed
+                sNext = lds16(aQueue + 2 * (q + nThreads));
+                if (!c.outInSmem) slNext = __ldg(c.gOutSlots + sNext);
+              }
+              const uint32_t nx = pushState<kCluster>(c, sCur, slCur, flagged, sent);
               if (nx != kNoState) {
                 redOrShared(aFlag + 4 * (nx >> 5), 1u << (nx & 31));
                 flagged = true;
@@ -635,7 +649,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             uint32_t s = tid < n ? lds16(aQueue + 2 * tid) : kNoState;
             for (uint32_t hop = 0; hop < args.tailHops; ++hop) {
               if (__ballot_sync(0xFFFFFFFFu, s != kNoState) == 0u) break;
-              if (s != kNoState) s = pushState<kCluster>(c, s, flagged, sent);
+              if (s != kNoState)
+                s = pushState<kCluster>(c, s, c.outInSmem ? make_uint4(0, 0, 0, 0) : __ldg(c.gOutSlots + s), flagged, sent);
               if (dbgOn && tid == 0) ++dbgHops;
             }
             if (s != kNoState) {  // hop budget spent

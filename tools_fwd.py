@@ -1,0 +1,18 @@
+"""Scratch probe (GPU): forward kernel throughput."""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, 'tests')
+import numpy as np
+import bench, dnab_testutil as util, dnastore_b200 as d
+wl = sys.argv[1]; n = int(sys.argv[2]); cut = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+w = bench.WORKLOADS[wl]
+m = util.machine_from_recipe(w['recipe']); c = m.compile(d.ErrorFlags(length=w['length'], global_=True))
+dec = d.Decoder(c)
+reads = bench.make_reads(w, n, 7)
+if cut: reads = [r[:cut] for r in reads]
+dec.forward(reads[:2])
+t0 = time.perf_counter(); out = dec.forward(reads); dt = time.perf_counter() - t0
+st = dec.stats()
+cols = sum(len(r) + 1 for r in reads)
+print(json.dumps(dict(workload=wl, reads=n, kernel_ms=st['last_fill_ms'], wall_s=dt, reads_per_s=n / (st['last_fill_ms'] * 1e-3),
+      sweeps_per_col=float(out['sweeps'].sum()) / cols, us_per_sweep_per_cta=st['last_fill_ms'] * 1e3 * min(n, 148) / float(out['sweeps'].sum()),
+      cells_per_s=c.t.n_states * cols * (c.t.k + 2) / (st['last_fill_ms'] * 1e-3), status_ok=bool((out['status'] == 0).all()))))
