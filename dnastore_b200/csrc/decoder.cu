@@ -76,7 +76,7 @@ struct dnab_decoder {
   uint32_t wantBlockMode = 0;   // transition table: 0 auto, 1 shared memory, 2 global memory
   uint32_t idleSleepNs = 100;
   uint32_t tRecompute = 1;
-  uint32_t tailN = 0, tailHops = 64;  // push kernel: lockstep-chain mode (tuning: DNAB_TAIL_N / DNAB_TAIL_HOPS)
+  uint32_t tailN = 0, tailHops = 16;  // push kernel: lockstep-chain mode (tuning: DNAB_TAIL_N / DNAB_TAIL_HOPS)
   uint32_t wantSPrevMode = 0;   // S(pos-1): 0 auto, 1 shared memory, 2 global scratch
   uint32_t wantKernel = 0;      // 0 push kernel (viterbi_fill_push.cu), 1 pull kernel (viterbi_kernels.cu)
   uint32_t wantPartition = 0;   // 0/1 index-order runs + in-degree sort (default), 2 DFS runs unsorted, 3 DFS chunks dealt round-robin + sort, 4 DFS runs + sort
@@ -398,15 +398,11 @@ static int buildPushTables(const dnab_decoder* d, const Partition& P, uint32_t c
   return DNAB_OK;
 }
 
-// Threads per CTA of the push kernel: a dense pass takes ceil(M / (kPushStatesPerThread * threads)) steps, so
-// the count is chosen to fill the last step (7,779 states: 5 steps of 2 x 800 rather than 6 of 2 x 768).
+// Threads per CTA of the push kernel.
 static uint32_t pushThreads(const dnab_decoder* d, uint32_t M) {
-  if (d->wantThreads) return std::min<uint32_t>(1024, (d->wantThreads + 31) / 32 * 32);
-  const uint32_t target = M <= 1024 ? 128 : M <= 2048 ? 256 : M <= 6000 ? 512 : 800;
-  const uint32_t perStep = kPushStatesPerThread * target;
-  const uint32_t steps = (M + perStep - 1) / perStep;
-  const uint32_t threads = ((M + kPushStatesPerThread * steps - 1) / (kPushStatesPerThread * steps) + 31) / 32 * 32;
-  return std::max<uint32_t>(32, std::min<uint32_t>(1024, threads));
+  // measured on B200 (config 2, 11,668 states per CTA): 640 threads (96 registers each) beat 512, 736, 896 and 1024
+  const uint32_t threads = d->wantThreads ? d->wantThreads : M <= 1024 ? 128 : M <= 2048 ? 256 : M <= 6000 ? 512 : 640;
+  return std::max<uint32_t>(32, std::min<uint32_t>(1024, (threads + 31) / 32 * 32));
 }
 
 static int buildPlanPush(dnab_decoder* d, int32_t planLen) {
@@ -678,6 +674,8 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
                           (uint32_t)d->plan.maxLen, d->plan.sPrevGlobal);
     fa.nReads = n;
     fa.idleSleepNs = d->idleSleepNs;
+    // lockstep-chain mode for thin frontiers is a tuning knob (DNAB_TAIL_N), off by default: measured on B200
+    // it is +9 % on config 4 (57 levels per column), -10 % on config 3, -2 % on config 2
     fa.tailN = std::min<uint32_t>(d->tailN, d->plan.threads);
     fa.tailHops = d->tailHops;
     fa.tRecompute = d->tRecompute;

@@ -1,4 +1,5 @@
-for rep in 1 2 3; do for v in A B; do
- echo "lib=$v rep=$rep" >> gpurun_out/sweep.log
- DNAB_LIB=$PWD/ab/lib$v.so timeout 120 python tools_probe.py cfg2 33 >> gpurun_out/sweep.log 2>&1
-done; done
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+for wl in cfg3 cfg4; do for tn in 0 9999; do
+ echo "$wl tailN=$tn" >> gpurun_out/sweep.log
+ DNAB_TAIL_N=$tn timeout 120 python tools_probe.py $wl 296 >> gpurun_out/sweep.log 2>&1
+done; echo "$wl default" >> gpurun_out/sweep.log; timeout 120 python tools_probe.py $wl 296 >> gpurun_out/sweep.log 2>&1; done
