@@ -44,6 +44,9 @@ WORKLOADS = {
                  desc="sync16*hamming74*dnastore-l4 (12,361 states), indels"),
     "cfg4": dict(recipe=("l4c4", "water64.1"), pool="cfg4_water64.1_l4c4_64b", length=4,
                  mut=dict(sub_rate=0.01, del_rate=0.01, max_del=4), desc="watermark64.1*dnastore-l4 (7,066 states)"),
+    # BASELINE.json configs[4]'s machine (dnastore -l 8, 10,746 states, k = 4), 150-bit payloads, substitutions
+    "cfg5": dict(recipe=("l8c4",), pool="cfg5_l8c4_150b", length=8, mut=dict(sub_rate=0.01),
+                 desc="dnastore-l8 (10,746 states, k = 4), ~150-bit payloads, 1% substitutions"),
 }
 METRIC = "viterbi_dp_cells_per_sec"
 UNIT = "cells/s"
@@ -251,7 +254,7 @@ def main():
     if args.cluster or args.threads or args.tmode or args.table_mode or args.partition:
         dec.configure(args.cluster, args.threads, args.tmode, args.table_mode, args.partition)
     info = dec.info()
-    default_rps = {"cfg2": 960, "cfg1": 65536, "cfg3": 4096, "cfg4": 8192}[args.workload]
+    default_rps = {"cfg2": 960, "cfg1": 65536, "cfg3": 4096, "cfg4": 8192, "cfg5": 4096}[args.workload]
     rps = args.reads_per_step or default_rps
 
     # distinct batch per step, generated before timing and resident in HBM

@@ -108,7 +108,7 @@ def test_forward_at_least_viterbi(name):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,n,cut", [("l4c4_global_mixed", 24, None), ("l4c4_local_mixed", 8, None), ("l4c4_edge", 3, None),
                                         ("mr2l4c4_local", 3, None), ("cfg3_global_indels", 2, 48), ("cfg4_global_dels", 2, 60),
-                                        ("cfg2_global_subs", 1, 40)])
+                                        ("cfg2_global_subs", 1, 40), ("cfg5_l8_global", 2, 40), ("cfg5_l8_local", 1, 30)])
 def test_gpu_forward_matches_specification_bit_for_bit(name, n, cut):
     import dnastore_b200 as d
     case = util.golden_case(name)

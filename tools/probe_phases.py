@@ -1,6 +1,6 @@
 """Scratch probe (GPU): per-phase cycle counters for a workload/config."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, 'tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 import bench, dnab_testutil as util, dnastore_b200 as d
 wl = sys.argv[1] if len(sys.argv) > 1 else 'cfg2'
