@@ -41,6 +41,21 @@ def main():
         _a, f = mg.flag_args(dict(length=8), glob)
         cases.append(dict(name=name, recipe=["l8c4"], flags=f, global_=bool(glob),
                           note="BASELINE config 5 machine: dnastore -l 8, 10,746 states, k = 4", reads=res))
+    # the -l 10 machine (57,090 states here): the largest machine in the suite, 5 CTAs per read on the GPU
+    tf10 = tempfile.NamedTemporaryFile("wb", suffix=".json", delete=False)
+    tf10.write(gzip.open(os.path.join(HERE, "machines", "l10c4.json.gz"), "rb").read())
+    tf10.close()
+    mg.machine_args = lambda recipe: ["--machine", tf10.name]
+    rng10 = np.random.default_rng(0xD5A57012 + 10)
+    enc10 = mg.ref_encode(["l10c4"], [synth.random_bits(rng10, 40) for _ in range(2)])
+    reads10 = [(f"r{i}", synth.mutate(e, rng10, sub_rate=0.02, del_rate=0.02, max_del=2)) for i, e in enumerate(enc10)]
+    res = mg.ref_viterbi(["l10c4"], dict(length=10), True, reads10)
+    for r, (_n, seq) in zip(res, reads10):
+        r["seq"] = seq
+    _a, f = mg.flag_args(dict(length=10), True)
+    cases.append(dict(name="l10_global", recipe=["l10c4"], flags=f, global_=True,
+                      note="dnastore -l 10, 57,090 states, k = 5: the largest machine in the suite", reads=res))
+    os.unlink(tf10.name)
     json.dump(dict(generator="tests/golden/make_golden_cfg5.py", cases=cases),
               open(os.path.join(HERE, "viterbi_golden_cfg5.json"), "w"))
     os.unlink(tf.name)

@@ -83,6 +83,30 @@ def test_gpu_pull_kernel_same_bits(d, name):
     _check_against_golden(d, util.golden_case(name), dict(partition_mode=10))
 
 
+@pytest.mark.parametrize("workload,n", [("cfg2", 99), ("cfg5", 300), ("cfg3", 300)])
+def test_gpu_two_kernels_agree_at_batch_scale(d, workload, n):
+    """Two independent implementations of the fill (push-style and pull-style closure, different table
+    formats, different cluster sizes) must agree bit for bit -- log-likelihood, decoded string, traceback
+    path -- on a batch far larger than the oracle can check in a test (several waves of clusters, ragged
+    lengths, dynamic read scheduling)."""
+    import bench
+    w = bench.WORKLOADS[workload]
+    compiled = util.machine_from_recipe(w["recipe"]).compile(d.ErrorFlags(length=w["length"], global_=True))
+    reads = bench.make_reads(w, n, seed=4242)
+    outs = []
+    for part in (0, 10):
+        dec = d.Decoder(compiled, device=0)
+        dec.configure(partition_mode=part)
+        outs.append(dec.viterbi(reads, want_path=True))
+    a, b = outs
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert a["loglike"].tobytes() == b["loglike"].tobytes()
+    assert a["decoded"] == b["decoded"]
+    assert all(x.tolist() == y.tolist() for x, y in zip(a["path"], b["path"]))
+    # and the decoder does its job: most of these lightly mutated reads decode to a framed bit string
+    assert sum(s.startswith("^") and s.endswith("$") for s in a["decoded"]) > 0.9 * n
+
+
 @pytest.mark.parametrize("env", [dict(DNAB_TAIL_N="64", DNAB_TAIL_HOPS="8"), dict(DNAB_T_RECOMPUTE="0")])
 @pytest.mark.parametrize("name", ["l4c4_global_mixed", "cfg3_global_indels", "cfg2_global_subs"])
 def test_gpu_push_kernel_tuning_knobs_same_bits(d, name, env, monkeypatch):

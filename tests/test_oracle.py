@@ -12,7 +12,7 @@ import dnab_testutil as util
 
 CASES = [c["name"] for c in util.load_golden()]
 # the 46,670-state reads take a few seconds each in the oracle: keep one in the CPU suite
-SLOW_LIMIT = {"cfg2_global_subs": 1, "cfg3_global_indels": 2, "cfg4_global_dels": 2}
+SLOW_LIMIT = {"cfg2_global_subs": 1, "cfg3_global_indels": 2, "cfg4_global_dels": 2, "l10_global": 1}
 
 
 @pytest.mark.parametrize("name", CASES)
