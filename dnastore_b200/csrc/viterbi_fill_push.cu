@@ -246,7 +246,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   const uint32_t Np = C * M;
   const double NEG = negInf();
   const PushLayout& lay = args.play;
-  const uint32_t sm = smemAddr(smem);
+  // The shared-window address of the dynamic shared memory.  Taken through an opaque move: left to itself
+  // the compiler re-derives it (S2UR SR_CgaCtaId + ULEA + add) at every use -- 10 % of the executed
+  // instructions in the profile, and a long-latency S2UR at the head of every dependent address chain.
+  uint32_t sm = smemAddr(smem);
+  asm volatile("mov.u32 %0, %0;" : "+r"(sm));
   const bool sPrevSmem = tb.sPrevInSmem != 0;
   const bool tRecompute = !sPrevSmem && tb.k <= 2 && args.tRecompute;
 
