@@ -149,6 +149,7 @@ _sig("dnab_viterbi_batch", C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c
 _sig("dnab_viterbi_batch_device", C.c_int, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp)
 _sig("dnab_viterbi_cells", C.c_int, _vp, _vp, C.c_int32, _vp, _vp)
 _sig("dnab_forward_batch", C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp)
+_sig("dnab_fwdback_counts_batch", C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp)
 _sig("dnab_mutator_params_from_flags", None, C.POINTER(ErrorFlags), C.POINTER(MutatorParams))
 _sig("dnab_mutator_params_json", _vp, C.POINTER(MutatorParams))
 _sig("dnab_mutator_counts_json", _vp, C.POINTER(MutatorCounts))
@@ -488,6 +489,22 @@ class Decoder:
         if cells is not None:
             out["cells"] = cells
         return out
+
+    def fwdback_counts(self, reads, max_sweeps=0):
+        """Forward + backward over the machine lattice and the posterior expected counts of the error-model
+        events per read: dict(loglike, loglike_back, counts[n, 5+k+16], status). Not in the reference (8a-12)."""
+        packed, byte_off, read_len = pack_reads(reads)
+        n = len(read_len)
+        t = self._compiled.t
+        ll = np.zeros(n, dtype=np.float64)
+        llb = np.zeros(n, dtype=np.float64)
+        counts = np.zeros((n, 5 + t.k + 16), dtype=np.float64)
+        status = np.zeros(n, dtype=np.int32)
+        rc = lib.dnab_fwdback_counts_batch(self._h, n, _ptr(packed), _ptr(byte_off), _ptr(read_len), int(max_sweeps),
+                                           _ptr(ll), _ptr(llb), _ptr(counts), _ptr(status))
+        if rc:
+            raise _err(rc)
+        return dict(loglike=ll, loglike_back=llb, counts=counts, status=status)
 
     def viterbi_device(self, n_reads, max_read_len, d_packed, d_byte_off, d_read_len, d_loglike, d_decoded, decoded_stride,
                        d_decoded_len, d_status, stream=0):

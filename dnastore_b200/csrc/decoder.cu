@@ -96,7 +96,10 @@ struct dnab_decoder {
   bool fwdReady = false;
   DevBuf<uint32_t> dFwdEmitOff, dFwdEmitSrc, dFwdNullOff, dFwdNullSrc;
   DevBuf<uint8_t> dFwdEmitMeta, dFwdNullSym, dFwdCtx, dFwdMdl;
-  DevBuf<double> dFwdLse, dFwdScratch;
+  DevBuf<double> dFwdLse, dFwdScratch, dFwdF, dFwdCounts, dFwdLLBack;
+  DevBuf<uint32_t> dFwdOutEmitOff, dFwdOutEmitDst, dFwdOutNullOff, dFwdOutNullDst;
+  DevBuf<uint8_t> dFwdOutEmitMeta, dFwdOutNullSym;
+  DevBuf<long long> dFwdSweepsBack;
   DevBuf<long long> dFwdSweeps;
   bool debug = false;
   // staging for the host-buffer path
@@ -1024,8 +1027,9 @@ int dnab_viterbi_batch(dnab_decoder* d, int64_t n_reads, const uint8_t* packed, 
                      path, path_stride, path_len, nullptr);
 }
 
-int dnab_forward_batch(dnab_decoder* d, int64_t n, const uint8_t* packed, const int64_t* byteOff, const int32_t* readLen,
-                       int32_t maxSweeps, double* loglike, int64_t* sweeps, int32_t* status, double* cells) {
+static int forwardImpl(dnab_decoder* d, int64_t n, const uint8_t* packed, const int64_t* byteOff, const int32_t* readLen,
+                       int32_t maxSweeps, double* loglike, int64_t* sweeps, int32_t* status, double* cells,
+                       double* loglikeBack, double* counts) {
   if (!d || n < 0 || !loglike) {
     setLastError("dnab_forward_batch: bad argument");
     return DNAB_EINVAL;
@@ -1049,6 +1053,32 @@ int dnab_forward_batch(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
     CUDA_TRY(d->dFwdCtx.upload(d->ctx));
     CUDA_TRY(d->dFwdMdl.upload(d->mdl));
     CUDA_TRY(d->dFwdLse.upload(lseV));
+    // source-indexed lists for the backward pass: destination ascending, then list order
+    auto outLists = [&](const std::vector<uint32_t>& inOff, const std::vector<uint32_t>& inSrc, const std::vector<uint8_t>& inMeta,
+                        std::vector<uint32_t>& off, std::vector<uint32_t>& dst, std::vector<uint8_t>& meta) {
+      off.assign(N + 2, 0);
+      for (uint32_t s : inSrc) off[s + 2]++;
+      for (uint32_t s = 0; s < N; ++s) off[s + 2] += off[s + 1];
+      dst.assign(std::max<size_t>(inSrc.size(), 1), 0);
+      meta.assign(std::max<size_t>(inSrc.size(), 1), 0);
+      for (uint32_t dd = 0; dd < N; ++dd)
+        for (uint32_t e = inOff[dd]; e < inOff[dd + 1]; ++e) {
+          const uint32_t p = off[inSrc[e] + 1]++;
+          dst[p] = dd;
+          meta[p] = inMeta[e];
+        }
+      off.pop_back();  // off[s] .. off[s+1] is now the range of source s
+    };
+    std::vector<uint32_t> oeOff, oeDst, onOff, onDst;
+    std::vector<uint8_t> oeMeta, onSym;
+    outLists(d->emitOff, d->emitSrc, meta, oeOff, oeDst, oeMeta);
+    outLists(d->nullOff, d->nullSrc, d->nullSym, onOff, onDst, onSym);
+    CUDA_TRY(d->dFwdOutEmitOff.upload(oeOff));
+    CUDA_TRY(d->dFwdOutEmitDst.upload(oeDst));
+    CUDA_TRY(d->dFwdOutEmitMeta.upload(oeMeta));
+    CUDA_TRY(d->dFwdOutNullOff.upload(onOff));
+    CUDA_TRY(d->dFwdOutNullDst.upload(onDst));
+    CUDA_TRY(d->dFwdOutNullSym.upload(onSym));
     d->fwdReady = true;
   }
   int32_t maxLen = 0;
@@ -1062,14 +1092,26 @@ int dnab_forward_batch(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
     return DNAB_EINVAL;
   }
   packedBytes = std::max<size_t>(packedBytes, 16);
-  const uint32_t nBlocks = (uint32_t)std::min<int64_t>(n, d->smCount);
+  uint32_t nBlocks = (uint32_t)std::min<int64_t>(n, d->smCount);
+  const uint32_t nc = 5 + k + 16;
+  const size_t fPerBlock = counts ? (size_t)(maxLen + 1) * N * (k + 2) : 0;  // forward cells kept for the backward pass
+  if (counts) {
+    size_t freeB = 0, totalB = 0;
+    cudaMemGetInfo(&freeB, &totalB);
+    const size_t budget = std::max<size_t>(d->dFwdF.n * sizeof(double), freeB / 2);
+    nBlocks = (uint32_t)std::max<size_t>(1, std::min<size_t>(nBlocks, budget / (fPerBlock * sizeof(double))));
+    CUDA_TRY(d->dFwdF.ensure((size_t)nBlocks * fPerBlock));
+    CUDA_TRY(d->dFwdCounts.ensure((size_t)n * nc));
+    CUDA_TRY(d->dFwdLLBack.ensure((size_t)n));
+    CUDA_TRY(d->dFwdSweepsBack.ensure((size_t)n));
+  }
   CUDA_TRY(d->dPacked.ensure(packedBytes));
   CUDA_TRY(d->dByteOff.ensure((size_t)n));
   CUDA_TRY(d->dReadLen.ensure((size_t)n));
   CUDA_TRY(d->dLoglike.ensure((size_t)n));
   CUDA_TRY(d->dStatus.ensure((size_t)n));
   CUDA_TRY(d->dFwdSweeps.ensure((size_t)n));
-  CUDA_TRY(d->dFwdScratch.ensure((size_t)nBlocks * (6 + 2 * k) * N));
+  CUDA_TRY(d->dFwdScratch.ensure((size_t)nBlocks * (9 + 2 * k) * N));
   CUDA_TRY(d->dNextRead.ensure(1));
   size_t cellCount = 0;
   if (cells) {
@@ -1095,6 +1137,12 @@ int dnab_forward_batch(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   ft.ctx = d->dFwdCtx.p;
   ft.mdl = d->dFwdMdl.p;
   ft.lseTable = d->dFwdLse.p;
+  ft.outEmitOff = d->dFwdOutEmitOff.p;
+  ft.outEmitDst = d->dFwdOutEmitDst.p;
+  ft.outEmitMeta = d->dFwdOutEmitMeta.p;
+  ft.outNullOff = d->dFwdOutNullOff.p;
+  ft.outNullDst = d->dFwdOutNullDst.p;
+  ft.outNullSym = d->dFwdOutNullSym.p;
   for (int i = 0; i < kMaxSyms; ++i) ft.symScore[i] = i < (int)d->symScore.size() ? d->symScore[i] : 0.;
   std::memcpy(ft.sub, d->sub, sizeof ft.sub);
   std::memcpy(ft.len, d->len, sizeof ft.len);
@@ -1115,6 +1163,11 @@ int dnab_forward_batch(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   fa.status = d->dStatus.p;
   fa.nextRead = d->dNextRead.p;
   fa.cells = cells ? d->dCells.p : nullptr;
+  fa.maxLen = maxLen;
+  fa.F = counts ? d->dFwdF.p : nullptr;
+  fa.counts = counts ? d->dFwdCounts.p : nullptr;
+  fa.loglikeBack = counts ? d->dFwdLLBack.p : nullptr;
+  fa.sweepsBack = counts ? d->dFwdSweepsBack.p : nullptr;
   CUDA_TRY(cudaEventRecord(d->ev0, stream));
   CUDA_TRY(launchForward(ft, fa, nBlocks, 1024, stream));
   CUDA_TRY(cudaEventRecord(d->ev1, stream));
@@ -1124,11 +1177,29 @@ int dnab_forward_batch(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   if (sweeps) CUDA_TRY(cudaMemcpyAsync(sw.data(), d->dFwdSweeps.p, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, stream));
   if (status) CUDA_TRY(cudaMemcpyAsync(status, d->dStatus.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   if (cells) CUDA_TRY(cudaMemcpyAsync(cells, d->dCells.p, cellCount * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (counts) {
+    CUDA_TRY(cudaMemcpyAsync(counts, d->dFwdCounts.p, (size_t)n * nc * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (loglikeBack) CUDA_TRY(cudaMemcpyAsync(loglikeBack, d->dFwdLLBack.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(stream));
   for (size_t r = 0; r < sw.size(); ++r) sweeps[r] = (int64_t)sw[r];
   float ms = 0;
   if (cudaEventElapsedTime(&ms, d->ev0, d->ev1) == cudaSuccess) d->stats.last_fill_ms = ms;
   return DNAB_OK;
+}
+
+int dnab_forward_batch(dnab_decoder* d, int64_t n, const uint8_t* packed, const int64_t* byteOff, const int32_t* readLen,
+                       int32_t maxSweeps, double* loglike, int64_t* sweeps, int32_t* status, double* cells) {
+  return forwardImpl(d, n, packed, byteOff, readLen, maxSweeps, loglike, sweeps, status, cells, nullptr, nullptr);
+}
+
+int dnab_fwdback_counts_batch(dnab_decoder* d, int64_t n, const uint8_t* packed, const int64_t* byteOff, const int32_t* readLen,
+                              int32_t maxSweeps, double* loglike, double* loglikeBack, double* counts, int32_t* status) {
+  if (!counts) {
+    setLastError("dnab_fwdback_counts_batch: counts must not be null");
+    return DNAB_EINVAL;
+  }
+  return forwardImpl(d, n, packed, byteOff, readLen, maxSweeps, loglike, nullptr, status, nullptr, loglikeBack, counts);
 }
 
 int dnab_viterbi_cells(dnab_decoder* d, const uint8_t* packed, int32_t read_len, double* loglike, double* cells) {

@@ -190,6 +190,13 @@ struct ForwardTables {
   const uint8_t* nullSym;    // [nNull]
   const uint8_t* ctx;        // [N*k]
   const uint8_t* mdl;        // [N]
+  // source-indexed lists for the backward pass (destination ascending, then list order)
+  const uint32_t* outEmitOff;  // [N+1]
+  const uint32_t* outEmitDst;  // [nEmit]
+  const uint8_t* outEmitMeta;  // [nEmit] symbol id | base << 5
+  const uint32_t* outNullOff;  // [N+1]
+  const uint32_t* outNullDst;  // [nNull]
+  const uint8_t* outNullSym;   // [nNull]
   const double* lseTable;    // the reference's 100,001-entry log(1+exp(-x)) table (logsumexp.cpp:5-15)
   double symScore[kMaxSyms];
   double sub[16];
@@ -203,7 +210,12 @@ struct ForwardArgs {
   const uint8_t* packed;
   const int64_t* byteOff;
   const int32_t* readLen;
-  double* scratch;               // [nBlocks][(6+2k)*N]
+  int32_t maxLen;                // F stride: every block owns (maxLen+1) columns
+  double* scratch;               // [nBlocks][(9+2k)*N]
+  double* F;                     // optional [nBlocks][maxLen+1][N][k+2]: forward cells kept for the backward pass
+  double* counts;                // optional [nReads][5+k+16] posterior expected counts (needs F)
+  double* loglikeBack;           // [nReads] backward log-likelihood (with counts)
+  long long* sweepsBack;         // [nReads]
   double* loglike;               // [nReads]
   long long* sweeps;             // [nReads] closure sweeps summed over the columns
   int32_t* status;               // [nReads] 0 ok, 1 a closure did not settle within maxSweeps

@@ -182,6 +182,17 @@ int dnab_forward_batch(dnab_decoder* d, int64_t n_reads, const uint8_t* packed, 
                        const int32_t* read_len, int32_t max_sweeps, double* loglike, int64_t* sweeps, int32_t* status,
                        double* cells);
 
+/* Forward AND backward over the machine lattice with the posterior expected counts of the error-model
+ * events -- the machine-lattice analogue of FwdBackMatrix::counts (src/fwdback.cpp:154-188): what
+ * `--error-counts` computes from given alignments, here summed over every input the machine accepts.
+ * NOT IN THE REFERENCE, specified by oracle/forward_oracle.c, parity unpinned.
+ * counts[r*(5+k+16) ...] = nDelOpen, nTanDup, nNoGap, nDelExtend, nDelEnd, nLen[k], nSub[16] (row = machine
+ * base, column = observed base), the order of dnab_mutator_counts.  loglike_back[r] = B_S(start, 0), which
+ * equals loglike[r] up to the accuracy of the table log_sum_exp. */
+int dnab_fwdback_counts_batch(dnab_decoder* d, int64_t n_reads, const uint8_t* packed, const int64_t* read_byte_off,
+                              const int32_t* read_len, int32_t max_sweeps, double* loglike, double* loglike_back,
+                              double* counts, int32_t* status);
+
 /* Counters since creation: kernels launched by this library and DP cells filled. */
 typedef struct dnab_decoder_stats {
   uint64_t kernel_launches;

@@ -178,3 +178,172 @@ int dnab_oracle_forward(const dnab_tables* t, const uint8_t* seq, int L, int max
   free(T[1]);
   return rc;
 }
+
+/* Backward pass and posterior expected counts of the error-model events (the machine-lattice analogue of
+ * FwdBackMatrix::counts, reference src/fwdback.cpp:154-188 / fwdback.h:92-113; PARITY UNPINNED like the rest
+ * of this file).  Every forward move  from-cell --w--> to-cell  listed in the header has the backward
+ * recursion  B(from) = lse over its moves of (w + B(to))  and the posterior usage exp(F(from)+w+B(to)-ll):
+ *   pos-1 -> pos   S(s) --(score+noGap)+sub[base][x]--> S(d)      counts nNoGap, nSub[base][x]
+ *                  T(d,0) --sub[ctx0][x]--> S(d);  T(d,i+1) --sub[ctx(i+1)][x]--> T(d,i)     nSub[ctx][x]
+ *   within pos     D(s) --delExtend+score--> D(d)   nDelExtend      S(s) --delOpen+score--> D(d)   nDelOpen
+ *                  D(s) --score--> D(d), S(s) --score--> S(d) (null transitions)
+ *                  D(d) --delEnd--> S(d)            nDelEnd         S(d) --tanDup+len[i]--> T(d,i)  nTanDup, nLen[i]
+ * The within-column system is again solved by synchronous sweeps from the base values until a sweep changes
+ * no cell.  ll_back = B_S(start,0) (global) must agree with the forward value up to the table's accuracy.
+ * counts: [nDelOpen, nTanDup, nNoGap, nDelExtend, nDelEnd, nLen[k], nSub[16]] (the order of pairhmm_oracle.c).
+ * F: the forward cells of dnab_oracle_forward (ViterbiMatrix layout). */
+int dnab_oracle_backward_counts(const dnab_tables* t, const uint8_t* seq, int L, int max_sweeps, const double* F,
+                                double ll, double* ll_back, double* counts, long* total_sweeps) {
+  const uint32_t n = t->n_states, k = t->k;
+  lse_table_init();
+  /* outgoing lists, built from the destination-indexed tables (order: destination ascending, list order) */
+  uint32_t* eoff = (uint32_t*)calloc(n + 2, sizeof(uint32_t));
+  uint32_t* noff = (uint32_t*)calloc(n + 2, sizeof(uint32_t));
+  for (uint32_t e = 0; e < t->n_emit; ++e) eoff[t->emit_src[e] + 2]++;
+  for (uint32_t e = 0; e < t->n_null; ++e) noff[t->null_src[e] + 2]++;
+  for (uint32_t s = 0; s < n; ++s) {
+    eoff[s + 2] += eoff[s + 1];
+    noff[s + 2] += noff[s + 1];
+  }
+  uint32_t* eedge = (uint32_t*)malloc(sizeof(uint32_t) * (t->n_emit ? t->n_emit : 1)); /* edge id */
+  uint32_t* edst = (uint32_t*)malloc(sizeof(uint32_t) * (t->n_emit ? t->n_emit : 1));
+  uint32_t* nedge = (uint32_t*)malloc(sizeof(uint32_t) * (t->n_null ? t->n_null : 1));
+  uint32_t* ndst = (uint32_t*)malloc(sizeof(uint32_t) * (t->n_null ? t->n_null : 1));
+  for (uint32_t d = 0; d < n; ++d) {
+    for (uint32_t e = t->emit_off[d]; e < t->emit_off[d + 1]; ++e) {
+      const uint32_t p = eoff[t->emit_src[e] + 1]++;
+      eedge[p] = e;
+      edst[p] = d;
+    }
+    for (uint32_t e = t->null_off[d]; e < t->null_off[d + 1]; ++e) {
+      const uint32_t p = noff[t->null_src[e] + 1]++;
+      nedge[p] = e;
+      ndst[p] = d;
+    }
+  }
+  const int W = (int)k + 2;
+  double* Bn = (double*)malloc(sizeof(double) * (size_t)n * W); /* column pos+1 */
+  double* Bc = (double*)malloc(sizeof(double) * (size_t)n * W); /* column pos   */
+  double* base = (double*)malloc(sizeof(double) * n);
+  double* S[2] = {(double*)malloc(sizeof(double) * n), (double*)malloc(sizeof(double) * n)};
+  double* D[2] = {(double*)malloc(sizeof(double) * n), (double*)malloc(sizeof(double) * n)};
+  const int nc = 5 + (int)k + 16;
+  for (int i = 0; i < nc; ++i) counts[i] = 0;
+  long sweeps = 0;
+  int rc = 0;
+#define FC(pos, s, m) F[((size_t)(pos) * n + (s)) * W + (m)]
+#define POST(f, w, b) (((f) == NEG_INF || (b) == NEG_INF || (w) == NEG_INF) ? 0. : exp((f) + (w) + (b)-ll))
+  for (int pos = L; pos >= 0; --pos) {
+    const int xn = pos < L ? seq[pos] : 0; /* base consumed by the moves into column pos+1 */
+    /* T cells of this column and the base value of S */
+    for (uint32_t s = 0; s < n; ++s) {
+      const uint32_t mdl = t->mdl[s];
+      double* bc = Bc + (size_t)s * W;
+      for (uint32_t i = 0; i < k; ++i) bc[2 + i] = NEG_INF;
+      double b = NEG_INF;
+      if (pos == L)
+        b = (t->local || s == n - 1) ? 0. : NEG_INF;
+      else {
+        const double* bn = Bn + (size_t)s * W;
+        if (mdl > 0) {
+          bc[2] = t->sub[t->ctx[(size_t)s * k] * 4 + xn] + bn[0];
+          for (uint32_t i = 0; i + 1 < mdl; ++i) bc[2 + i + 1] = t->sub[t->ctx[(size_t)s * k + i + 1] * 4 + xn] + bn[2 + i];
+        }
+        for (uint32_t p = eoff[s]; p < eoff[s + 1]; ++p) {
+          const uint32_t e = eedge[p];
+          b = lse(b, ((t->emit_score[e] + t->noGap) + t->sub[t->emit_base[e] * 4 + xn]) + Bn[(size_t)edst[p] * W]);
+        }
+      }
+      if (pos > 0)
+        for (uint32_t i = 0; i < mdl; ++i) b = lse(b, (t->tanDup + t->len[i]) + bc[2 + i]);
+      base[s] = b;
+    }
+    /* closure by synchronous sweeps */
+    int cur = 0;
+    for (uint32_t s = 0; s < n; ++s) {
+      S[0][s] = base[s];
+      D[0][s] = NEG_INF;
+    }
+    for (int sweep = 0;; ++sweep) {
+      if (sweep >= max_sweeps) {
+        rc = 1;
+        break;
+      }
+      const double *So = S[cur], *Do = D[cur];
+      double *Sn = S[cur ^ 1], *Dn = D[cur ^ 1];
+      int changed = 0;
+      for (uint32_t s = 0; s < n; ++s) {
+        double ns = base[s], nd = NEG_INF;
+        for (uint32_t p = eoff[s]; p < eoff[s + 1]; ++p) {
+          const double sc = t->emit_score[eedge[p]], bd = Do[edst[p]];
+          ns = lse(ns, (t->delOpen + sc) + bd);
+          nd = lse(nd, (t->delExtend + sc) + bd);
+        }
+        for (uint32_t p = noff[s]; p < noff[s + 1]; ++p) {
+          const double sc = t->null_score[nedge[p]];
+          ns = lse(ns, sc + So[ndst[p]]);
+          nd = lse(nd, sc + Do[ndst[p]]);
+        }
+        nd = lse(nd, t->delEnd + ns);
+        Sn[s] = ns;
+        Dn[s] = nd;
+        if (!same_bits(ns, So[s]) || !same_bits(nd, Do[s])) changed = 1;
+      }
+      cur ^= 1;
+      ++sweeps;
+      if (!changed) break;
+    }
+    for (uint32_t s = 0; s < n; ++s) {
+      Bc[(size_t)s * W] = S[cur][s];
+      Bc[(size_t)s * W + 1] = D[cur][s];
+    }
+    /* posterior usage of the moves leaving column pos */
+    for (uint32_t s = 0; s < n; ++s) {
+      const double fS = FC(pos, s, 0), fD = FC(pos, s, 1);
+      const uint32_t mdl = t->mdl[s];
+      const double* bc = Bc + (size_t)s * W;
+      for (uint32_t p = eoff[s]; p < eoff[s + 1]; ++p) {
+        const uint32_t e = eedge[p], d = edst[p];
+        const double sc = t->emit_score[e];
+        counts[0] += POST(fS, t->delOpen + sc, Bc[(size_t)d * W + 1]);   /* nDelOpen */
+        counts[3] += POST(fD, t->delExtend + sc, Bc[(size_t)d * W + 1]); /* nDelExtend */
+        if (pos < L) {
+          const int b = t->emit_base[e];
+          const double u = POST(fS, (sc + t->noGap) + t->sub[b * 4 + xn], Bn[(size_t)d * W]);
+          counts[2] += u;                   /* nNoGap */
+          counts[5 + k + b * 4 + xn] += u; /* nSub */
+        }
+      }
+      counts[4] += POST(fD, t->delEnd, bc[0]); /* nDelEnd */
+      if (pos > 0)
+        for (uint32_t i = 0; i < mdl; ++i) {
+          const double u = POST(fS, t->tanDup + t->len[i], bc[2 + i]);
+          counts[1] += u;     /* nTanDup */
+          counts[5 + i] += u; /* nLen[i] */
+        }
+      if (pos < L && mdl > 0) {
+        const double* bn = Bn + (size_t)s * W;
+        const int c0 = t->ctx[(size_t)s * k];
+        counts[5 + k + c0 * 4 + xn] += POST(FC(pos, s, 2), t->sub[c0 * 4 + xn], bn[0]);
+        for (uint32_t i = 0; i + 1 < mdl; ++i) {
+          const int ci = t->ctx[(size_t)s * k + i + 1];
+          counts[5 + k + ci * 4 + xn] += POST(FC(pos, s, 2 + i + 1), t->sub[ci * 4 + xn], bn[2 + i]);
+        }
+      }
+    }
+    double* tmp = Bn;
+    Bn = Bc;
+    Bc = tmp;
+  }
+  /* Bn now holds column 0 */
+  if (t->local) {
+    double acc = NEG_INF;
+    for (uint32_t s = 0; s < n; ++s) acc = lse(acc, Bn[(size_t)s * W]);
+    *ll_back = acc;
+  } else
+    *ll_back = Bn[0];
+  if (total_sweeps) *total_sweeps = sweeps;
+  free(eoff); free(noff); free(eedge); free(edst); free(nedge); free(ndst);
+  free(Bn); free(Bc); free(base); free(S[0]); free(S[1]); free(D[0]); free(D[1]);
+  return rc;
+}

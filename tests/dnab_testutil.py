@@ -118,12 +118,31 @@ def forward_oracle_lib():
     lib.dnab_oracle_forward.restype = C.c_int
     lib.dnab_oracle_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double),
                                         C.POINTER(C.c_long), C.c_void_p]
+    lib.dnab_oracle_backward_counts.restype = C.c_int
+    lib.dnab_oracle_backward_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double,
+                                                C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_long)]
     return lib
 
 
-def oracle_forward(compiled, seq, want_cells=False, max_sweeps=4096):
+def oracle_fwdback(compiled, seq, max_sweeps=4096, tables=None):
+    """Forward cells, backward log-likelihood and posterior expected counts of the error-model events
+    [nDelOpen, nTanDup, nNoGap, nDelExtend, nDelEnd, nLen[k], nSub[16]] (oracle/forward_oracle.c)."""
+    t = tables if tables is not None else compiled.t
+    f = oracle_forward(compiled, seq, want_cells=True, max_sweeps=max_sweeps, tables=t)
+    tok = tokens(seq)
+    counts = np.zeros(5 + t.k + 16, dtype=np.float64)
+    llb = C.c_double(0)
+    sw = C.c_long(0)
+    rc = forward_oracle_lib().dnab_oracle_backward_counts(C.addressof(t), tok.ctypes.data, len(seq), max_sweeps,
+                                                          f["cells"].ctypes.data, f["loglike"], C.byref(llb),
+                                                          counts.ctypes.data, C.byref(sw))
+    return dict(rc=rc | f["rc"], loglike=f["loglike"], loglike_back=llb.value, counts=counts, sweeps_back=sw.value,
+                sweeps=f["sweeps"])
+
+
+def oracle_forward(compiled, seq, want_cells=False, max_sweeps=4096, tables=None):
     """The forward specification (oracle/forward_oracle.c). Returns dict(rc, loglike, sweeps, cells)."""
-    t = compiled.t
+    t = tables if tables is not None else compiled.t
     tok = tokens(seq)
     L = len(seq)
     ll = C.c_double(0)

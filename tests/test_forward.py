@@ -105,6 +105,54 @@ def test_forward_at_least_viterbi(name):
         assert f >= v or (np.isinf(f) and np.isinf(v)), (name, f, v)
 
 
+def _perturbed(compiled, field, index, eps):
+    """A copy of the tables with one score shifted by eps (the arrays stay shared with `compiled`)."""
+    import ctypes as C
+    t = type(compiled.t)()
+    C.memmove(C.addressof(t), C.addressof(compiled.t), C.sizeof(t))
+    if field == "sub":
+        arr = (C.c_double * 16)(*list(t.sub))
+        arr[index] += eps
+        t.sub = arr
+    elif field == "len":
+        arr = (C.c_double * t.k)(*[t.len[i] for i in range(t.k)])
+        arr[index] += eps
+        t.len = C.cast(arr, C.POINTER(C.c_double))
+        t._keep = arr
+    else:
+        setattr(t, field, getattr(t, field) + eps)
+    return t
+
+
+@pytest.mark.parametrize("name,idx", [("l4c4_global_mixed", 0), ("l4c4_global_mixed", 5), ("l4c4_local_mixed", 1)])
+def test_backward_and_counts_specification(name, idx):
+    """Backward pass + posterior expected counts (the machine-lattice analogue of FwdBackMatrix::counts):
+    backward and forward log-likelihoods agree; every read base is emitted by exactly one move (sum of nSub
+    = L); every deletion run that opens also ends; and each count is the derivative of the forward
+    log-likelihood with respect to its score (central differences; loose, the table log_sum_exp is only
+    piecewise smooth)."""
+    case = util.golden_case(name)
+    compiled = util.compiled_for_case(case)
+    seq = case["reads"][idx]["seq"]
+    fb = util.oracle_fwdback(compiled, seq)
+    assert fb["rc"] == 0
+    k = compiled.t.k
+    c = fb["counts"]
+    assert abs(fb["loglike_back"] - fb["loglike"]) < 2e-3
+    assert abs(c[5 + k:].sum() - len(seq)) < 2e-3 * len(seq)
+    assert abs(c[0] - c[4]) < 1e-3 * max(1.0, c[0])          # nDelOpen == nDelEnd
+    assert abs(c[1] - c[5:5 + k].sum()) < 1e-12 * max(1.0, c[1])  # nTanDup == sum nLen
+    eps = 0.02
+    checks = [("delOpen", 0, 0), ("tanDup", 0, 1), ("noGap", 0, 2), ("delExtend", 0, 3), ("delEnd", 0, 4), ("len", 0, 5)]
+    big = int(np.argmax(c[5 + k:]))
+    checks.append(("sub", big, 5 + k + big))
+    for field, index, ci in checks:
+        up = util.oracle_forward(compiled, seq, tables=_perturbed(compiled, field, index, +eps))["loglike"]
+        dn = util.oracle_forward(compiled, seq, tables=_perturbed(compiled, field, index, -eps))["loglike"]
+        deriv = (up - dn) / (2 * eps)
+        assert abs(deriv - c[ci]) < 0.02 + 0.03 * abs(c[ci]), (field, index, deriv, c[ci])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,n,cut", [("l4c4_global_mixed", 24, None), ("l4c4_local_mixed", 8, None), ("l4c4_edge", 3, None),
                                         ("mr2l4c4_local", 3, None), ("cfg3_global_indels", 2, 48), ("cfg4_global_dels", 2, 60),
@@ -134,3 +182,22 @@ def test_gpu_forward_cells_bit_exact_and_empty_read():
     assert out["cells"].tobytes() == o["cells"].tobytes()
     for i, s in enumerate([seq, "", "ACGT"]):
         assert util.hexf(out["loglike"][i]) == util.hexf(util.oracle_forward(compiled, s)["loglike"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,cut", [("l4c4_global_mixed", 6, None), ("l4c4_local_mixed", 4, None), ("cfg4_global_dels", 1, 40),
+                                        ("cfg5_l8_global", 2, 40), ("cfg2_global_subs", 1, 24)])
+def test_gpu_fwdback_counts_match_specification(name, n, cut):
+    """Backward log-likelihood bit for bit, posterior counts within 1e-9 (the sums run in a different order)."""
+    import dnastore_b200 as d
+    case = util.golden_case(name)
+    compiled = util.compiled_for_case(case)
+    reads = [s[:cut] if cut else s for s in _reads(name, n)]
+    dec = d.Decoder(compiled, device=0)
+    out = dec.fwdback_counts(reads)
+    for i, s in enumerate(reads):
+        o = util.oracle_fwdback(compiled, s)
+        assert out["status"][i] == o["rc"]
+        assert util.hexf(out["loglike"][i]) == util.hexf(o["loglike"]), (name, i)
+        assert util.hexf(out["loglike_back"][i]) == util.hexf(o["loglike_back"]), (name, i)
+        np.testing.assert_allclose(out["counts"][i], o["counts"], rtol=1e-9, atol=1e-12, err_msg=f"{name} read {i}")
