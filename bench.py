@@ -182,6 +182,82 @@ def cpu_reference_run(w, machine, compiled, reads, n_procs):
     return max(dt, 1e-9), decoded, kind
 
 
+def bench_fwdback(args, w, compiled, dec, rank, local_rank, world, dev, dist, torch, d, util):
+    """Forward-backward step: dnab_fwdback_counts_batch over one batch of reads per GPU (host buffers; the
+    copies are a few hundred bytes per read). Algorithmic bytes: 16 per DP cell (the forward cell is written
+    once and read once by the backward pass)."""
+    t = compiled.t
+    rps = args.reads_per_step or {"cfg5": 1184, "cfg1": 8192}.get(args.workload, 592)
+    n_batches = args.warmup + args.steps
+    batches = [make_reads(w, rps, seed=(rank + 1) * 200003 + b) for b in range(n_batches)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for b in range(args.warmup):
+        dec.fwdback_counts(batches[b])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    kernel_ms, cells, max_gap = 0.0, 0, 0.0
+    t0 = time.perf_counter()
+    for b in range(args.warmup, n_batches):
+        out = dec.fwdback_counts(batches[b])
+        kernel_ms += dec.stats()["last_fill_ms"]  # CUDA events around the kernel, on its stream
+        cells += cells_of(t.n_states, t.k, np.array([len(r) for r in batches[b]]))
+        max_gap = max(max_gap, float(np.abs(out["loglike_back"] - out["loglike"]).max()))
+        assert (out["status"] == 0).all()
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    vals = torch.tensor([kernel_ms, wall_s], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(cells), float(rps * args.steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    kernel_ms_max, wall_max = vals.tolist()
+    tot_cells, tot_reads = sums.tolist()
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = 16.0 * cells / (kernel_ms * 1e-3) / 1e9
+        cpu = None
+        if args.cpu_sample > 0:
+            sample = batches[-1][:min(args.cpu_sample, 2)]
+            t1 = time.perf_counter()
+            ref = [util.oracle_fwdback(compiled, r) for r in sample]
+            dt = time.perf_counter() - t1
+            for i, o in enumerate(ref):
+                assert util.hexf(o["loglike"]) == util.hexf(out["loglike"][i]), "GPU forward log-likelihood differs from the specification"
+                np.testing.assert_allclose(out["counts"][i], o["counts"], rtol=1e-9, atol=1e-12)
+            cpu_cells = cells_of(t.n_states, t.k, np.array([len(r) for r in sample]))
+            cpu = dict(value=cpu_cells / dt, unit=UNIT, cores=1, kind="port", reads_per_sec=len(sample) / dt,
+                       sample=f"first {len(sample)} reads of the last timed batch through oracle/forward_oracle.c (a specification: "
+                              f"the reference has no machine-lattice forward-backward), results equal to the GPU's; host has {os.cpu_count()} cores")
+        line = dict(metric="fwdback_dp_cells_per_sec", value=tot_cells / (kernel_ms_max * 1e-3), unit=UNIT, n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * wall_max / args.steps, higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    reads_per_sec=tot_reads / (kernel_ms_max * 1e-3),
+                    config=dict(workload=f"{args.workload}: {w['desc']}, --error-global, -l {w['length']}; forward + backward + "
+                                         "posterior counts (parity unpinned: not in the reference)",
+                                reads_per_step_per_gpu=rps, n_states=int(t.n_states), k=int(t.k),
+                                l2="distinct read batch per step; the forward cells (8 B each) are streamed to HBM and read back",
+                                max_abs_loglike_back_minus_forward=max_gap),
+                    e2e=dict(value=tot_cells / wall_max, unit=UNIT, h2d_bytes_per_step=int(sum((len(r) + 3) // 4 + 12 for r in batches[-1])),
+                             d2h_bytes_per_step=int(rps * (8 * (5 + t.k + 16) + 20)), steps=args.steps,
+                             reads_per_sec=tot_reads / wall_max),
+                    gpu_launches=int(args.steps * world),
+                    roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                                  kernel="forwardKernel", launches=args.steps, avg_launch_ms=kernel_ms / args.steps,
+                                  peak_source=peak_src, algorithmic_bytes_per_launch=16.0 * cells / args.steps),
+                    cpu_baseline=cpu, clocks=clocks)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -197,6 +273,9 @@ def main():
     ap.add_argument("--table-mode", type=int, default=0)
     ap.add_argument("--partition", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=4, help="reads in the single-core CPU baseline sample (0 = skip)")
+    ap.add_argument("--mode", default="viterbi", choices=["viterbi", "fwdback"],
+                    help="fwdback: forward + backward + posterior counts over the machine lattice (SURVEY 8a-12, BASELINE "
+                         "configs[4]; not in the reference, CPU baseline = the specification in oracle/forward_oracle.c)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -253,6 +332,8 @@ def main():
     dec = d.Decoder(compiled, device=local_rank)
     if args.cluster or args.threads or args.tmode or args.table_mode or args.partition:
         dec.configure(args.cluster, args.threads, args.tmode, args.table_mode, args.partition)
+    if args.mode == "fwdback":
+        return bench_fwdback(args, w, compiled, dec, rank, local_rank, world, dev, dist, torch, d, util)
     info = dec.info()
     default_rps = {"cfg2": 960, "cfg1": 65536, "cfg3": 4096, "cfg4": 8192, "cfg5": 4096}[args.workload]
     rps = args.reads_per_step or default_rps
