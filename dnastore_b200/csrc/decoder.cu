@@ -196,7 +196,9 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
   // locality for CTAs that are busy for equally long inside a closure round
   std::vector<std::vector<uint32_t>> dealt(C);
   if (partMode == 3 && C > 1) {
-    const uint32_t chunk = std::max<uint32_t>(32, (N + 8 * C - 1) / (8 * C));
+    uint32_t deal = 8;  // chunks per CTA (tuning: DNAB_DEAL_CHUNKS)
+    if (const char* e = getenv("DNAB_DEAL_CHUNKS")) deal = std::max(1, atoi(e));
+    const uint32_t chunk = std::max<uint32_t>(32, (N + deal * C - 1) / (deal * C));
     uint32_t r = 0;
     for (uint32_t lo = 0; lo < N;) {
       while (dealt[r].size() >= M) r = (r + 1) % C;  // a CTA never takes more than M states
