@@ -405,8 +405,10 @@ static int buildPushTables(const dnab_decoder* d, const Partition& P, uint32_t c
 
 // Threads per CTA of the push kernel.
 static uint32_t pushThreads(const dnab_decoder* d, uint32_t M) {
-  // measured on B200 (config 2, 11,668 states per CTA): 640 threads (96 registers each) beat 512, 736, 896 and 1024
-  const uint32_t threads = d->wantThreads ? d->wantThreads : M <= 1024 ? 128 : M <= 2048 ? 256 : M <= 6000 ? 512 : 640;
+  // measured on B200 with one state per thread and step: 1024 threads are best for the large slices (configs 2, 3,
+  // 5: 10,746-12,361 states per CTA), 640 for 7,066 states (config 4), 128 for 384 states (config 1)
+  const uint32_t threads = d->wantThreads ? d->wantThreads
+                           : M <= 1024 ? 128 : M <= 2048 ? 256 : M <= 4096 ? 512 : M <= 8192 ? 640 : 1024;
   return std::max<uint32_t>(32, std::min<uint32_t>(1024, (threads + 31) / 32 * 32));
 }
 

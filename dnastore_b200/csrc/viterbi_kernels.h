@@ -99,7 +99,8 @@ struct PushLayout {
   uint32_t total;
 };
 
-constexpr int kPushStatesPerThread = 2;  // states a thread handles per step of a dense pass (interleaved loads)
+constexpr int kPushStatesPerThread = 1;  // states a thread handles per step of a dense pass (measured on B200: 1 state x 1024
+                                         // threads beats 2 x 640, 3 x 512 and 4 x 384 -- more warps hide more latency than interleaved loads)
 
 inline PushLayout makePushLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint32_t sPrevInSmem, uint32_t outBytes,
                                  uint32_t chunkBytes, uint32_t nChunks, uint32_t maxLen, uint32_t queueCap = 0) {
