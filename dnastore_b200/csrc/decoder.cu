@@ -440,7 +440,8 @@ static int buildPlanPush(dnab_decoder* d, int32_t planLen) {
     const uint32_t opts[8][4] = {{1, 1, 1, 1}, {1, 1, 0, 1}, {1, 0, 1, 1}, {1, 0, 0, 1}, {1, 0, 0, 0}, {0, 0, 1, 1}, {0, 0, 0, 1}, {0, 0, 0, 0}};
     for (const auto& o : opts) {
       const uint32_t needOut = o[0], sIn = o[1], tIn = (k == 0) ? 0 : o[2];
-      const uint32_t qCap = o[3] ? M : std::max<uint32_t>(1024, M / 4);
+      uint32_t qCap = o[3] ? M : std::max<uint32_t>(1024, M / 4);
+      if (const char* e = getenv("DNAB_QUEUE_CAP")) qCap = std::max<uint32_t>(32, std::min<uint32_t>(qCap, (uint32_t)atoi(e)));  // test hook
       if (d->wantBlockMode == 1 && !needOut) continue;
       if (d->wantBlockMode == 2 && needOut) continue;
       if (d->wantSPrevMode == 1 && !sIn) continue;
