@@ -76,7 +76,7 @@ struct dnab_decoder {
   uint32_t wantBlockMode = 0;   // transition table: 0 auto, 1 shared memory, 2 global memory
   uint32_t idleSleepNs = 100;
   uint32_t tRecompute = 1;
-  uint32_t tailN = 0, tailHops = 16;  // push kernel: lockstep-chain mode (tuning: DNAB_TAIL_N / DNAB_TAIL_HOPS)
+  uint32_t thinN = 1024;  // push kernel, one-CTA machines: levels of at most this many states queue their successors directly (DNAB_THIN_N)
   uint32_t wantSPrevMode = 0;   // S(pos-1): 0 auto, 1 shared memory, 2 global scratch
   uint32_t wantKernel = 0;      // 0 push kernel (viterbi_fill_push.cu), 1 pull kernel (viterbi_kernels.cu)
   uint32_t wantPartition = 0;   // 0/1 index-order runs + in-degree sort (default), 2 DFS runs unsorted, 3 DFS chunks dealt round-robin + sort, 4 DFS runs + sort
@@ -682,10 +682,7 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
                           (uint32_t)d->plan.maxLen, d->plan.sPrevGlobal);
     fa.nReads = n;
     fa.idleSleepNs = d->idleSleepNs;
-    // lockstep-chain mode for thin frontiers is a tuning knob (DNAB_TAIL_N), off by default: measured on B200
-    // it is +9 % on config 4 (57 levels per column), -10 % on config 3, -2 % on config 2
-    fa.tailN = std::min<uint32_t>(d->tailN, d->plan.threads);
-    fa.tailHops = d->tailHops;
+    fa.thinN = d->thinN;
     fa.tRecompute = d->tRecompute;
     fa.maxLen = maxLen;
     fa.packed = dPacked;
@@ -785,8 +782,7 @@ dnab_decoder* dnab_decoder_create(const dnab_tables* t, int device) {
     delete d;
     return nullptr;
   }
-  if (const char* e = getenv("DNAB_TAIL_N")) d->tailN = (uint32_t)atoi(e);
-  if (const char* e = getenv("DNAB_TAIL_HOPS")) d->tailHops = (uint32_t)atoi(e);
+  if (const char* e = getenv("DNAB_THIN_N")) d->thinN = (uint32_t)atoi(e);
   if (const char* e = getenv("DNAB_T_RECOMPUTE")) d->tRecompute = (uint32_t)atoi(e);
   d->smCount = prop.multiProcessorCount;
   d->smemOptin = prop.sharedMemPerBlockOptin;

@@ -23,8 +23,8 @@
 //     low): per level the dirty bitmap is compacted into a queue, the queued states push, one CTA
 //     barrier; in a cluster, peers are relaxed directly through distributed shared memory (ld /
 //     atom.cas / red.or .shared::cluster) and ONE cluster barrier per level makes the flags they set
-//     visible; a thin frontier (the long tail of a column) is followed in lockstep chains by the lanes
-//     of a warp without any barrier.
+//     visible; on one-CTA machines a thin frontier (the long tail of a column) is queued by the pushers
+//     themselves, which saves the scan and one of the two CTA barriers of a level.
 // Everything else -- the emission step, the predecessor records evaluated with the TRACEBACK's own
 // floating-point association and candidate order (src/viterbi.cpp:251-286), duplication opens, the
 // record layout read by viterbiTracebackKernel -- is as in viterbi_kernels.cu.
@@ -32,6 +32,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "viterbi_kernels.h"
 
@@ -146,8 +147,40 @@ struct Ctx {
   const uint4* gOutSlots;    // this CTA's out-slots in global memory (when the table is not in shared memory)
   const uint32_t* gOutOvf;
   uint32_t outInSmem;
+  uint32_t aQueueNext;  // thin frontier: this level's pushers queue the states they raise themselves into this small queue
+  uint32_t aTailNext;   // ... counted here
+  uint32_t capNext;
   double delOpen, delExtend, delEnd;
 };
+
+__device__ __forceinline__ uint32_t atomOrShared(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void redAndShared(uint32_t a, uint32_t v) {
+  asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// State l of this CTA grew and must push in the next level.  Wide frontier: its bit in the dirty bitmap is set
+// and the next level starts with a scan of the bitmap.  Thin frontier (appendMode): the bit doubles as "already
+// queued" and the pusher appends the state to the next level's small queue itself, which saves the scan and one
+// CTA barrier per level; if that queue is full the bit simply stays set and `deferred` makes the next level scan.
+template <bool kAppend>
+__device__ __forceinline__ void raise(const Ctx& c, uint32_t l, bool& flagged, bool& deferred) {
+  const uint32_t aWord = c.aFlag + 4 * (l >> 5), bit = 1u << (l & 31);
+  if (!kAppend) {
+    redOrShared(aWord, bit);  // no fence: the flag is consumed only after the next CTA barrier
+    flagged = true;
+    return;
+  }
+  if (atomOrShared(aWord, bit) & bit) return;  // queued already (or pending from a peer: the next scan takes it)
+  const uint32_t idx = atomAddShared(c.aTailNext, 1u);
+  if (idx < c.capNext)
+    sts16(c.aQueueNext + 2 * idx, l);
+  else
+    deferred = true;
+}
 
 constexpr uint32_t kNoState = 0xFFFFFFFFu;
 
@@ -158,8 +191,8 @@ constexpr uint32_t kNoState = 0xFFFFFFFFu;
 // bitmap (this CTA's or a peer's) and `flagged` is set.
 // Loads that do not depend on each other are issued together: the chain is cells+offsets -> edge word
 // -> destination cells -> add/compare -> compare-and-swap (only when the destination grows).
-template <bool kCluster>
-__device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, uint4 slot, bool& flagged, bool& sent) {
+template <bool kCluster, bool kAppend>
+__device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, uint4 slot, bool& flagged, bool& deferred, bool& sent) {
   const uint32_t myS = c.aS + 8 * s, myD = c.aD + 8 * s;
   uint32_t o0, o1;  // shared-memory table: edge range; L2 slots: 0 .. nOut
   if (c.outInSmem) {
@@ -201,12 +234,10 @@ __device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, uint4 sl
       if (candD > oldD) grew = casMaxLocal(dD, candD, oldD);
       if (candS > oldS) grew |= casMaxLocal(dS, candS, oldS);
       if (grew) {
-        if (next == kNoState)
+        if (next == kNoState && !kAppend)
           next = l;
-        else {  // no fence: the flag is consumed only after the next CTA barrier
-          redOrShared(c.aFlag + 4 * (l >> 5), 1u << (l & 31));
-          flagged = true;
-        }
+        else
+          raise<kAppend>(c, l, flagged, deferred);
       }
     } else {
       const uint32_t r = peRank(w);
@@ -582,96 +613,121 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
       // for the slowest CTA).
       {
         const uint32_t nWords = (M + 31) / 32, cap = lay.queueCap;
-        const uint32_t aQueue = sm + lay.queue, aTail = sm + lay.ctl;  // ctl[0], ctl[1]: queue tails, by level parity
-        uint32_t round = 0;
-        bool sent = false;
+        const uint32_t aQueue = sm + lay.queue, aTail = sm + lay.ctl;  // ctl[0], ctl[1]: scan-queue tails, by level parity
+        // thin frontiers: two small queues (by level parity) the pushers append to themselves, counters ctl[4..6]
+        // rotated by level (a counter is zeroed one level before it is appended to)
+        const uint32_t capA = lay.appendCap, aA = sm + lay.appendQueue, strideA = (2 * capA + 15u) & ~15u, aTailA = sm + lay.ctl + 16;
+        uint32_t round = 0, tA = 0;  // tA = level % 3
+        bool sent = false, fromAppend = false;
+        // (one-CTA machines only: with peers, their flags would wait for the next scan and cost extra cluster rounds --
+        // measured -4 % ... -20 % on config 2, against +23 % / +5 % on configs 4 / 3)
+        if (!kCluster) {
+          if (tid < 3) sts32(aTailA + 4 * tid, 0u);
+          __syncthreads();
+        }
         for (uint32_t levels = 0;; ++levels) {
           const uint32_t par = levels & 1;
+          const uint32_t tANext = tA == 2 ? 0u : tA + 1, tAAfter = tANext == 2 ? 0u : tANext + 1;
           const long long tl0 = dbgOn ? clock64() : 0;
-          bool flagged = false;
-          for (uint32_t base = 0; base < nWords; base += nThreads) {
-            if (base + (tid & ~31u) >= nWords) break;  // warp-uniform: this warp has no bitmap word to scan
-            const uint32_t wi = base + tid;
-            const uint32_t aWord = aFlag + 4 * wi;
-            uint32_t taken = (wi < nWords && ldsVolatile32(aWord)) ? atomExchShared(aWord, 0u) : 0u;
-            const uint32_t cnt = __popc(taken);
-            uint32_t incl = cnt;
+          bool flagged = false, deferred = false;
+          uint32_t n, aList;
+          if (kCluster || !fromAppend) {
+            // the work list of this level: the set bits of the dirty bitmap, compacted into the big queue
+            for (uint32_t base = 0; base < nWords; base += nThreads) {
+              if (base + (tid & ~31u) >= nWords) break;  // warp-uniform: this warp has no bitmap word to scan
+              const uint32_t wi = base + tid;
+              const uint32_t aWord = aFlag + 4 * wi;
+              uint32_t taken = (wi < nWords && ldsVolatile32(aWord)) ? atomExchShared(aWord, 0u) : 0u;
+              const uint32_t cnt = __popc(taken);
+              uint32_t incl = cnt;
 #pragma unroll
-            for (uint32_t dlt = 1; dlt < 32; dlt <<= 1) {
-              const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, dlt);
-              if (lane >= dlt) incl += up;
+              for (uint32_t dlt = 1; dlt < 32; dlt <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, dlt);
+                if (lane >= dlt) incl += up;
+              }
+              const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+              if (total == 0) continue;  // warp-uniform
+              uint32_t wbase = 0;
+              if (lane == 31) wbase = atomAddShared(aTail + 4 * par, total);
+              wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+              uint32_t at = wbase + incl - cnt, putBack = 0;
+              while (taken) {
+                const uint32_t bit = __ffs(taken) - 1;
+                taken &= taken - 1;
+                if (at < cap)
+                  sts16(aQueue + 2 * at, 32 * wi + bit);
+                else
+                  putBack |= 1u << bit;  // queue full: the state waits for the next level
+                ++at;
+              }
+              if (putBack) {
+                redOrShared(aWord, putBack);
+                flagged = true;
+              }
             }
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (total == 0) continue;  // warp-uniform
-            uint32_t wbase = 0;
-            if (lane == 31) wbase = atomAddShared(aTail + 4 * par, total);
-            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
-            uint32_t at = wbase + incl - cnt, putBack = 0;
-            while (taken) {
-              const uint32_t bit = __ffs(taken) - 1;
-              taken &= taken - 1;
-              if (at < cap)
-                sts16(aQueue + 2 * at, 32 * wi + bit);
-              else
-                putBack |= 1u << bit;  // queue full: the state waits for the next level
-              ++at;
-            }
-            if (putBack) {
-              redOrShared(aWord, putBack);
-              flagged = true;
-            }
+            __syncthreads();  // queue complete; every cell stored before the bits were set is visible
+            n = ldsVolatile32(aTail + 4 * par);
+            if (n > cap) n = cap;
+            if (tid == 0) sts32(aTail + 4 * (par ^ 1), 0u);  // the other tail is idle until the next scan
+            aList = aQueue;
+          } else {
+            // the work list was appended by the previous level's pushers (their bits are still set: see below)
+            n = ldsVolatile32(aTailA + 4 * tA);
+            if (n > capA) n = capA;
+            aList = aA + par * strideA;
           }
-          __syncthreads();  // queue complete; every cell stored before the bits were set is visible
           const long long tl1 = dbgOn ? clock64() : 0;
-          uint32_t n = ldsVolatile32(aTail + 4 * par);
-          if (n > cap) n = cap;
           if (dbgOn && tid == 0) ++dbgLevels;
           if (levels > (1u << 22)) __trap();  // never hang the GPU: a closure that does not settle is a bug
-          if (tid == 0) sts32(aTail + 4 * (par ^ 1), 0u);  // the other tail is idle until the next scan
-          if (n > args.tailN) {
-            // wide frontier: one hop per level, breadth first
-            uint32_t sNext = tid < n ? lds16(aQueue + 2 * tid) : 0u;
+          if (!kCluster && tid == 0) sts32(aTailA + 4 * tAAfter, 0u);
+          c.aQueueNext = aA + (par ^ 1) * strideA;
+          c.aTailNext = aTailA + 4 * tANext;
+          c.capNext = capA;
+          // one hop per level, breadth first; one state per thread and step
+          auto pushList = [&](auto appendTag) {
+            constexpr bool kAppend = decltype(appendTag)::value;
+            uint32_t sNext = tid < n ? lds16(aList + 2 * tid) : 0u;
             uint4 slNext = (!c.outInSmem && tid < n) ? __ldg(c.gOutSlots + sNext) : make_uint4(0, 0, 0, 0);
             for (uint32_t q = tid; q < n; q += nThreads) {
               const uint32_t sCur = sNext;
               const uint4 slCur = slNext;
               if (q + nThreads < n) {  // the next entry's slot travels while this one is pushed
-                sNext = lds16(aQueue + 2 * (q + nThreads));
+                sNext = lds16(aList + 2 * (q + nThreads));
                 if (!c.outInSmem) slNext = __ldg(c.gOutSlots + sNext);
               }
-              const uint32_t nx = pushState<kCluster>(c, sCur, slCur, flagged, sent);
+              // an appended state is "queued" until now: a pusher that raises it after its cells are read queues it again
+              if (!kCluster && fromAppend) redAndShared(aFlag + 4 * (sCur >> 5), ~(1u << (sCur & 31)));
+              const uint32_t nx = pushState<kCluster, kAppend>(c, sCur, slCur, flagged, deferred, sent);
               if (nx != kNoState) {
                 redOrShared(aFlag + 4 * (nx >> 5), 1u << (nx & 31));
                 flagged = true;
               }
             }
-          } else if (n > 0) {
-            // thin frontier (the long tail of a column's closure): at most one state per thread, and the
-            // lanes of a warp follow their chains in LOCKSTEP -- still breadth first, but a hop now
-            // costs one dependent chain of shared-memory accesses instead of a scan and two barriers.
-            // Fan-out beyond one successor per state goes through the bitmap as usual.
-            uint32_t s = tid < n ? lds16(aQueue + 2 * tid) : kNoState;
-            for (uint32_t hop = 0; hop < args.tailHops; ++hop) {
-              if (__ballot_sync(0xFFFFFFFFu, s != kNoState) == 0u) break;
-              if (s != kNoState)
-                s = pushState<kCluster>(c, s, c.outInSmem ? make_uint4(0, 0, 0, 0) : __ldg(c.gOutSlots + s), flagged, sent);
-              if (dbgOn && tid == 0) ++dbgHops;
-            }
-            if (s != kNoState) {  // hop budget spent
-              redOrShared(aFlag + 4 * (s >> 5), 1u << (s & 31));
-              flagged = true;
-            }
-          }
+          };
+          if (!kCluster && n <= args.thinN)
+            pushList(std::true_type{});
+          else
+            pushList(std::false_type{});
           if (dbgOn && tid == 0) dbgWork += n;
           const long long tl2 = dbgOn ? clock64() : 0;
-          const uint32_t anyFlagged = (uint32_t)__syncthreads_or(flagged ? 1 : 0);  // every push of this level has set its flags
+          // every push of this level has flagged or queued its successors
+          const uint32_t needScan = (uint32_t)__syncthreads_or((flagged || deferred) ? 1 : 0);
+          tA = tANext;
           if (dbgOn && tid == 0) {
             const long long tl3 = clock64();
             dbgScan += tl1 - tl0;
             dbgPush += tl2 - tl1;
             dbgPushWait += tl3 - tl2;
           }
-          if (anyFlagged) continue;  // this CTA is not quiet yet
+          if (needScan) {  // (a scan also takes the bits of whatever was appended meanwhile: that list is dropped)
+            fromAppend = false;
+            continue;
+          }
+          if (!kCluster && ldsVolatile32(aTailA + 4 * tA) != 0u) {
+            fromAppend = true;
+            continue;
+          }
+          fromAppend = false;
           if (!kCluster) break;
           // locally quiet: meet the cluster; another round if anything crossed CTAs since the last meeting
           const long long tcb = dbgOn ? clock64() : 0;
@@ -683,8 +739,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           uint32_t tot = 0;
           for (uint32_t r = 0; r < C; ++r) tot |= ctl[16 + (round & 1) * kMaxCluster + r];
           ++round;
-          if (dbgOn && tid == 0 && tot) ++dbgRounds;
           if (!tot) break;
+          if (dbgOn && tid == 0) ++dbgRounds;
         }
       }
       long long tc2 = dbgOn ? clock64() : 0;

@@ -87,6 +87,8 @@ struct PushLayout {
   uint32_t flag;       // [ceil(M/32)] u32 dirty bitmap: the state must push to its successors
   uint32_t queue;      // [queueCap] u16: the dirty states of the current closure level, compacted
   uint32_t queueCap;
+  uint32_t appendQueue;  // 2 x [appendCap] u16: thin frontiers are queued by the pushers themselves
+  uint32_t appendCap;
   uint32_t tsE;        // [4 bases][32 syms][4 observed] (score+noGap)+sub, traceback association (src/viterbi.cpp:255)
   uint32_t symScore;   // [kMaxSyms]
   uint32_t tsDext;     // [kMaxSyms] score+delExtend (src/viterbi.cpp:272)
@@ -121,6 +123,9 @@ inline PushLayout makePushLayout(uint32_t M, uint32_t k, uint32_t tInSmem, uint3
   L.flag = take(((M + 31) / 32) * 4);
   L.queueCap = queueCap ? queueCap : M;  // M entries never overflow; a smaller queue defers states to the next level
   L.queue = take(L.queueCap * 2);
+  L.appendCap = 1024;
+  L.appendQueue = take(L.appendCap * 2);
+  take(L.appendCap * 2);
   L.tsE = take(4 * 32 * 4 * 8);
   L.symScore = take(kMaxSyms * 8);
   L.tsDext = take(kMaxSyms * 8);
@@ -140,8 +145,7 @@ struct FillArgs {
   int64_t nReads;
   int32_t maxLen;            // pred stride: every read owns (maxLen+1) columns of records
   uint32_t idleSleepNs;      // back-off of a warp whose closure sweep found nothing to do
-  uint32_t tailN;            // push kernel: a closure level with at most this many dirty states (<= threads) runs in lockstep-chain mode
-  uint32_t tailHops;         // push kernel: hop budget of one lockstep-chain episode
+  uint32_t thinN;            // push kernel: a level of at most this many states lets its pushers queue the next level themselves
   uint32_t tRecompute;       // push kernel: re-derive the duplication cells from S(pos-1), S(pos-2) (k <= 2) instead of storing them
   const uint8_t* packed;     // 2-bit reads
   const int64_t* byteOff;    // [nReads]

@@ -107,13 +107,14 @@ def test_gpu_two_kernels_agree_at_batch_scale(d, workload, n):
     assert sum(s.startswith("^") and s.endswith("$") for s in a["decoded"]) > 0.9 * n
 
 
-@pytest.mark.parametrize("env", [dict(DNAB_TAIL_N="64", DNAB_TAIL_HOPS="8"), dict(DNAB_T_RECOMPUTE="0"),
-                                 dict(DNAB_QUEUE_CAP="40"), dict(DNAB_QUEUE_CAP="40", DNAB_TAIL_N="32", DNAB_TAIL_HOPS="3")])
-@pytest.mark.parametrize("name", ["l4c4_global_mixed", "cfg3_global_indels", "cfg2_global_subs"])
+@pytest.mark.parametrize("env", [dict(DNAB_THIN_N="0"), dict(DNAB_THIN_N="48"), dict(DNAB_T_RECOMPUTE="0"),
+                                 dict(DNAB_QUEUE_CAP="40"), dict(DNAB_QUEUE_CAP="40", DNAB_THIN_N="100000")])
+@pytest.mark.parametrize("name", ["l4c4_global_mixed", "cfg3_global_indels", "cfg4_global_dels", "cfg2_global_subs"])
 def test_gpu_push_kernel_tuning_knobs_same_bits(d, name, env, monkeypatch):
-    """Lockstep-chain mode for thin frontiers, stored (not re-derived) duplication cells and a level queue far
-    smaller than the frontier (dirty states then wait for a later level) are schedule / placement choices of
-    the push kernel: no bit may change."""
+    """How a level's work list is made (bitmap scan, or appended by the previous level's pushers below a size
+    threshold -- including a threshold so large that the small append queues overflow), stored (not re-derived)
+    duplication cells and a scan queue far smaller than the frontier are schedule / placement choices of the
+    push kernel: no bit may change."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     _check_against_golden(d, util.golden_case(name))
