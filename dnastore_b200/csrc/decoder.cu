@@ -89,7 +89,7 @@ struct dnab_decoder {
   DevBuf<uint8_t> dSymChar;
   // scratch
   DevBuf<uint8_t> dPred;
-  DevBuf<double> dTScratch, dSScratch, dPartVal, dCells;
+  DevBuf<double> dTScratch, dSScratch, dS0Scratch, dPartVal, dCells;
   DevBuf<uint32_t> dStart, dPartOrig, dPartG;
   DevBuf<unsigned long long> dDbg, dNextRead;
   // forward kernel (forward_kernels.cu): CSR tables in reference order, uploaded on first use
@@ -536,6 +536,7 @@ static int buildPlanPush(dnab_decoder* d, int32_t planLen) {
   }
   best.nClusters = (uint32_t)nClusters;
   if (!best.tInSmem && k) CUDA_TRY(d->dTScratch.ensure((size_t)nClusters * C * k * M));
+  CUDA_TRY(d->dS0Scratch.ensure((size_t)nClusters * C * M));
   if (best.sPrevGlobal) CUDA_TRY(d->dSScratch.ensure((size_t)nClusters * 2 * C * M));
   d->plan = best;
   return DNAB_OK;
@@ -691,6 +692,7 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
     fa.pred = d->dPred.p;
     fa.tScratch = d->dTScratch.p;
     fa.sScratch = d->dSScratch.p;
+    fa.s0Scratch = d->dS0Scratch.p;
     fa.loglike = dLoglike + at;
     fa.startState = d->dStart.p;
     fa.partVal = d->dPartVal.p;

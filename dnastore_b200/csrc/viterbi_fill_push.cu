@@ -13,8 +13,9 @@
 //     within-column weight is <= 0, so any schedule reaches the reference's least fixed point bit for
 //     bit; a hop needs one table access: the pusher's outgoing list;
 //   * that out-table is compact (one word per transition) and RESIDENT in shared memory;
-//   * the incoming lists, needed only by the three dense passes that walk the states in order
-//     (emission step, first closure pass, predecessor pass), are STREAMED through one shared-memory
+//   * the incoming lists, needed only by the two dense passes that walk the states in order (first
+//     closure pass; predecessor pass, which also performs the emission step of the NEXT column from the
+//     same gathered S(pos)[src]), are STREAMED through one shared-memory
 //     staging buffer in chunks: every thread fetches its 16-byte pieces of the NEXT chunk into registers
 //     (coalesced 128-bit loads) before it works on the current one and stores them after a CTA barrier,
 //     so the L2 latency of the table is hidden behind a whole step of the pass; each thread handles
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   volatile uint32_t* ctl = reinterpret_cast<volatile uint32_t*>(smem + lay.ctl);
   uint8_t* seqS = smem + lay.seq;
   double* sG = sPrevSmem ? nullptr : args.sScratch + (size_t)clusterId * 2 * Np;
+  double* s0G = args.s0Scratch + (size_t)clusterId * Np;  // S0 of the next column, written by the fused emission step
   double* tCol = tb.tInSmem ? reinterpret_cast<double*>(smem + lay.tBuf)
                             : args.tScratch + ((size_t)clusterId * C + rank) * (size_t)k * M;
 
@@ -435,6 +437,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
       const double* sPrevG = sG + (size_t)prev * Np;  // (only dereferenced when !sPrevSmem)
       double* sCurG = sG + (size_t)cur * Np;
       const uint32_t x = pos > 0 ? (seqS[(pos - 1) >> 2] >> (2 * ((pos - 1) & 3))) & 3u : 0u;
+      const uint32_t xNext = pos < L ? (seqS[pos >> 2] >> (2 * (pos & 3))) & 3u : 0u;  // the base column pos+1 reads
       c.aS = aScur;
 
       // S(pos-1) of the source named by an in-edge word
@@ -471,74 +474,22 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
       };
 
       long long tc0 = dbgOn ? clock64() : 0;
-      // ---- (1) emission step: S0 from the previous column, T shift (src/viterbi.cpp:92-106) ----
-      for (uint32_t j = 0; j < nChunks; ++j) {
-        prefetch();
-        uint32_t i[kU], rec[kU], h[kU];
-        double s[kU], t0[kU];
-        uint32_t maxE = 0;
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          i[u] = j * chunkStates + u * nThreads + tid;
-          rec[u] = recOf(u);
-          h[u] = i[u] < M ? lds32(rec[u]) : (kInPad << 7);
-          s[u] = NEG;
-          t0[u] = NEG;
-          if (pos > 0) {
-            if (inMdl(h[u]) > 0) {
-              if (tRecompute) {
-                double t1;
-                dupPrev(h[u], ldsCell(aScur + 8 * i[u]), sCurG[rank * M + i[u]], t0[u], t1);  // S(pos-1) is still in place
-              } else
-                t0[u] = tCol[i[u]];
-            }
-            maxE = max(maxE, inNEmit(h[u]));
-          }
-        }
+      // ---- (1) S0(pos) into shared memory.  The emission step itself (src/viterbi.cpp:92-106) is FUSED into the
+      // predecessor pass of the previous column (3b below), which has every S(pos-1)[src] in shared memory
+      // anyway; its result travelled through a scratch column in global memory because S(pos-1) was still being
+      // read by peers.  Column 0 is initialised here (src/viterbi.cpp:75-79).
+      for (uint32_t i = tid; i < M; i += nThreads) {
+        const uint32_t g = rank * M + i;
+        double s0;
         if (pos == 0) {
-#pragma unroll
-          for (int u = 0; u < kU; ++u)
-            if (i[u] < M) {
-              const bool real = inNIn(h[u]) != kInPad;
-              s[u] = (real && (tb.local || rank * M + i[u] == tb.startG)) ? 0.0 : NEG;  // src/viterbi.cpp:75-79
-              if (!tRecompute)
-                for (uint32_t t = 0; t < k; ++t) tCol[t * M + i[u]] = NEG;
-            }
-        } else {
-          for (uint32_t e = 0; e < maxE; ++e) {
-            uint32_t w[kU];
-            double v[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) w[u] = e < inNEmit(h[u]) ? lds32(rec[u] + 4 + 4 * e) : 0u;
-#pragma unroll
-            for (int u = 0; u < kU; ++u) v[u] = e < inNEmit(h[u]) ? loadPrev(w[u]) : NEG;
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-              const double cand = ((v[u] + ldsTab(aSym + 8 * peSym(w[u]))) + noGap) + ldsTab(aSub + 8 * (peBase(w[u]) * 4 + x));
-              if (e < inNEmit(h[u])) s[u] = dmax(s[u], cand);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < kU; ++u) {
-            const uint32_t mdl = inMdl(h[u]);
-            if (mdl > 0) {
-              const double t2s = t0[u] + subS[inCtx(h[u], 0) * 4 + x];
-              s[u] = dmax(s[u], t2s);
-              if (!tRecompute) {
-                for (uint32_t t = 0; t + 1 < mdl; ++t)
-                  tCol[t * M + i[u]] = tCol[(t + 1) * M + i[u]] + subS[inCtx(h[u], t + 1) * 4 + x];
-                tCol[(mdl - 1) * M + i[u]] = t2s;  // slot mdl-1 is free until step (4): park the T->S candidate there
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-          if (i[u] < M) {
-            stsCell(aScur + 8 * i[u], s[u]);
-            stsCell(aD + 8 * i[u], NEG);
-          }
-        commit();
+          const bool real = __ldg(&tb.origId[g]) != 0xFFFFFFFFu;
+          s0 = (real && (tb.local || g == tb.startG)) ? 0.0 : NEG;
+          if (!tRecompute)
+            for (uint32_t t = 0; t < k; ++t) tCol[t * M + i] = NEG;
+        } else
+          s0 = s0G[g];
+        stsCell(aScur + 8 * i, s0);
+        stsCell(aD + 8 * i, NEG);
       }
       clusterBarrier();  // S0 of every CTA is complete before a peer reads it
       long long tc1 = dbgOn ? clock64() : 0;
@@ -751,7 +702,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
       for (uint32_t j = 0; j < nChunks; ++j) {
         prefetch();
         uint32_t i[kU], rec[kU], h[kU], nIn[kU], idx[kU], idxD[kU];
-        double sHere[kU], dHere[kU], parked[kU], tPrev1[kU], best[kU], bestD[kU];
+        double sHere[kU], dHere[kU], parked[kU], tPrev1[kU], best[kU], bestD[kU], s0n[kU];
         uint32_t maxIn = 0;
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
@@ -774,6 +725,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           bestD[u] = NEG;
           idx[u] = kNoPred;
           idxD[u] = kNoPred;
+          s0n[u] = NEG;
         }
         for (uint32_t e = 0; e < maxIn; ++e) {
           uint32_t w[kU];
@@ -808,6 +760,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                 bestD[u] = vo;
                 idxD[u] = 2 * e + 1;
               }
+              // (3b) emission step of column pos+1 (src/viterbi.cpp:92-95): the same S(pos)[src], fill association
+              if (pos < L)
+                s0n[u] = dmax(s0n[u], ((vs[u] + ldsTab(aSym + sym8)) + noGap) + ldsTab(aSub + 8 * (peBase(w[u]) * 4 + xNext)));
             } else if (e < nIn[u]) {
               const double sc = ldsTab(aSym + sym8);
               const double v = vs[u] + sc;
@@ -858,6 +813,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
               cell[0] = sHere[u];
               cell[1] = dHere[u];
             }
+            double tNow0 = NEG;  // T(state,pos,0)
             for (uint32_t t = 0; t < k; ++t) {
               uint32_t idxT = kNoPred;
               double tNow = NEG;
@@ -871,6 +827,20 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
               }
               predCol[(size_t)(2 + t) * Np + g] = (uint8_t)idxT;
               if (cell) cell[2 + t] = tNow;
+              if (t == 0) tNow0 = tNow;
+            }
+            // (3b) continued: the T -> S candidate and the T shift of column pos+1 (src/viterbi.cpp:102-106)
+            if (pos < L) {
+              if (mdl > 0) {
+                const double t2s = tNow0 + subS[inCtx(h[u], 0) * 4 + xNext];
+                s0n[u] = dmax(s0n[u], t2s);
+                if (!tRecompute) {
+                  for (uint32_t t = 0; t + 1 < mdl; ++t)
+                    tCol[t * M + i[u]] = tCol[(t + 1) * M + i[u]] + subS[inCtx(h[u], t + 1) * 4 + xNext];
+                  tCol[(mdl - 1) * M + i[u]] = t2s;  // slot mdl-1 is free until (4) of the next column: park the T->S candidate there
+                }
+              }
+              s0G[g] = s0n[u];
             }
           }
         commit();

@@ -153,6 +153,7 @@ struct FillArgs {
   uint8_t* pred;             // [nReads][maxLen+1][k+2][Np] predecessor records, 1 byte per DP cell
   double* tScratch;          // [nClusters*C][k][M] T columns when they do not fit in shared memory
   double* sScratch;          // [nClusters][2][Np] S columns of the last two positions when sPrevGlobal
+  double* s0Scratch;         // push kernel: [nClusters][Np] S0 of the next column (the emission step is fused into the predecessor pass)
   double* loglike;           // [nReads] (global mode; local mode: written by the traceback kernel)
   uint32_t* startState;      // [nReads] traceback start (padded index), global mode
   double* partVal;           // [nReads][C] local mode: per-CTA best final S ...
