@@ -394,9 +394,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   };
   clusterBarrier();  // every CTA's flags exist before a peer can touch them
 
-  unsigned long long dbgLevels = 0, dbgRounds = 0, dbgTE = 0, dbgTC = 0, dbgTP = 0, dbgTB = 0, dbgCols = 0, dbgWork = 0,
-                     dbgClusterWait = 0, dbgDirty = 0, dbgScan = 0, dbgPush = 0, dbgPushWait = 0, dbgHops = 0;
+  // profiling counters (dnab_decoder_debug_counters): added straight to global memory by thread 0 of rank 0, so that
+  // they cost no registers when they are off
   const bool dbgOn = args.dbg != nullptr;
+  const bool dbgMe = dbgOn && tid == 0 && rank == 0;
+  auto dbgAdd = [&](int slot, unsigned long long v) { atomicAdd(&args.dbg[slot], v); };
 
   // Reads are handed out dynamically (one global counter, fetched by rank 0 and broadcast through
   // distributed shared memory): reads differ in length, and a static stride leaves the clusters that
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           const uint32_t mask = __ballot_sync(0xFFFFFFFFu, dirty);
           if (lane == 0 && i[u] < M) {
             sts32(aFlag + 4 * (i[u] >> 5), mask);
-            if (dbgOn) dbgDirty += __popc(mask);
+            if (dbgOn && rank == 0) dbgAdd(8, (unsigned long long)__popc(mask));
           }
         }
         commit();
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             aList = aA + par * strideA;
           }
           const long long tl1 = dbgOn ? clock64() : 0;
-          if (dbgOn && tid == 0) ++dbgLevels;
+          if (dbgMe) dbgAdd(1, 1);
           if (levels > (1u << 22)) __trap();  // never hang the GPU: a closure that does not settle is a bug
           if (!kCluster && tid == 0) sts32(aTailA + 4 * tAAfter, 0u);
           c.aQueueNext = aA + (par ^ 1) * strideA;
@@ -659,16 +661,16 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             pushList(std::true_type{});
           else
             pushList(std::false_type{});
-          if (dbgOn && tid == 0) dbgWork += n;
+          if (dbgMe) dbgAdd(2, n);
           const long long tl2 = dbgOn ? clock64() : 0;
           // every push of this level has flagged or queued its successors
           const uint32_t needScan = (uint32_t)__syncthreads_or((flagged || deferred) ? 1 : 0);
           tA = tANext;
-          if (dbgOn && tid == 0) {
+          if (dbgMe) {
             const long long tl3 = clock64();
-            dbgScan += tl1 - tl0;
-            dbgPush += tl2 - tl1;
-            dbgPushWait += tl3 - tl2;
+            dbgAdd(9, tl1 - tl0);
+            dbgAdd(10, tl2 - tl1);
+            dbgAdd(12, tl3 - tl2);
           }
           if (needScan) {  // (a scan also takes the bits of whatever was appended meanwhile: that list is dropped)
             fromAppend = false;
@@ -686,12 +688,12 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           sent = false;
           if (tid < C) stPeerU32(sm + lay.ctl + (16 + (round & 1) * kMaxCluster + rank) * 4, tid, anySent);
           cluster.sync();
-          if (dbgOn && tid == 0) dbgClusterWait += clock64() - tcb;
+          if (dbgMe) dbgAdd(11, clock64() - tcb);
           uint32_t tot = 0;
           for (uint32_t r = 0; r < C; ++r) tot |= ctl[16 + (round & 1) * kMaxCluster + r];
           ++round;
           if (!tot) break;
-          if (dbgOn && tid == 0) ++dbgRounds;
+          if (dbgMe) dbgAdd(6, 1);
         }
       }
       long long tc2 = dbgOn ? clock64() : 0;
@@ -846,13 +848,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         commit();
       }
       clusterBarrier();
-      if (dbgOn && tid == 0) {
+      if (dbgMe) {
         const long long tc3 = clock64();
-        dbgTE += tc1 - tc0;
-        dbgTB += tc1b - tc1;
-        dbgTC += tc2 - tc1;
-        dbgTP += tc3 - tc2;
-        dbgCols++;
+        dbgAdd(3, tc1 - tc0);
+        dbgAdd(7, tc1b - tc1);
+        dbgAdd(4, tc2 - tc1);
+        dbgAdd(5, tc3 - tc2);
+        dbgAdd(0, 1);
       }
     }
 
@@ -916,24 +918,6 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         buildTsE();
         __syncthreads();
       }
-    }
-  }
-  if (dbgOn && rank == 0) {
-    if (lane == 0 && dbgDirty) atomicAdd(&args.dbg[8], dbgDirty);
-    if (tid == 0) {
-      atomicAdd(&args.dbg[0], dbgCols);
-      atomicAdd(&args.dbg[1], dbgLevels);
-      atomicAdd(&args.dbg[2], dbgWork);
-      atomicAdd(&args.dbg[3], dbgTE);
-      atomicAdd(&args.dbg[4], dbgTC);
-      atomicAdd(&args.dbg[5], dbgTP);
-      atomicAdd(&args.dbg[6], dbgRounds);
-      atomicAdd(&args.dbg[7], dbgTB);
-      atomicAdd(&args.dbg[11], dbgClusterWait);
-      atomicAdd(&args.dbg[9], dbgScan);
-      atomicAdd(&args.dbg[10], dbgPush);
-      atomicAdd(&args.dbg[12], dbgPushWait);
-      atomicAdd(&args.dbg[13], dbgHops);
     }
   }
   clusterBarrier();  // no CTA may exit while a peer can still touch its shared memory
