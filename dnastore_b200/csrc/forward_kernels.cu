@@ -21,35 +21,13 @@
 
 #include <cstdint>
 
+#include "lse_table.cuh"
 #include "viterbi_kernels.h"
 
 namespace dnab {
 namespace {
 
 __device__ __forceinline__ double ninf() { return __longlong_as_double(0xFFF0000000000000LL); }
-
-__device__ __forceinline__ double lseUnary(const double* __restrict__ table, double x) {  // logsumexp.h:52-74
-  if (x >= 10 || isnan(x) || isinf(x)) return 0;
-  const int n = (int)(x / .0001);
-  const double dx = x - (n * .0001);
-  const double f0 = __ldg(table + n), f1 = __ldg(table + n + 1);
-  const double df = f1 - f0;
-  return f0 + df * (dx / .0001);
-}
-__device__ __forceinline__ double lse(const double* __restrict__ table, double a, double b) {  // logsumexp.h:34-50
-  double mx, diff;
-  if (a == b) {
-    mx = a;
-    diff = 0;
-  } else if (a < b) {
-    mx = b;
-    diff = b - a;
-  } else {
-    mx = a;
-    diff = a - b;
-  }
-  return mx + lseUnary(table, diff);
-}
 
 }  // namespace
 

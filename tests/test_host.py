@@ -105,3 +105,35 @@ def test_decoder_needs_a_gpu_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(d.DnabError, match="no CPU fallback"):
         d.Decoder(util.compiled_for(["l4c4"], dict(length=4), True))
+
+
+def test_divide_by_table_step_is_ieee_division(tmp_path):
+    """csrc/lse_table.cuh replaces the two `/ .0001` of the reference's log_sum_exp_unary
+    (src/logsumexp.h:61-72) by q = x*10000; r = fma(-1e-4, q, x); q + r*10000 (one more fma).  The same
+    three operations on the CPU must equal hardware division for every operand: random in [0,10), random
+    exponents of both signs, and +-200 ulps around every multiple of the step (where the truncation to a
+    table index is decided)."""
+    import subprocess
+    src = tmp_path / "divstep.c"
+    src.write_text(r'''
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+static double div3(double x) { const double c = .0001, y = 10000.0; double q = x * y; double r = fma(-c, q, x); return fma(r, y, q); }
+static uint64_t s = 88172645463325252ULL;
+static uint64_t rnd(void) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+int main(void) {
+  const double c = .0001; long bad = 0, tot = 0;
+  for (long i = 0; i < 20000000L; i++) { double x = (rnd() >> 11) * (10.0 / 9007199254740992.0); bad += (x / c != div3(x)); tot++; }
+  for (long i = 0; i < 20000000L; i++) {
+    uint64_t bits = ((uint64_t)(1023 - 80 + (int)(rnd() % 85)) << 52) | (rnd() & 0xFFFFFFFFFFFFFULL) | ((rnd() & 1) << 63);
+    double x; memcpy(&x, &bits, 8); bad += (x / c != div3(x)); tot++; }
+  for (long n = 0; n <= 100000; n++) { double x0 = n * c; uint64_t b0; memcpy(&b0, &x0, 8);
+    for (int d = -200; d <= 200; d++) { if (n == 0 && d < 0) continue; uint64_t bb = b0 + d; double x; memcpy(&x, &bb, 8); bad += (x / c != div3(x)); tot++; } }
+  printf("%ld %ld\n", tot, bad); return 0; }
+''')
+    exe = tmp_path / "divstep"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(src), "-lm"], check=True)
+    tot, bad = map(int, subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
+    assert tot > 8e7 and bad == 0
