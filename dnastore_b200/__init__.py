@@ -22,6 +22,11 @@ from ._capi import (  # noqa: F401
     pairhmm_fb_batch,
     expected_counts,
     baum_welch,
+    ExactDecoder,
+    exact_decode_bits,
+    exact_decode_string,
+    exact_decode_fasta,
+    pack_decoded_symbols,
     READ_OK,
     READ_NO_DECODING,
     READ_OVERFLOW,
@@ -31,5 +36,6 @@ from ._capi import (  # noqa: F401
 __all__ = [
     "DnabError", "Machine", "ErrorFlags", "Compiled", "Decoder", "Tables", "lib", "lib_path", "pack_reads", "MutatorParams", "MutatorCounts", "PairDb",
     "pairhmm_fb_batch", "expected_counts", "baum_welch",
+    "ExactDecoder", "exact_decode_bits", "exact_decode_string", "exact_decode_fasta", "pack_decoded_symbols",
     "READ_OK", "READ_NO_DECODING", "READ_OVERFLOW", "READ_TRACEBACK_FAILED",
 ]

@@ -176,6 +176,15 @@ _sig("dnab_decoded_seq", C.c_char_p, _vp, C.c_int64)
 _sig("dnab_decoded_loglike", C.c_double, _vp, C.c_int64)
 _sig("dnab_decoded_status", C.c_int32, _vp, C.c_int64)
 _sig("dnab_decoded_free", None, _vp)
+_sig("dnab_exact_decoder_create", _vp, _vp)
+_sig("dnab_exact_decoder_feed", C.c_int, _vp, C.c_char_p, C.c_size_t)
+_sig("dnab_exact_decoder_close", C.c_int, _vp)
+_sig("dnab_exact_decoder_take_symbols", _vp, _vp)
+_sig("dnab_exact_decoder_warnings", _vp, _vp)
+_sig("dnab_exact_decoder_hypotheses", C.c_int64, _vp)
+_sig("dnab_exact_decoder_destroy", None, _vp)
+_sig("dnab_pack_decoded_symbols", C.c_int64, C.c_char_p, C.c_size_t, _vp, C.c_size_t, C.c_char_p, C.POINTER(_vp))
+_sig("dnab_exact_decode_fasta", C.c_int, _vp, C.c_char_p, C.POINTER(_vp), C.POINTER(C.c_size_t), C.POINTER(_vp))
 
 
 def _err(code=-1):
@@ -248,6 +257,94 @@ class Machine:
             lib.dnab_machine_free(self._h)
             self._h = None
 
+
+
+def _take_string(p):
+    if not p:
+        raise _err()
+    try:
+        return C.string_at(p).decode()
+    finally:
+        lib.dnab_free(p)
+
+
+class ExactDecoder:
+    """Error-free decoding on the host: the reference's ``Decoder<Writer>`` (src/decoder.h:7-190), i.e. what
+    ``--decode-string`` / ``--decode-bits`` / ``-d`` drive.  ``feed`` = ``decodeString``, ``close`` = ``close``;
+    ``take_symbols`` returns the input symbols resolved so far ('0', '1', '^', '$', control letters)."""
+
+    def __init__(self, machine):
+        self._machine = machine  # the C++ decoder keeps a reference to it
+        self._h = lib.dnab_exact_decoder_create(machine._h)
+        if not self._h:
+            raise _err()
+
+    def feed(self, bases):
+        b = bases.encode()
+        rc = lib.dnab_exact_decoder_feed(self._h, b, len(b))
+        if rc:
+            raise _err(rc)
+        return self
+
+    def close(self):
+        rc = lib.dnab_exact_decoder_close(self._h)
+        if rc:
+            raise _err(rc)
+        return self
+
+    def take_symbols(self):
+        return _take_string(lib.dnab_exact_decoder_take_symbols(self._h))
+
+    @property
+    def warnings(self):
+        return _take_string(lib.dnab_exact_decoder_warnings(self._h)).splitlines()
+
+    @property
+    def hypotheses(self):
+        return lib.dnab_exact_decoder_hypotheses(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.dnab_exact_decoder_destroy(self._h)
+            self._h = None
+
+
+def exact_decode_bits(machine, dna):
+    """``--decode-bits DNA`` (reference t/dnastore.cpp:205-211): the input-symbol string, e.g. ``^0001...0$``."""
+    dec = ExactDecoder(machine).feed(dna).close()
+    return dec.take_symbols()
+
+
+def pack_decoded_symbols(symbols):
+    """``BinaryWriter`` (reference src/decoder.h:193-240). Returns (bytes, leftover bits as the reference's warning
+    prints them, warnings)."""
+    s = symbols.encode()
+    buf = C.create_string_buffer(len(s) // 8 + 1)
+    left = C.create_string_buffer(16)
+    warn = _vp()
+    n = lib.dnab_pack_decoded_symbols(s, len(s), buf, len(s) // 8 + 1, left, C.byref(warn))
+    if n < 0:
+        raise _err(n)
+    return buf.raw[:n], left.value.decode(), _take_string(warn.value).splitlines()
+
+
+def exact_decode_string(machine, dna):
+    """``--decode-string DNA`` (reference t/dnastore.cpp:199-202): the decoded bytes."""
+    return pack_decoded_symbols(exact_decode_bits(machine, dna))[0]
+
+
+def exact_decode_fasta(machine, path):
+    """``-d/--decode-file FASTA`` (reference t/dnastore.cpp:185-190): every record through one decoder, bytes out.
+    Returns (bytes, warnings)."""
+    out, n, warn = _vp(), C.c_size_t(0), _vp()
+    rc = lib.dnab_exact_decode_fasta(machine._h, os.fspath(path).encode(), C.byref(out), C.byref(n), C.byref(warn))
+    if rc:
+        raise _err(rc)
+    try:
+        data = C.string_at(out.value, n.value)
+    finally:
+        lib.dnab_free(out)
+    return data, _take_string(warn.value).splitlines()
 
 class Compiled:
     """Flat tables in host memory (include/dnab_tables.h)."""

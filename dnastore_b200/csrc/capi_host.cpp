@@ -10,6 +10,7 @@
 
 #include "../../include/dnastore_b200.h"
 #include "capi_error.h"
+#include "host/exact_decoder.h"
 #include "host/fasta.h"
 #include "host/machine.h"
 #include "host/pairhmm.h"
@@ -27,6 +28,10 @@ struct dnab_machine {
 };
 struct dnab_compiled {
   CompiledTables c;
+};
+struct dnab_exact_decoder {
+  ExactDecoder d;
+  explicit dnab_exact_decoder(const Machine& m) : d(m) {}
 };
 struct dnab_pair_db {
   std::vector<PairAlignment> aligns;
@@ -365,6 +370,99 @@ int dnab_baum_welch(int device, const dnab_mutator_params* init, const dnab_pair
         return (int)DNAB_OK;
       },
       (int)DNAB_EINVAL);
+}
+
+/* ---- exact decoding (host/exact_decoder.h) ---- */
+static std::string joinLines(const std::vector<std::string>& lines) {
+  std::string all;
+  for (const auto& l : lines) all += l + "\n";
+  return all;
+}
+
+dnab_exact_decoder* dnab_exact_decoder_create(const dnab_machine* m) {
+  if (!m) {
+    setLastError("dnab_exact_decoder_create: null machine");
+    return nullptr;
+  }
+  return guarded([&]() { return new dnab_exact_decoder(m->m); }, (dnab_exact_decoder*)nullptr);
+}
+int dnab_exact_decoder_feed(dnab_exact_decoder* d, const char* bases, size_t n) {
+  if (!d || (!bases && n)) return DNAB_EINVAL;
+  return guarded(
+      [&]() {
+        for (size_t i = 0; i < n; ++i) d->d.decodeSymbol(bases[i]);
+        return (int)DNAB_OK;
+      },
+      (int)DNAB_EINVAL);
+}
+int dnab_exact_decoder_close(dnab_exact_decoder* d) {
+  if (!d) return DNAB_EINVAL;
+  return guarded(
+      [&]() {
+        d->d.close();
+        return (int)DNAB_OK;
+      },
+      (int)DNAB_EINVAL);
+}
+char* dnab_exact_decoder_take_symbols(dnab_exact_decoder* d) {
+  if (!d) return nullptr;
+  return guarded([&]() { return dupString(d->d.takeSymbols()); }, (char*)nullptr);
+}
+char* dnab_exact_decoder_warnings(const dnab_exact_decoder* d) {
+  if (!d) return nullptr;
+  return guarded([&]() { return dupString(joinLines(d->d.warnings())); }, (char*)nullptr);
+}
+int64_t dnab_exact_decoder_hypotheses(const dnab_exact_decoder* d) { return d ? (int64_t)d->d.hypotheses() : 0; }
+void dnab_exact_decoder_destroy(dnab_exact_decoder* d) { delete d; }
+
+int64_t dnab_pack_decoded_symbols(const char* symbols, size_t n, uint8_t* bytes, size_t cap, char* leftover_bits,
+                                  char** warnings) {
+  if (!symbols && n) return DNAB_EINVAL;
+  return guarded(
+      [&]() -> int64_t {
+        const PackedBits p = packDecodedSymbols(std::string(symbols ? symbols : "", n));
+        if (p.bytes.size() > cap) {
+          setLastError("dnab_pack_decoded_symbols: output buffer too small");
+          return DNAB_EINVAL;
+        }
+        if (bytes && !p.bytes.empty()) std::memcpy(bytes, p.bytes.data(), p.bytes.size());
+        if (leftover_bits) std::memcpy(leftover_bits, p.leftoverBits.c_str(), p.leftoverBits.size() + 1);
+        if (warnings) *warnings = dupString(joinLines(p.warnings));
+        return (int64_t)p.bytes.size();
+      },
+      (int64_t)DNAB_EINVAL);
+}
+
+int dnab_exact_decode_fasta(const dnab_machine* m, const char* fasta_path, uint8_t** bytes, size_t* n_bytes,
+                            char** warnings) {
+  if (!m || !fasta_path || !bytes || !n_bytes) return DNAB_EINVAL;
+  *bytes = nullptr;
+  *n_bytes = 0;
+  if (warnings) *warnings = nullptr;
+  try {
+    std::vector<FastSeq> seqs;
+    try {
+      seqs = readFastSeqs(fasta_path);
+    } catch (const std::exception& e) {
+      setLastError(e.what());
+      return DNAB_EIO;
+    }
+    ExactDecoder dec(m->m);  // ONE decoder for every record: its state carries over (t/dnastore.cpp:187-190)
+    for (const auto& fs : seqs) dec.decodeString(fs.seq);
+    dec.close();
+    const PackedBits p = packDecodedSymbols(dec.symbols());
+    *bytes = (uint8_t*)std::malloc(p.bytes.size() + 1);
+    if (!*bytes) throw std::bad_alloc();
+    std::memcpy(*bytes, p.bytes.data(), p.bytes.size());
+    *n_bytes = p.bytes.size();
+    if (warnings) *warnings = dupString(joinLines(dec.warnings()) + joinLines(p.warnings));
+    return DNAB_OK;
+  } catch (const std::exception& e) {
+    setLastError(e.what());
+    std::free(*bytes);
+    *bytes = nullptr;
+    return DNAB_EINVAL;
+  }
 }
 
 }  // extern "C"

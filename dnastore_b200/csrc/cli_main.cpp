@@ -8,6 +8,9 @@
 //   -C/--compose-machine FILE     repeatable; first listed = outermost
 //   -S/--save-machine FILE|-      write the (composed) machine JSON
 //   -V/--decode-viterbi FASTA     batched Viterbi decode on the GPU
+//   -d/--decode-file FASTA        exact (error-free) decode on the host, bytes to stdout (decoder.h)
+//   -D/--decode-string DNA        the same for one DNA string
+//   -B/--decode-bits DNA          the decoded input-symbol string (^0101...$) instead of bytes
 //   -r/--raw                      print bare decoded strings, one per line
 //   --error-sub-prob (.01) --error-iv-ratio (10) --error-dup-prob (.001)
 //   --error-del-open (.001) --error-del-ext (.01) --error-global  -F/--error-file
@@ -32,7 +35,8 @@ static void die(const std::string& msg, int code = 1) {
 int main(int argc, char** argv) {
   dnab_error_flags ef;
   dnab_error_flags_default(&ef);
-  std::string loadMachine, saveMachine, viterbiFile, errorFile;
+  std::string loadMachine, saveMachine, viterbiFile, errorFile, exactFile, exactString, exactBits;
+  bool haveExactString = false, haveExactBits = false;
   std::vector<std::string> composes;
   bool raw = false;
   int verbose = 2, device = 0;
@@ -79,6 +83,9 @@ int main(int argc, char** argv) {
     else if (name == "compose-machine") composes.push_back(need());
     else if (name == "save-machine") saveMachine = need();
     else if (name == "decode-viterbi") viterbiFile = need();
+    else if (name == "decode-file") exactFile = need();
+    else if (name == "decode-string") { exactString = need(); haveExactString = true; }
+    else if (name == "decode-bits") { exactBits = need(); haveExactBits = true; }
     else if (name == "raw") raw = true;
     else if (name == "error-sub-prob") ef.sub_prob = std::atof(need().c_str());
     else if (name == "error-iv-ratio") ef.iv_ratio = std::atof(need().c_str());
@@ -125,7 +132,60 @@ int main(int argc, char** argv) {
     dnab_free(text);
   }
 
-  if (!viterbiFile.empty()) {
+  // exact decoding on the host (reference t/dnastore.cpp:185-211); same precedence as the reference's if-chain
+  auto warn = [](char* lines) {
+    if (!lines) return;
+    std::string all = lines, line;
+    dnab_free(lines);
+    for (char c : all) {
+      if (c == '\n') {
+        std::cerr << "Warning: " << line << std::endl;
+        line.clear();
+      } else
+        line.push_back(c);
+    }
+  };
+  auto exactSymbols = [&](const std::string& dna) -> std::string {
+    dnab_exact_decoder* xd = dnab_exact_decoder_create(machine);
+    if (!xd) die(dnab_last_error());
+    if (dnab_exact_decoder_feed(xd, dna.data(), dna.size()) != DNAB_OK || dnab_exact_decoder_close(xd) != DNAB_OK) {
+      std::cerr << dnab_last_error() << std::endl;
+      std::abort();  // the reference's Assert aborts (util.h:31)
+    }
+    warn(dnab_exact_decoder_warnings(xd));
+    char* sym = dnab_exact_decoder_take_symbols(xd);
+    std::string out = sym ? sym : "";
+    dnab_free(sym);
+    dnab_exact_decoder_destroy(xd);
+    return out;
+  };
+  if (!exactFile.empty()) {
+    uint8_t* bytes = nullptr;
+    size_t n = 0;
+    char* w = nullptr;
+    const int rc = dnab_exact_decode_fasta(machine, exactFile.c_str(), &bytes, &n, &w);
+    if (rc != DNAB_OK) {
+      std::cerr << dnab_last_error() << std::endl;
+      if (rc == DNAB_EIO) return 1;
+      std::abort();
+    }
+    std::fwrite(bytes, 1, n, stdout);
+    std::fflush(stdout);
+    dnab_free(bytes);
+    warn(w);
+  } else if (haveExactString) {
+    const std::string sym = exactSymbols(exactString);
+    std::string bytes(sym.size() / 8 + 1, '\0');
+    char left[16];
+    char* w = nullptr;
+    const int64_t n = dnab_pack_decoded_symbols(sym.data(), sym.size(), (uint8_t*)&bytes[0], bytes.size(), left, &w);
+    if (n < 0) die(dnab_last_error());
+    std::fwrite(bytes.data(), 1, (size_t)n, stdout);
+    std::fflush(stdout);
+    warn(w);
+  } else if (haveExactBits) {
+    std::cout << exactSymbols(exactBits) << std::endl;
+  } else if (!viterbiFile.empty()) {
     dnab_compiled* compiled = errorFile.empty() ? dnab_compile(machine, &ef)
                                                 : dnab_compile_with_error_file(machine, errorFile.c_str());
     if (!compiled) {

@@ -233,6 +233,44 @@ void dnab_decoded_free(dnab_decoded_set* s);
 
 
 /* ------------------------------------------------------------------------
+ * Exact (error-free) decoding on the host: dnastore's -d/--decode-file, --decode-string and
+ * --decode-bits (call sites t/dnastore.cpp:185-211).  Not a GPU path: O(L) per read and strictly
+ * sequential; kept so that BASELINE config 1 and the reference's testdecode goldens
+ * (Makefile:142-144,153,168,176,183) run through this library.
+ *   Decoder<Writer>   src/decoder.h:7-190   (expand :54-103, decodeSymbol :130-158,
+ *                                            shiftResolvedSymbols :160-184, close :28-47)
+ *   BinaryWriter      src/decoder.h:193-240 (bits packed least significant first)
+ * ---------------------------------------------------------------------- */
+typedef struct dnab_exact_decoder dnab_exact_decoder;
+/* Decoder::Decoder (decoder.h:16-22); `m` must outlive the decoder. */
+dnab_exact_decoder* dnab_exact_decoder_create(const dnab_machine* m);
+/* Decoder::decodeString (decoder.h:186-189): n bases, case-insensitive.  DNAB_EINVAL with
+ * dnab_last_error() = the reference's assertion text when a base cannot be decoded or the machine is
+ * ambiguous (the reference aborts there). */
+int dnab_exact_decoder_feed(dnab_exact_decoder* d, const char* bases, size_t n);
+/* Decoder::close (decoder.h:28-47): end of input. */
+int dnab_exact_decoder_close(dnab_exact_decoder* d);
+/* Input symbols ('0','1','^','$', control letters) resolved since the last call; dnab_free() it. */
+char* dnab_exact_decoder_take_symbols(dnab_exact_decoder* d);
+/* The reference's "Decoder unresolved ..." warnings so far, one per line; dnab_free() it. */
+char* dnab_exact_decoder_warnings(const dnab_exact_decoder* d);
+int64_t dnab_exact_decoder_hypotheses(const dnab_exact_decoder* d);   /* |current| of decoder.h:13 */
+void dnab_exact_decoder_destroy(dnab_exact_decoder* d);
+
+/* BinaryWriter (decoder.h:193-240): packs the '0'/'1' symbols into bytes (first bit = bit 0), skips
+ * '^' '$', warns about anything else.  Returns the number of bytes (written to `bytes` if cap allows, else
+ * DNAB_EINVAL); leftover_bits (>= 8 chars incl. NUL) receives the bits of an unfinished last byte, most
+ * significant first, as the reference's destructor warning prints them; *warnings (optional): one per line,
+ * dnab_free() it. */
+int64_t dnab_pack_decoded_symbols(const char* symbols, size_t n, uint8_t* bytes, size_t cap, char* leftover_bits,
+                                  char** warnings);
+/* -d/--decode-file (t/dnastore.cpp:185-190): every record of a FASTA/FASTQ file through ONE decoder
+ * (its state carries over between records, as in the reference), close, then BinaryWriter.
+ * *bytes is malloc'ed (dnab_free); *warnings optional, as above. */
+int dnab_exact_decode_fasta(const dnab_machine* m, const char* fasta_path, uint8_t** bytes, size_t* n_bytes,
+                            char** warnings);
+
+/* ------------------------------------------------------------------------
  * Pair-HMM forward / backward / expected counts: the reference's
  * only forward-backward, over the (original DNA x observed DNA) lattice of a 2-row
  * alignment, used to train the error model (--error-counts / --fit-error).
