@@ -15,16 +15,8 @@
 //
 // Mapping: one CTA per read, reads handed out dynamically; the columns live in an L2-resident
 // scratch (6+2k doubles per state and CTA), the transition lists are the destination-indexed CSR
-// tables of include/dnab_tables.h in the reference's list order.
-//
-// Frontier.  A Jacobi sweep evaluates state d from the previous sweep's values of its in-neighbours; if
-// none of them changed in the previous sweep, the result is bit for bit what the previous sweep computed
-// for d.  So from the second sweep on only the states with a changed in-neighbour are evaluated (38-67 %
-// of the state-sweeps on the BASELINE machines): pass A reads one "changed" bit per in-neighbour from a
-// bitmap in shared memory and compacts the active states into a per-CTA queue (one shared-memory atomic
-// per warp), pass B evaluates the queue with all lanes busy.  A state that is skipped but changed in the
-// previous sweep is copied into the other ping-pong buffer.  The cells, the sweep counts and the
-// termination test are those of the specification (every state evaluated in every sweep).
+// tables of include/dnab_tables.h in the reference's list order.  A first version: correct and
+// batched, not yet tuned (no shared-memory columns, no frontier).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -47,14 +39,9 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
   __shared__ unsigned long long nextSlot;
   __shared__ __align__(16) uint8_t seqS[4096];
   __shared__ double symScore[kMaxSyms];
-  __shared__ uint32_t qCount[2];
-  extern __shared__ uint32_t chgBits[];  // two bitmaps of nWords words: states changed by the latest / the previous sweep
-  const uint32_t nWords = (N + 31) / 32, lane = tid & 31;
-  uint32_t* const chg[2] = {chgBits, chgBits + nWords};
 
   for (uint32_t s = tid; s < kMaxSyms; s += nThreads) symScore[s] = s < tb.nSyms ? tb.symScore[s] : NEG;
-  double* base = args.scratch + (size_t)blockIdx.x * (10 + 2 * k) * N;
-  uint32_t* const queue = reinterpret_cast<uint32_t*>(base + (size_t)(9 + 2 * k) * N);  // active states of a sweep
+  double* base = args.scratch + (size_t)blockIdx.x * (9 + 2 * k) * N;
   double* Sprev = base;
   double* S0 = base + N;
   double* Sb[2] = {base + 2 * (size_t)N, base + 3 * (size_t)N};
@@ -109,9 +96,8 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
         Db[0][d] = NEG;
       }
       __syncthreads();
-      // closure: Jacobi sweeps until a sweep changes no cell (evaluated on the frontier, see the header)
+      // closure: Jacobi sweeps until a sweep changes no cell
       cur = 0;
-      uint32_t cw = 0;
       for (int sweep = 0;; ++sweep) {
         if (sweep >= args.maxSweeps) {
           status = 1;
@@ -121,10 +107,8 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
         const double* Do = Db[cur];
         double* Sn = Sb[cur ^ 1];
         double* Dn = Db[cur ^ 1];
-        const uint32_t* chgOld = chg[cw];
-        uint32_t* chgNew = chg[cw ^ 1];
         int changed = 0;
-        auto evaluate = [&](uint32_t d) -> bool {
+        for (uint32_t d = tid; d < N; d += nThreads) {
           double nd = NEG, ns = S0[d];
           for (uint32_t e = __ldg(tb.emitOff + d); e < __ldg(tb.emitOff + d + 1); ++e) {
             const uint32_t s = __ldg(tb.emitSrc + e);
@@ -139,59 +123,10 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
           ns = lse(L2T, ns, nd + tb.delEnd);
           Dn[d] = nd;
           Sn[d] = ns;
-          return __double_as_longlong(nd) != __double_as_longlong(Do[d]) || __double_as_longlong(ns) != __double_as_longlong(So[d]);
-        };
-        if (sweep == 0) {
-          if (tid == 0) qCount[1] = 0;
-          for (uint32_t d0 = tid - lane; d0 < N; d0 += nThreads) {
-            const uint32_t d = d0 + lane;
-            const bool c = d < N && evaluate(d);
-            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, c);
-            if (lane == 0) chgNew[d0 >> 5] = mask;
-            changed |= c;
-          }
-        } else {
-          // pass A: which states have an in-neighbour that changed in the previous sweep?
-          for (uint32_t d0 = tid - lane; d0 < N; d0 += nThreads) {
-            const uint32_t d = d0 + lane;
-            bool act = false;
-            if (d < N) {
-              for (uint32_t e = __ldg(tb.emitOff + d); e < __ldg(tb.emitOff + d + 1); ++e) {
-                const uint32_t s = __ldg(tb.emitSrc + e);
-                act |= (chgOld[s >> 5] >> (s & 31)) & 1u;
-              }
-              for (uint32_t e = __ldg(tb.nullOff + d); e < __ldg(tb.nullOff + d + 1); ++e) {
-                const uint32_t s = __ldg(tb.nullSrc + e);
-                act |= (chgOld[s >> 5] >> (s & 31)) & 1u;
-              }
-              if (!act && ((chgOld[d >> 5] >> (d & 31)) & 1u)) {  // same value as last sweep: bring the other buffer up to date
-                Sn[d] = So[d];
-                Dn[d] = Do[d];
-              }
-            }
-            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, act);
-            uint32_t at = 0;
-            if (lane == 0) {
-              chgNew[d0 >> 5] = 0;
-              if (mask) at = atomicAdd(&qCount[sweep & 1], (uint32_t)__popc(mask));
-            }
-            at = __shfl_sync(0xFFFFFFFFu, at, 0);
-            if (act) queue[at + __popc(mask & ((1u << lane) - 1u))] = d;
-          }
-          __syncthreads();
-          const uint32_t nQueued = qCount[sweep & 1];
-          if (tid == 0) qCount[(sweep + 1) & 1] = 0;
-          // pass B: evaluate them
-          for (uint32_t i = tid; i < nQueued; i += nThreads) {
-            const uint32_t d = queue[i];
-            if (evaluate(d)) {
-              atomicOr(&chgNew[d >> 5], 1u << (d & 31));
-              changed = 1;
-            }
-          }
+          if (__double_as_longlong(nd) != __double_as_longlong(Do[d]) || __double_as_longlong(ns) != __double_as_longlong(So[d]))
+            changed = 1;
         }
         cur ^= 1;
-        cw ^= 1;
         ++sweepsTotal;
         if (!__syncthreads_or(changed)) break;
       }
@@ -277,7 +212,7 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
           D2[0][s] = NEG;
         }
         __syncthreads();
-        uint32_t cb = 0, cwb = 0;
+        uint32_t cb = 0;
         for (int sweep = 0;; ++sweep) {
           if (sweep >= args.maxSweeps) {
             status = 1;
@@ -287,10 +222,8 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
           const double* Do = D2[cb];
           double* Sn = S2[cb ^ 1];
           double* Dn = D2[cb ^ 1];
-          const uint32_t* chgOld = chg[cwb];
-          uint32_t* chgNew = chg[cwb ^ 1];
           int changed = 0;
-          auto evaluate = [&](uint32_t s) -> bool {
+          for (uint32_t s = tid; s < N; s += nThreads) {
             double ns = bbase[s], nd = NEG;
             for (uint32_t p = __ldg(tb.outEmitOff + s); p < __ldg(tb.outEmitOff + s + 1); ++p) {
               const double sc = symScore[__ldg(tb.outEmitMeta + p) & 31], bd = Do[__ldg(tb.outEmitDst + p)];
@@ -306,58 +239,10 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
             nd = lse(L2T, nd, tb.delEnd + ns);
             Sn[s] = ns;
             Dn[s] = nd;
-            return __double_as_longlong(ns) != __double_as_longlong(So[s]) || __double_as_longlong(nd) != __double_as_longlong(Do[s]);
-          };
-          if (sweep == 0) {
-            if (tid == 0) qCount[1] = 0;
-            for (uint32_t s0 = tid - lane; s0 < N; s0 += nThreads) {
-              const uint32_t s = s0 + lane;
-              const bool c = s < N && evaluate(s);
-              const uint32_t mask = __ballot_sync(0xFFFFFFFFu, c);
-              if (lane == 0) chgNew[s0 >> 5] = mask;
-              changed |= c;
-            }
-          } else {
-            // pass A: states with an out-neighbour that changed in the previous sweep
-            for (uint32_t s0 = tid - lane; s0 < N; s0 += nThreads) {
-              const uint32_t s = s0 + lane;
-              bool act = false;
-              if (s < N) {
-                for (uint32_t p = __ldg(tb.outEmitOff + s); p < __ldg(tb.outEmitOff + s + 1); ++p) {
-                  const uint32_t d = __ldg(tb.outEmitDst + p);
-                  act |= (chgOld[d >> 5] >> (d & 31)) & 1u;
-                }
-                for (uint32_t p = __ldg(tb.outNullOff + s); p < __ldg(tb.outNullOff + s + 1); ++p) {
-                  const uint32_t d = __ldg(tb.outNullDst + p);
-                  act |= (chgOld[d >> 5] >> (d & 31)) & 1u;
-                }
-                if (!act && ((chgOld[s >> 5] >> (s & 31)) & 1u)) {
-                  Sn[s] = So[s];
-                  Dn[s] = Do[s];
-                }
-              }
-              const uint32_t mask = __ballot_sync(0xFFFFFFFFu, act);
-              uint32_t at = 0;
-              if (lane == 0) {
-                chgNew[s0 >> 5] = 0;
-                if (mask) at = atomicAdd(&qCount[sweep & 1], (uint32_t)__popc(mask));
-              }
-              at = __shfl_sync(0xFFFFFFFFu, at, 0);
-              if (act) queue[at + __popc(mask & ((1u << lane) - 1u))] = s;
-            }
-            __syncthreads();
-            const uint32_t nQueued = qCount[sweep & 1];
-            if (tid == 0) qCount[(sweep + 1) & 1] = 0;
-            for (uint32_t i = tid; i < nQueued; i += nThreads) {
-              const uint32_t s = queue[i];
-              if (evaluate(s)) {
-                atomicOr(&chgNew[s >> 5], 1u << (s & 31));
-                changed = 1;
-              }
-            }
+            if (__double_as_longlong(ns) != __double_as_longlong(So[s]) || __double_as_longlong(nd) != __double_as_longlong(Do[s]))
+              changed = 1;
           }
           cb ^= 1;
-          cwb ^= 1;
           ++sweepsBack;
           if (!__syncthreads_or(changed)) break;
         }
@@ -436,13 +321,7 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
 
 cudaError_t launchForward(const ForwardTables& tb, const ForwardArgs& args, uint32_t nBlocks, uint32_t threads,
                           cudaStream_t stream) {
-  const size_t smem = 2 * (size_t)((tb.nStates + 31) / 32) * sizeof(uint32_t);  // the two "changed" bitmaps
-  if (smem > 200 * 1024) return cudaErrorInvalidValue;                            // > 819,200 states
-  if (smem > 32 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(forwardKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  forwardKernel<<<nBlocks, threads, smem, stream>>>(tb, args);
+  forwardKernel<<<nBlocks, threads, 0, stream>>>(tb, args);
   return cudaGetLastError();
 }
 
