@@ -1114,7 +1114,7 @@ static int forwardImpl(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   CUDA_TRY(d->dLoglike.ensure((size_t)n));
   CUDA_TRY(d->dStatus.ensure((size_t)n));
   CUDA_TRY(d->dFwdSweeps.ensure((size_t)n));
-  CUDA_TRY(d->dFwdScratch.ensure((size_t)nBlocks * (9 + 2 * k) * N));
+  CUDA_TRY(d->dFwdScratch.ensure((size_t)nBlocks * (10 + 2 * k) * N));
   CUDA_TRY(d->dNextRead.ensure(1));
   size_t cellCount = 0;
   if (cells) {

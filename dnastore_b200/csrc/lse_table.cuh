@@ -48,4 +48,23 @@ __device__ __forceinline__ double lse(const double* __restrict__ table, double a
   return mx + lseUnary(table, diff);
 }
 
+// The same function without branches (select instead of early return), so that two independent
+// evaluations can be interleaved by the instruction scheduler.  Bit-identical to lse(): for a == b finite the
+// difference is +0 and the interpolation yields table[0] exactly as lseUnary(0) does; for a == b == -inf the
+// difference is NaN, which takes the "return 0" arm just like an infinite difference, and -inf + 0 == -inf +
+// log 2; every other case evaluates the same expressions.
+__device__ __forceinline__ double lseFlat(const double* __restrict__ table, double a, double b) {
+  const bool lt = a < b;
+  const double mx = lt ? b : a;
+  const double diff = lt ? b - a : a - b;
+  const bool far = !(diff < 10);  // >= 10, inf or NaN: logsumexp.h:53-55
+  const double x = far ? 0. : diff;
+  const int n = (int)divByLseStep(x);
+  const double dx = x - (n * .0001);
+  const double f0 = __ldg(table + n), f1 = __ldg(table + n + 1);
+  const double df = f1 - f0;
+  const double r = f0 + df * divByLseStep(dx);
+  return mx + (far ? 0. : r);
+}
+
 }  // namespace dnab

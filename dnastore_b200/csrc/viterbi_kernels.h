@@ -217,7 +217,7 @@ struct ForwardArgs {
   const int64_t* byteOff;
   const int32_t* readLen;
   int32_t maxLen;                // F stride: every block owns (maxLen+1) columns
-  double* scratch;               // [nBlocks][(9+2k)*N]
+  double* scratch;               // [nBlocks][(10+2k)*N]: columns + the frontier queue
   double* F;                     // optional [nBlocks][maxLen+1][N][k+2]: forward cells kept for the backward pass
   double* counts;                // optional [nReads][5+k+16] posterior expected counts (needs F)
   double* loglikeBack;           // [nReads] backward log-likelihood (with counts)

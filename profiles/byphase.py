@@ -27,9 +27,10 @@ def find(marker):
 
 
 marks = [("helpers", 1), ("pushState", find("uint32_t pushState(")), ("kernel set-up", find("viterbiFillPushKernel(const __grid_constant__")),
-         ("(1) emission step", find("// ---- (1) emission step")), ("(2a) first closure pass", find("// ---- (2a) closure, first pass")),
-         ("(2b) level scan", find("// ---- (2b) closure, PUSH levels")), ("(2b) push loop", find("if (n > args.tailN) {")),
-         ("(2b) level-end barrier / cluster meeting", find("const uint32_t anyFlagged")), ("(3) predecessor pass", find("// ---- (3) predecessor records")),
+         ("(1) S0 copy into shared memory", find("// ---- (1) S0(pos) into shared memory")), ("(2a) first closure pass", find("// ---- (2a) closure, first pass")),
+         ("(2b) level scan + queue barrier", find("// ---- (2b) closure, PUSH levels")), ("(2b) push loop", find("// one hop per level, breadth first")),
+         ("(2b) level-end barrier / cluster meeting", find("// every push of this level has flagged or queued")),
+         ("(3) predecessor pass + emission step of the next column", find("// ---- (3) predecessor records")),
          ("end of read", find("// ---- end of read"))]
 
 
