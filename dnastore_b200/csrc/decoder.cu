@@ -1095,7 +1095,11 @@ static int forwardImpl(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
     return DNAB_EINVAL;
   }
   packedBytes = std::max<size_t>(packedBytes, 16);
-  uint32_t nBlocks = (uint32_t)std::min<int64_t>(n, d->smCount);
+  // one CTA per read in flight; small machines get narrower CTAs and several of them per SM (the kernel is capped
+  // at 64 registers, so 1024 threads per SM in total): l4c4 (384 states) 12.1k -> 24.0k reads/s
+  const uint32_t fwdThreads = N >= 4096 ? 1024u : N >= 2048 ? 512u : N >= 1024 ? 256u : 128u;
+  const uint32_t fwdPerSm = 1024 / fwdThreads;
+  uint32_t nBlocks = (uint32_t)std::min<int64_t>(n, (int64_t)d->smCount * fwdPerSm);
   const uint32_t nc = 5 + k + 16;
   const size_t fPerBlock = counts ? (size_t)(maxLen + 1) * N * (k + 2) : 0;  // forward cells kept for the backward pass
   if (counts) {
@@ -1172,7 +1176,7 @@ static int forwardImpl(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   fa.loglikeBack = counts ? d->dFwdLLBack.p : nullptr;
   fa.sweepsBack = counts ? d->dFwdSweepsBack.p : nullptr;
   CUDA_TRY(cudaEventRecord(d->ev0, stream));
-  CUDA_TRY(launchForward(ft, fa, nBlocks, 1024, stream));
+  CUDA_TRY(launchForward(ft, fa, nBlocks, fwdThreads, stream));
   CUDA_TRY(cudaEventRecord(d->ev1, stream));
   d->stats.kernel_launches += 1;
   CUDA_TRY(cudaMemcpyAsync(loglike, d->dLoglike.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
