@@ -263,7 +263,7 @@ __device__ __forceinline__ uint32_t pushState(const Ctx& c, uint32_t s, uint4 sl
 
 }  // namespace
 
-template <int kMaxThreads, int kMinBlocks, bool kCluster>
+template <int kMaxThreads, int kMinBlocks, bool kCluster, bool kDebug>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
     viterbiFillPushKernel(const __grid_constant__ DevTables tb, const __grid_constant__ FillArgs args) {
   constexpr int kU = kPushStatesPerThread;  // states per thread and step of a dense pass
@@ -396,9 +396,23 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 
   // profiling counters (dnab_decoder_debug_counters): added straight to global memory by thread 0 of rank 0, so that
   // they cost no registers when they are off
-  const bool dbgOn = args.dbg != nullptr;
+  // (the counters exist only in the kDebug instantiation, launched when dnab_decoder_set_debug is on: in the
+  // production kernel they would cost registers and branches -- 14 counters kept in registers once cost 11 %)
+  constexpr bool dbgOn = kDebug;
   const bool dbgMe = dbgOn && tid == 0 && rank == 0;
   auto dbgAdd = [&](int slot, unsigned long long v) { atomicAdd(&args.dbg[slot], v); };
+  // time stamps of the cluster's reporting thread (column phase, closure start, level phase)
+  __shared__ unsigned long long dbgStamps[kDebug ? 3 : 1];
+  auto dbgStamp = [&](int stamp) {
+    if (dbgMe) dbgStamps[stamp] = (unsigned long long)clock64();
+  };
+  auto dbgLap = [&](int stamp, int slot) {  // adds the time since the stamp to a counter and renews the stamp
+    if (dbgMe) {
+      const unsigned long long t = (unsigned long long)clock64();
+      atomicAdd(&args.dbg[slot], t - dbgStamps[stamp]);
+      dbgStamps[stamp] = t;
+    }
+  };
 
   // Reads are handed out dynamically (one global counter, fetched by rank 0 and broadcast through
   // distributed shared memory): reads differ in length, and a static stride leaves the clusters that
@@ -475,7 +489,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         tPrev0 = dmax(shifted, (s1 + tb.tanDup) + lenS[0]);
       };
 
-      long long tc0 = dbgOn ? clock64() : 0;
+      dbgStamp(0);
       // ---- (1) S0(pos) into shared memory.  The emission step itself (src/viterbi.cpp:92-106) is FUSED into the
       // predecessor pass of the previous column (3b below), which has every S(pos-1)[src] in shared memory
       // anyway; its result travelled through a scratch column in global memory because S(pos-1) was still being
@@ -494,7 +508,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         stsCell(aD + 8 * i, NEG);
       }
       clusterBarrier();  // S0 of every CTA is complete before a peer reads it
-      long long tc1 = dbgOn ? clock64() : 0;
+      dbgLap(0, 3);
+      dbgStamp(1);
 
       // ---- (2a) closure, first pass, PULL over the streamed in-table (src/viterbi.cpp:97-99,110-159).
       // Successors may have read S0(d) / D = -inf or the new values (racy, benign); a state is flagged
@@ -554,7 +569,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         commit();
       }
       clusterBarrier();  // no peer pushes into this CTA's cells while its first pass still stores them
-      long long tc1b = dbgOn ? clock64() : 0;
+      dbgLap(0, 7);
 
       // ---- (2b) closure, PUSH levels.  Per level: the set bits of the dirty bitmap are taken and
       // compacted into a CTA-wide queue (one lane per bitmap word, one shared-memory atomic per warp);
@@ -581,7 +596,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         for (uint32_t levels = 0;; ++levels) {
           const uint32_t par = levels & 1;
           const uint32_t tANext = tA == 2 ? 0u : tA + 1, tAAfter = tANext == 2 ? 0u : tANext + 1;
-          const long long tl0 = dbgOn ? clock64() : 0;
+          dbgStamp(2);
           bool flagged = false, deferred = false;
           uint32_t n, aList;
           if (kCluster || !fromAppend) {
@@ -629,7 +644,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             if (n > capA) n = capA;
             aList = aA + par * strideA;
           }
-          const long long tl1 = dbgOn ? clock64() : 0;
+          dbgLap(2, 9);
           if (dbgMe) dbgAdd(1, 1);
           if (levels > (1u << 22)) __trap();  // never hang the GPU: a closure that does not settle is a bug
           if (!kCluster && tid == 0) sts32(aTailA + 4 * tAAfter, 0u);
@@ -662,16 +677,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           else
             pushList(std::false_type{});
           if (dbgMe) dbgAdd(2, n);
-          const long long tl2 = dbgOn ? clock64() : 0;
+          dbgLap(2, 10);
           // every push of this level has flagged or queued its successors
           const uint32_t needScan = (uint32_t)__syncthreads_or((flagged || deferred) ? 1 : 0);
           tA = tANext;
-          if (dbgMe) {
-            const long long tl3 = clock64();
-            dbgAdd(9, tl1 - tl0);
-            dbgAdd(10, tl2 - tl1);
-            dbgAdd(12, tl3 - tl2);
-          }
+          dbgLap(2, 12);
           if (needScan) {  // (a scan also takes the bits of whatever was appended meanwhile: that list is dropped)
             fromAppend = false;
             continue;
@@ -683,12 +693,12 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           fromAppend = false;
           if (!kCluster) break;
           // locally quiet: meet the cluster; another round if anything crossed CTAs since the last meeting
-          const long long tcb = dbgOn ? clock64() : 0;
+          dbgStamp(2);
           const uint32_t anySent = (uint32_t)__syncthreads_or(sent ? 1 : 0);
           sent = false;
           if (tid < C) stPeerU32(sm + lay.ctl + (16 + (round & 1) * kMaxCluster + rank) * 4, tid, anySent);
           cluster.sync();
-          if (dbgMe) dbgAdd(11, clock64() - tcb);
+          dbgLap(2, 11);
           uint32_t tot = 0;
           for (uint32_t r = 0; r < C; ++r) tot |= ctl[16 + (round & 1) * kMaxCluster + r];
           ++round;
@@ -696,7 +706,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           if (dbgMe) dbgAdd(6, 1);
         }
       }
-      long long tc2 = dbgOn ? clock64() : 0;
+      if (dbgMe) {
+        const unsigned long long t = (unsigned long long)clock64();
+        atomicAdd(&args.dbg[4], t - dbgStamps[1]);
+        dbgStamps[0] = t;
+      }
 
       // ---- (3) predecessor records with the traceback's arithmetic (src/viterbi.cpp:251-286)
       //      (4) duplication opens (src/viterbi.cpp:161-168) ----
@@ -848,14 +862,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         commit();
       }
       clusterBarrier();
-      if (dbgMe) {
-        const long long tc3 = clock64();
-        dbgAdd(3, tc1 - tc0);
-        dbgAdd(7, tc1b - tc1);
-        dbgAdd(4, tc2 - tc1);
-        dbgAdd(5, tc3 - tc2);
-        dbgAdd(0, 1);
-      }
+      dbgLap(0, 5);
+      if (dbgMe) dbgAdd(0, 1);
     }
 
     // ---- end of read: log-likelihood and traceback start (src/viterbi.cpp:171-173, 239-245) ----
@@ -927,16 +935,17 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 // launchers
 // ---------------------------------------------------------------------------
 typedef void (*PushKernelPtr)(const DevTables, const FillArgs);
-template <bool kCluster>
+template <bool kCluster, bool kDebug>
 static PushKernelPtr pickPushKernelT(uint32_t threads) {
-  if (threads > 800) return viterbiFillPushKernel<1024, 1, kCluster>;  // 64 registers/thread
-  if (threads > 640) return viterbiFillPushKernel<800, 1, kCluster>;   // 80
-  if (threads > 512) return viterbiFillPushKernel<640, 1, kCluster>;   // 96
-  if (threads > 256) return viterbiFillPushKernel<512, 1, kCluster>;   // 128
-  return viterbiFillPushKernel<256, 2, kCluster>;                      // 128
+  if (threads > 800) return viterbiFillPushKernel<1024, 1, kCluster, kDebug>;  // 64 registers/thread
+  if (threads > 640) return viterbiFillPushKernel<800, 1, kCluster, kDebug>;   // 80
+  if (threads > 512) return viterbiFillPushKernel<640, 1, kCluster, kDebug>;   // 96
+  if (threads > 256) return viterbiFillPushKernel<512, 1, kCluster, kDebug>;   // 128
+  return viterbiFillPushKernel<256, 2, kCluster, kDebug>;                      // 128
 }
-static PushKernelPtr pickPushKernel(const DevTables& tb, uint32_t threads) {
-  return tb.C > 1 ? pickPushKernelT<true>(threads) : pickPushKernelT<false>(threads);
+static PushKernelPtr pickPushKernel(const DevTables& tb, uint32_t threads, bool debug) {
+  if (debug) return tb.C > 1 ? pickPushKernelT<true, true>(threads) : pickPushKernelT<false, true>(threads);
+  return tb.C > 1 ? pickPushKernelT<true, false>(threads) : pickPushKernelT<false, false>(threads);
 }
 
 static cudaError_t prepPush(PushKernelPtr kern, const DevTables& tb, uint32_t smemBytes) {
@@ -963,7 +972,7 @@ static void pushClusterConfig(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr
 
 cudaError_t launchFillPush(const DevTables& tb, const FillArgs& args, uint32_t nClusters, uint32_t threads,
                            uint32_t smemBytes, cudaStream_t stream) {
-  PushKernelPtr kern = pickPushKernel(tb, threads);
+  PushKernelPtr kern = pickPushKernel(tb, threads, args.dbg != nullptr);
   cudaError_t err = prepPush(kern, tb, smemBytes);
   if (err != cudaSuccess) return err;
   cudaLaunchConfig_t cfg;
@@ -973,7 +982,7 @@ cudaError_t launchFillPush(const DevTables& tb, const FillArgs& args, uint32_t n
 }
 
 cudaError_t queryMaxClustersPush(const DevTables& tb, uint32_t threads, uint32_t smemBytes, int* nClusters) {
-  PushKernelPtr kern = pickPushKernel(tb, threads);
+  PushKernelPtr kern = pickPushKernel(tb, threads, false);
   cudaError_t err = prepPush(kern, tb, smemBytes);
   if (err != cudaSuccess) return err;
   cudaLaunchConfig_t cfg;

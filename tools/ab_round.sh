@@ -14,3 +14,4 @@ for l in sys.stdin:
 }
 for rep in 1 2; do run x A cfg2; run x B cfg2; done
 for wl in cfg3 cfg4 cfg5 cfg1; do run x A $wl; run x B $wl; done
+unset DNAB_LIB; python tools/probe_phases.py cfg2 66 2>&1 | tail -1 | tee gpurun_out/probe_phases_cfg2.log
