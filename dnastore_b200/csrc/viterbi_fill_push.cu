@@ -941,7 +941,12 @@ static PushKernelPtr pickPushKernelT(uint32_t threads) {
   if (threads > 640) return viterbiFillPushKernel<800, 1, kCluster, kDebug>;   // 80
   if (threads > 512) return viterbiFillPushKernel<640, 1, kCluster, kDebug>;   // 96
   if (threads > 256) return viterbiFillPushKernel<512, 1, kCluster, kDebug>;   // 128
-  return viterbiFillPushKernel<256, 2, kCluster, kDebug>;                      // 128
+  // narrow CTAs (small machines, many CTAs per SM): registers are allocated in units of 8, so 81 means 88 and one
+  // resident CTA fewer than 80 -- a third block in the launch bounds caps the one-CTA kernel at 80
+  if constexpr (!kCluster)
+    return viterbiFillPushKernel<256, 3, false, kDebug>;  // 80
+  else
+    return viterbiFillPushKernel<256, 2, true, kDebug>;  // 128
 }
 static PushKernelPtr pickPushKernel(const DevTables& tb, uint32_t threads, bool debug) {
   if (debug) return tb.C > 1 ? pickPushKernelT<true, true>(threads) : pickPushKernelT<false, true>(threads);
