@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
   // they cost no registers when they are off
   // (the counters exist only in the kDebug instantiation, launched when dnab_decoder_set_debug is on: in the
   // production kernel they would cost registers and branches -- 14 counters kept in registers once cost 11 %)
-  constexpr bool dbgOn = kDebug;
+  const bool dbgOn = kDebug && args.dbg != nullptr;  // (the kDebug kernel also serves the cell dump of dnab_viterbi_cells)
   const bool dbgMe = dbgOn && tid == 0 && rank == 0;
   auto dbgAdd = [&](int slot, unsigned long long v) { atomicAdd(&args.dbg[slot], v); };
   // time stamps of the cluster's reporting thread (column phase, closure start, level phase)
@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
             }
             predCol[g] = (uint8_t)(real ? idx[u] : kNoPred);
             predCol[Np + g] = (uint8_t)(real ? idxD[u] : kNoPred);
-            double* cell = (args.cells && read == 0 && real)
+            double* cell = (kDebug && args.cells && read == 0 && real)  // the cell dump exists in the kDebug kernel only
                                ? args.cells + ((size_t)pos * tb.nStates + __ldg(&tb.origId[g])) * (k + 2)
                                : nullptr;
             if (cell) {
@@ -977,7 +977,7 @@ static void pushClusterConfig(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr
 
 cudaError_t launchFillPush(const DevTables& tb, const FillArgs& args, uint32_t nClusters, uint32_t threads,
                            uint32_t smemBytes, cudaStream_t stream) {
-  PushKernelPtr kern = pickPushKernel(tb, threads, args.dbg != nullptr);
+  PushKernelPtr kern = pickPushKernel(tb, threads, args.dbg != nullptr || args.cells != nullptr);
   cudaError_t err = prepPush(kern, tb, smemBytes);
   if (err != cudaSuccess) return err;
   cudaLaunchConfig_t cfg;
