@@ -137,3 +137,31 @@ int main(void) {
     subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(src), "-lm"], check=True)
     tot, bad = map(int, subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
     assert tot > 8e7 and bad == 0
+
+
+def test_fasta_ingest_forms_through_the_exact_decoder(tmp_path):
+    """readFastSeqs (reference src/fastseq.cpp:123-148, kseq): plain or gzip, FASTA or FASTQ, multi-line records
+    concatenated, name = header up to the first blank, lower case accepted downstream.  Exercised on the CPU through
+    dnab_exact_decode_fasta (-d), which reads with the same ingest code as the Viterbi path."""
+    case = [c for c in json.load(open(os.path.join(util.GOLDEN, "exact_golden.json")))["cases"] if c["kind"] == "file"][0]
+    m = util.machine_from_recipe(tuple(case["recipe"]))
+    dna = case["records"][0]
+    forms = {
+        "plain.fa": f">hello some comment\n{dna}\n",
+        "multiline.fa": ">hello\n" + "\n".join(dna[i:i + 7] for i in range(0, len(dna), 7)) + "\n",
+        "lower.fa": f">hello\n{dna.lower()}\n",
+        "reads.fq": f"@hello\n{dna}\n+\n{'I' * len(dna)}\n",
+        "two_records.fa": f">a\n{dna[:20]}\n>b\n{dna[20:]}\n",  # one decoder across records (t/dnastore.cpp:187-190)
+    }
+    for name, text in forms.items():
+        p = tmp_path / name
+        p.write_text(text)
+        data, warnings = d.exact_decode_fasta(m, p)
+        assert data == b"HELLO", name
+        assert warnings == case["warnings"], name
+    gz = tmp_path / "plain.fa.gz"
+    with gzip.open(gz, "wt") as f:
+        f.write(forms["multiline.fa"])
+    assert d.exact_decode_fasta(m, gz)[0] == b"HELLO"
+    with pytest.raises(d.DnabError):
+        d.exact_decode_fasta(m, tmp_path / "missing.fa")
