@@ -157,7 +157,7 @@ def cpu_reference_run(w, machine, compiled, reads, n_procs):
         subprocess.run(base + ["--save-machine", os.devnull], check=True, capture_output=True)
         t_load = time.perf_counter() - t0
         t0 = time.perf_counter()
-        procs = [subprocess.Popen(base + ["-V", f, "--error-global", "--raw"], stdout=subprocess.PIPE, text=True)
+        procs = [subprocess.Popen(base + ["-V", f, "--error-global", "--raw"] + list(w.get("ref_flags", [])), stdout=subprocess.PIPE, text=True)
                  for f in files]
         outs = [p.communicate()[0] for p in procs]
         dt = time.perf_counter() - t0 - t_load
@@ -273,6 +273,7 @@ def main():
     ap.add_argument("--table-mode", type=int, default=0)
     ap.add_argument("--partition", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=4, help="reads in the single-core CPU baseline sample (0 = skip)")
+    ap.add_argument("--no-indel", action="store_true", help="decode with --error-del-open 0 --error-dup-prob 0 (closure degenerates)")
     ap.add_argument("--mode", default="viterbi", choices=["viterbi", "fwdback"],
                     help="fwdback: forward + backward + posterior counts over the machine lattice (SURVEY 8a-12, BASELINE "
                          "configs[4]; not in the reference, CPU baseline = the specification in oracle/forward_oracle.c)")
@@ -282,6 +283,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = WORKLOADS[args.workload]
+    if args.no_indel:
+        # the same workload decoded with --error-del-open 0 --error-dup-prob 0 -- the within-column
+        # closure degenerates to one visit per state, an upper bound on what the exact closure costs
+        w = dict(w, flags=dict(del_open=0., dup_prob=0.), ref_flags=["--error-del-open", "0", "--error-dup-prob", "0"],
+                 desc=w["desc"] + ", --error-del-open 0 --error-dup-prob 0")
 
     import __graft_entry__ as g
     if rank == 0:
@@ -293,7 +299,7 @@ def main():
         if rank != 0:
             return
         machine = util.machine_from_recipe(w["recipe"])
-        compiled = machine.compile(d.ErrorFlags(length=w["length"], global_=True))
+        compiled = machine.compile(d.ErrorFlags(length=w["length"], global_=True, **w.get("flags", {})))
         t = compiled.t
         cores = os.cpu_count() or 1
         per_step = cores  # one read per core per step: a bounded sample of the same workload
@@ -327,7 +333,7 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     machine = util.machine_from_recipe(w["recipe"])
-    compiled = machine.compile(d.ErrorFlags(length=w["length"], global_=True))
+    compiled = machine.compile(d.ErrorFlags(length=w["length"], global_=True, **w.get("flags", {})))
     t = compiled.t
     dec = d.Decoder(compiled, device=local_rank)
     if args.cluster or args.threads or args.tmode or args.table_mode or args.partition:
