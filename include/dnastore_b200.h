@@ -212,7 +212,9 @@ typedef struct dnab_decoder_stats {
 int dnab_decoder_get_stats(const dnab_decoder* d, dnab_decoder_stats* s);
 int dnab_decoder_set_timing(dnab_decoder* d, int enabled);
 int dnab_decoder_reset_timing(dnab_decoder* d);
-/* Profiling aid: in-kernel counters (columns, closure sweeps, worklist entries, SM cycles per phase). */
+/* Profiling aid: in-kernel counters (columns, closure sweeps, worklist entries, SM cycles per phase).  When on, the
+ * fill runs an instrumented instantiation of the kernel (same results, a few per cent slower); the production
+ * instantiation carries no counters at all.  dnab_viterbi_cells uses the instrumented one as well. */
 int dnab_decoder_set_debug(dnab_decoder* d, int enabled);
 int dnab_decoder_debug_counters(dnab_decoder* d, unsigned long long* out16);
 
