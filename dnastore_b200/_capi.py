@@ -58,6 +58,11 @@ class DecoderInfo(C.Structure):
                                           "smem_bytes_per_cta", "t_in_smem", "table_in_smem", "s_prev_in_smem", "n_clusters", "sm_count")]
 
 
+class BatchInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("enabled", "reads_per_group", "team_size", "states_per_cta", "warps_per_cta",
+                                          "smem_bytes_per_cta", "n_teams", "reserved")] + [("cross_cta_transition_fraction", C.c_double)]
+
+
 class DecoderStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("fill_launches", C.c_uint64), ("traceback_launches", C.c_uint64),
                 ("reads", C.c_uint64), ("cells", C.c_uint64), ("last_fill_ms", C.c_double), ("last_traceback_ms", C.c_double),
@@ -141,6 +146,8 @@ _sig("dnab_decoder_configure_ex", C.c_int, _vp, C.c_uint32, C.c_uint32)
 _sig("dnab_decoder_get_stats", C.c_int, _vp, C.POINTER(DecoderStats))
 _sig("dnab_decoder_set_timing", C.c_int, _vp, C.c_int)
 _sig("dnab_decoder_reset_timing", C.c_int, _vp)
+_sig("dnab_decoder_set_option", C.c_int, _vp, C.c_char_p, C.c_int64)
+_sig("dnab_decoder_get_batch_info", C.c_int, _vp, _vp)
 _sig("dnab_decoder_set_debug", C.c_int, _vp, C.c_int)
 _sig("dnab_decoder_debug_counters", C.c_int, _vp, _vp)
 _sig("dnab_packed_size", C.c_size_t, _vp, C.c_int64)
@@ -497,6 +504,19 @@ class Decoder:
         rc = lib.dnab_decoder_configure_ex(self._h, table_mode, partition_mode)
         if rc:
             raise _err(rc)
+
+    def set_option(self, key, value):
+        """Named option (include/dnastore_b200.h dnab_decoder_set_option), e.g. kernel=1 (read-batched), 2 (push), 3 (pull)."""
+        rc = lib.dnab_decoder_set_option(self._h, key.encode(), int(value))
+        if rc:
+            raise _err(rc)
+
+    def batch_info(self):
+        i = BatchInfo()
+        rc = lib.dnab_decoder_get_batch_info(self._h, C.byref(i))
+        if rc:
+            raise _err(rc)
+        return {n: getattr(i, n) for n, _ in BatchInfo._fields_}
 
     def info(self):
         i = DecoderInfo()

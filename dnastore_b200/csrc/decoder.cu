@@ -13,6 +13,7 @@
 
 #include "../../include/dnastore_b200.h"
 #include "capi_error.h"
+#include "viterbi_batch.h"
 #include "viterbi_kernels.h"
 
 namespace dnab {
@@ -56,6 +57,13 @@ struct LaunchPlan {
   int32_t maxLen = -1;
 };
 
+// plan of the read-batched kernel (viterbi_fill_batch.cu)
+struct BatchPlan {
+  bool ready = false, feasible = false;
+  uint32_t T = 0, M = 0, warps = 0, smemBytes = 0, nTeams = 0, ctasPerSm = 0;
+  double crossFraction = 0;  // transitions whose ends live in different CTAs
+};
+
 }  // namespace dnab
 
 using namespace dnab;
@@ -76,7 +84,9 @@ struct dnab_decoder {
   uint32_t wantBlockMode = 0;   // transition table: 0 auto, 1 shared memory, 2 global memory
   uint32_t idleSleepNs = 100;
   uint32_t tRecompute = 1;
-  uint32_t thinN = 1024;  // push kernel, one-CTA machines: levels of at most this many states queue their successors directly (DNAB_THIN_N)
+  uint32_t thinN = 1024;  // push kernel, one-CTA machines: levels of at most this many states queue their successors directly (option "thin_n")
+  uint32_t dealChunks = 8;  // push kernel, partition mode 3: DFS chunks dealt per CTA (option "deal_chunks")
+  uint32_t queueCap = 0;    // push kernel: cap of the level queue, 0 = automatic (option "queue_cap")
   uint32_t wantSPrevMode = 0;   // S(pos-1): 0 auto, 1 shared memory, 2 global scratch
   uint32_t wantKernel = 0;      // 0 push kernel (viterbi_fill_push.cu), 1 pull kernel (viterbi_kernels.cu)
   uint32_t wantPartition = 0;   // 0/1 index-order runs + in-degree sort (default), 2 DFS runs unsorted, 3 DFS chunks dealt round-robin + sort, 4 DFS runs + sort
@@ -102,6 +112,21 @@ struct dnab_decoder {
   DevBuf<long long> dFwdSweepsBack;
   DevBuf<long long> dFwdSweeps;
   bool debug = false;
+  // read-batched kernel: 32 reads per group are the SIMD lanes (viterbi_fill_batch.cu)
+  int32_t wantBatch = -1;       // -1 auto (used when feasible and no push/pull tuning was requested), 0 off, 1 required
+  uint32_t wantTeam = 0;        // CTAs per team (0 = smallest that fits)
+  uint32_t wantWarps = 0;       // warps per CTA (0 = 32)
+  BatchPlan bplan;
+  BatchTables btab{};
+  BatchTraceTables btrace{};
+  DevBuf<uint4> dbHdr;
+  DevBuf<uint2> dbIn;
+  DevBuf<uint32_t> dbOut, dbRankInOff, dbRankOutOff, dbEmitOff, dbEmitSrc, dbNullOff, dbNullSrc, dbInbox, dbPartOrig;
+  DevBuf<uint8_t> dbEmitSym, dbNullSym;
+  DevBuf<double> dbTsE, dbSPub, dbS0Next, dbTPark, dbPartVal;
+  DevBuf<double2> dbSdPub;
+  DevBuf<unsigned long long> dbBarrier;
+  DevBuf<int32_t> dbOrder;
   // staging for the host-buffer path
   DevBuf<uint8_t> dPacked;
   DevBuf<int64_t> dByteOff;
@@ -196,8 +221,7 @@ static int buildPartition(const dnab_decoder* d, uint32_t C, Partition& P) {
   // locality for CTAs that are busy for equally long inside a closure round
   std::vector<std::vector<uint32_t>> dealt(C);
   if (partMode == 3 && C > 1) {
-    uint32_t deal = 8;  // chunks per CTA (tuning: DNAB_DEAL_CHUNKS)
-    if (const char* e = getenv("DNAB_DEAL_CHUNKS")) deal = std::max(1, atoi(e));
+    const uint32_t deal = std::max<uint32_t>(1, d->dealChunks);  // chunks per CTA (option "deal_chunks")
     const uint32_t chunk = std::max<uint32_t>(32, (N + deal * C - 1) / (deal * C));
     uint32_t r = 0;
     for (uint32_t lo = 0; lo < N;) {
@@ -441,7 +465,7 @@ static int buildPlanPush(dnab_decoder* d, int32_t planLen) {
     for (const auto& o : opts) {
       const uint32_t needOut = o[0], sIn = o[1], tIn = (k == 0) ? 0 : o[2];
       uint32_t qCap = o[3] ? M : std::max<uint32_t>(1024, M / 4);
-      if (const char* e = getenv("DNAB_QUEUE_CAP")) qCap = std::max<uint32_t>(32, std::min<uint32_t>(qCap, (uint32_t)atoi(e)));  // test hook
+      if (d->queueCap) qCap = std::max<uint32_t>(32, std::min<uint32_t>(qCap, d->queueCap));  // option "queue_cap" (test hook)
       if (d->wantBlockMode == 1 && !needOut) continue;
       if (d->wantBlockMode == 2 && needOut) continue;
       if (d->wantSPrevMode == 1 && !sIn) continue;
@@ -648,6 +672,347 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
   return DNAB_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// read-batched kernel: partition, tables, scratch (formats: viterbi_batch.h)
+// ---------------------------------------------------------------------------
+static bool batchWanted(const dnab_decoder* d) {
+  if (d->wantBatch == 0) return false;
+  if (d->wantBatch == 1) return true;
+  // automatic: the batched kernel, unless the caller tuned the one-read-per-cluster kernels explicitly
+  return !(d->wantC || d->wantThreads || d->wantTMode || d->wantBlockMode || d->wantSPrevMode || d->wantKernel ||
+           d->wantPartition);
+}
+
+static int buildBatchPlan(dnab_decoder* d) {
+  BatchPlan& bp = d->bplan;
+  if (bp.ready) {
+    if (!bp.feasible) setLastError("the read-batched kernel cannot take this machine");
+    return bp.feasible ? DNAB_OK : DNAB_EINVAL;
+  }
+  bp.ready = true;
+  bp.feasible = false;
+  const uint32_t N = d->nStates, k = d->k;
+  const uint32_t W = d->wantWarps ? (d->wantWarps > 16 ? 32u : d->wantWarps > 8 ? 16u : 8u) : 32u;
+  auto nEmitOf = [&](uint32_t s) { return d->emitOff[s + 1] - d->emitOff[s]; };
+  auto nNullOf = [&](uint32_t s) { return d->nullOff[s + 1] - d->nullOff[s]; };
+  for (uint32_t s = 0; s < N; ++s) {
+    const uint32_t nE = nEmitOf(s), nN = nNullOf(s);
+    if (nE > 126 || 2 * nE + nN > 254 || nE + nN + 2 > 254) {
+      setLastError("state " + std::to_string(s) + " has too many incoming transitions for 1-byte predecessor records");
+      return DNAB_EINVAL;
+    }
+  }
+  // successors of every state with the bit they own in the successor's work mask
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> outs(N);
+  for (uint32_t dst = 0; dst < N; ++dst) {
+    uint32_t j = 0;
+    for (uint32_t e = d->emitOff[dst]; e < d->emitOff[dst + 1]; ++e, ++j) outs[d->emitSrc[e]].push_back({dst, std::min(j, 31u)});
+    for (uint32_t e = d->nullOff[dst]; e < d->nullOff[dst + 1]; ++e, ++j) outs[d->nullSrc[e]].push_back({dst, std::min(j, 31u)});
+  }
+  for (auto& o : outs) {
+    std::sort(o.begin(), o.end());
+    o.erase(std::unique(o.begin(), o.end()), o.end());
+    if (o.size() > 255) {
+      setLastError("a state has more than 255 outgoing transitions");
+      return DNAB_EINVAL;
+    }
+  }
+  const std::vector<uint32_t> dfs = dfsOrder(d);
+  const uint32_t maxTeam = (uint32_t)d->smCount;
+  uint32_t T0 = std::max<uint32_t>(1, (uint32_t)(((size_t)N * kBatchReads * 16 + d->smemOptin - 1) / d->smemOptin));
+  if (d->wantTeam) T0 = d->wantTeam;
+  std::vector<uint4> hdr;
+  std::vector<uint2> inE;
+  std::vector<uint32_t> outE, rankInOff, rankOutOff, newOf(N), origOf;
+  for (uint32_t T = T0; T <= maxTeam; ++T) {
+    const uint32_t M = (N + T - 1) / T, Np = T * M;
+    if (M > kBatchMaxSlots * W || M > 65535 || T > 1023) {
+      if (d->wantTeam) break;
+      continue;
+    }
+    if (makeBatchLayout(M, 0, 0, W).total > d->smemOptin) {
+      if (d->wantTeam) break;
+      continue;
+    }
+    // CTA assignment: balanced runs of a depth-first order (T > 1); inside a CTA descending in-degree, dealt to the warps
+    origOf.assign(Np, 0xFFFFFFFFu);
+    for (uint32_t r = 0; r < T; ++r) {
+      const uint32_t lo = (uint32_t)((uint64_t)N * r / T), hi = (uint32_t)((uint64_t)N * (r + 1) / T);
+      std::vector<uint32_t> mine;
+      for (uint32_t i = lo; i < hi; ++i) mine.push_back(T > 1 ? dfs[i] : i);
+      std::stable_sort(mine.begin(), mine.end(),
+                       [&](uint32_t a, uint32_t b) { return nEmitOf(a) + nNullOf(a) > nEmitOf(b) + nNullOf(b); });
+      for (uint32_t j = 0; j < mine.size(); ++j) {
+        origOf[r * M + j] = mine[j];
+        newOf[mine[j]] = r * M + j;
+      }
+    }
+    hdr.assign(Np, make_uint4(0, 0, 1u << 17, 0xFFFFFFFFu));
+    inE.clear();
+    outE.clear();
+    rankInOff.assign(T + 1, 0);
+    rankOutOff.assign(T + 1, 0);
+    uint32_t maxIn = 0, maxOut = 0;
+    uint64_t cross = 0, total = 0;
+    bool ok = true;
+    for (uint32_t r = 0; r < T && ok; ++r) {
+      rankInOff[r] = (uint32_t)inE.size();
+      rankOutOff[r] = (uint32_t)outE.size();
+      for (uint32_t i = 0; i < M; ++i) {
+        const uint32_t s = origOf[r * M + i];
+        if (s == 0xFFFFFFFFu) continue;
+        const uint32_t inOff = (uint32_t)inE.size() - rankInOff[r], outOff = (uint32_t)outE.size() - rankOutOff[r];
+        if (inOff > 65535 || outOff > 65535) {
+          ok = false;
+          break;
+        }
+        const uint32_t nE = nEmitOf(s), nN = nNullOf(s);
+        auto pushIn = [&](uint32_t src, uint32_t sym, uint32_t base) {
+          const uint32_t sg = newOf[src];
+          const bool remote = sg / M != r;
+          inE.push_back(make_uint2(sg, sym | (base << 5) | (remote ? 1u << 7 : 0u)));
+          ++total;
+          cross += remote;
+        };
+        for (uint32_t e = d->emitOff[s]; e < d->emitOff[s + 1]; ++e) pushIn(d->emitSrc[e], d->emitSym[e], d->emitBase[e]);
+        for (uint32_t e = d->nullOff[s]; e < d->nullOff[s + 1]; ++e) pushIn(d->nullSrc[e], d->nullSym[e], 0);
+        bool remoteOut = (d->local && s == 0 && T > 1);  // local mode: every CTA reads S(start,0) for the (0,0) escape
+        for (const auto& o : outs[s]) {
+          const uint32_t dg = newOf[o.first];
+          const bool remote = dg / M != r;
+          remoteOut |= remote;
+          outE.push_back((dg % M) | (o.second << 16) | ((dg / M) << 21) | (remote ? 1u << 31 : 0u));
+        }
+        uint32_t ctxBits = 0;
+        for (uint32_t t = 0; t < d->mdl[s]; ++t) ctxBits |= (uint32_t)(d->ctx[(size_t)s * k + t] & 3u) << (2 * t);
+        hdr[r * M + i] = make_uint4(inOff | (outOff << 16), nE | (nN << 8) | ((uint32_t)outs[s].size() << 16) | ((uint32_t)d->mdl[s] << 24),
+                                    ctxBits | (remoteOut ? 1u << 16 : 0u), s);
+      }
+      maxIn = std::max(maxIn, (uint32_t)inE.size() - rankInOff[r]);
+      maxOut = std::max(maxOut, (uint32_t)outE.size() - rankOutOff[r]);
+    }
+    rankInOff[T] = (uint32_t)inE.size();
+    rankOutOff[T] = (uint32_t)outE.size();
+    if (!ok) {
+      if (d->wantTeam) break;
+      continue;
+    }
+    const uint32_t smem = makeBatchLayout(M, maxIn, maxOut, W).total;
+    if (smem > d->smemOptin) {
+      if (d->wantTeam) break;
+      continue;
+    }
+    bp.T = T;
+    bp.M = M;
+    bp.warps = W;
+    bp.smemBytes = smem;
+    bp.crossFraction = total ? (double)cross / (double)total : 0.;
+    BatchTables& t = d->btab;
+    t = BatchTables{};
+    t.nStates = N;
+    t.M = M;
+    t.T = T;
+    t.k = k;
+    t.local = d->local;
+    t.nSyms = (uint32_t)d->symChar.size();
+    t.startRank = newOf[0] / M;
+    t.startLocal = newOf[0] % M;
+    t.endRank = newOf[N - 1] / M;
+    t.endLocal = newOf[N - 1] % M;
+    t.maxIn = maxIn;
+    t.maxOut = maxOut;
+    bp.feasible = true;
+    break;
+  }
+  if (!bp.feasible) {
+    setLastError("the read-batched kernel cannot take this machine: " + std::to_string(N) +
+                 " states x 32 reads x 16 bytes exceed the shared memory of " + std::to_string(maxTeam) + " SMs");
+    return DNAB_EINVAL;
+  }
+  BatchTables& t = d->btab;
+  inE.push_back(make_uint2(0, 0));
+  outE.push_back(0);
+  CUDA_TRY(d->dbHdr.upload(hdr));
+  CUDA_TRY(d->dbIn.upload(inE));
+  CUDA_TRY(d->dbOut.upload(outE));
+  CUDA_TRY(d->dbRankInOff.upload(rankInOff));
+  CUDA_TRY(d->dbRankOutOff.upload(rankOutOff));
+  // score tables with the traceback's association, formed once on the host in IEEE fp64 (-ffp-contract=off)
+  std::vector<double> tsE(32 * 16, 0.);
+  for (uint32_t sym = 0; sym < d->symScore.size(); ++sym)
+    for (uint32_t b = 0; b < 4; ++b)
+      for (uint32_t x = 0; x < 4; ++x) {
+        volatile double a = d->symScore[sym] + d->noGap;  // (score + noGap) + sub, src/viterbi.cpp:255
+        tsE[(sym * 4 + b) * 4 + x] = a + d->sub[b * 4 + x];
+      }
+  CUDA_TRY(d->dbTsE.upload(tsE));
+  t.hdr = d->dbHdr.p;
+  t.inEdges = d->dbIn.p;
+  t.outEdges = d->dbOut.p;
+  t.rankInOff = d->dbRankInOff.p;
+  t.rankOutOff = d->dbRankOutOff.p;
+  t.tsE = d->dbTsE.p;
+  for (int i = 0; i < kMaxSyms; ++i) {
+    const double sc = i < (int)d->symScore.size() ? d->symScore[i] : 0.;
+    t.symScore[i] = sc;
+    t.tsDext[i] = sc + d->delExtend;  // src/viterbi.cpp:272
+    t.tsDopen[i] = sc + d->delOpen;   // src/viterbi.cpp:273
+  }
+  for (int i = 0; i < 8; ++i) {
+    t.len[i] = i < kMaxK ? d->len[i] : 0.;
+    t.tsT[i] = d->tanDup + t.len[i];  // src/viterbi.cpp:286
+  }
+  std::memcpy(t.sub, d->sub, sizeof t.sub);
+  t.noGap = d->noGap;
+  t.delOpen = d->delOpen;
+  t.delExtend = d->delExtend;
+  t.delEnd = d->delEnd;
+  t.tanDup = d->tanDup;
+  // traceback tables in reference order
+  CUDA_TRY(d->dbEmitOff.upload(d->emitOff));
+  CUDA_TRY(d->dbEmitSrc.upload(d->emitSrc));
+  CUDA_TRY(d->dbEmitSym.upload(d->emitSym));
+  CUDA_TRY(d->dbNullOff.upload(d->nullOff));
+  CUDA_TRY(d->dbNullSrc.upload(d->nullSrc));
+  CUDA_TRY(d->dbNullSym.upload(d->nullSym));
+  CUDA_TRY(d->dSymChar.upload(d->symChar));
+  BatchTraceTables& tt = d->btrace;
+  tt.nStates = N;
+  tt.k = k;
+  tt.local = d->local;
+  tt.T = bp.T;
+  tt.emitOff = d->dbEmitOff.p;
+  tt.emitSrc = d->dbEmitSrc.p;
+  tt.emitSym = d->dbEmitSym.p;
+  tt.nullOff = d->dbNullOff.p;
+  tt.nullSrc = d->dbNullSrc.p;
+  tt.nullSym = d->dbNullSym.p;
+  tt.symChar = d->dSymChar.p;
+  int perSm = 0;
+  CUDA_TRY(queryBatchTeams(t, bp.warps, bp.smemBytes, &perSm));
+  if (perSm < 1) {
+    bp.feasible = false;
+    setLastError("the read-batched kernel does not fit an SM");
+    return DNAB_ECUDA;
+  }
+  bp.ctasPerSm = (uint32_t)perSm;
+  bp.nTeams = (uint32_t)d->smCount * bp.ctasPerSm / bp.T;
+  if (bp.nTeams < 1) {
+    bp.feasible = false;
+    setLastError("a team of " + std::to_string(bp.T) + " CTAs cannot be resident at once");
+    return DNAB_EINVAL;
+  }
+  const size_t Np = (size_t)bp.T * bp.M;
+  CUDA_TRY(d->dbSPub.ensure((size_t)bp.nTeams * 2 * Np * 32));
+  CUDA_TRY(d->dbS0Next.ensure((size_t)bp.nTeams * Np * 32));
+  CUDA_TRY(d->dbTPark.ensure(std::max<size_t>(1, (size_t)bp.nTeams * k * Np * 32)));
+  CUDA_TRY(d->dbSdPub.ensure(bp.T > 1 ? (size_t)bp.nTeams * 2 * Np * 32 : 1));
+  CUDA_TRY(d->dbInbox.ensure((size_t)bp.nTeams * bp.T * bp.warps * 32));
+  CUDA_TRY(d->dbBarrier.ensure((size_t)bp.nTeams * 2));
+  return DNAB_OK;
+}
+
+// fill + traceback with the read-batched kernel; hostLen (optional) lets the groups be formed from reads of similar length
+static int runDeviceBatch(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint8_t* dPacked, const int64_t* dByteOff,
+                          const int32_t* dReadLen, double* dLoglike, char* dDecoded, int32_t decodedStride,
+                          int32_t* dDecodedLen, int32_t* dStatus, int32_t* dPath, int32_t pathStride, int32_t* dPathLen,
+                          double* dCells, cudaStream_t stream, bool timeIt, const int32_t* hostLen) {
+  const BatchPlan& bp = d->bplan;
+  const uint32_t N = d->nStates, K2 = d->k + 2;
+  const int64_t nGroups = (nReads + 31) / 32;
+  const size_t perGroup = (size_t)(maxLen + 1) * N * K2 * 32;
+  int64_t chunk = (int64_t)std::max<size_t>(1, d->predBudgetBytes / perGroup);
+  chunk = std::min<int64_t>(chunk, nGroups);
+  CUDA_TRY(d->dPred.ensure((size_t)chunk * perGroup));
+  if (d->local) {
+    CUDA_TRY(d->dbPartVal.ensure((size_t)chunk * bp.T * 32));
+    CUDA_TRY(d->dbPartOrig.ensure((size_t)chunk * bp.T * 32));
+  }
+  const int32_t* dOrder = nullptr;
+  if (hostLen && !dCells && nReads > 32) {
+    // groups of similar length: a group runs for as many columns as its longest read
+    std::vector<int32_t> order((size_t)nGroups * 32, -1);
+    for (int64_t i = 0; i < nReads; ++i) order[(size_t)i] = (int32_t)i;
+    std::stable_sort(order.begin(), order.begin() + nReads, [&](int32_t a, int32_t b) { return hostLen[a] > hostLen[b]; });
+    CUDA_TRY(d->dbOrder.ensure(order.size()));
+    CUDA_TRY(cudaMemcpyAsync(d->dbOrder.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));  // `order` is a local
+    dOrder = d->dbOrder.p;
+  }
+  for (int64_t at = 0; at < nGroups; at += chunk) {
+    const int64_t n = std::min(chunk, nGroups - at);
+    BatchArgs a{};
+    a.nReads = nReads;
+    a.readBase = at * 32;
+    a.nGroups = n;
+    a.nTeams = (uint32_t)std::min<int64_t>(bp.nTeams, n);
+    a.maxLen = maxLen;
+    a.packed = dPacked;
+    a.byteOff = dByteOff;
+    a.readLen = dReadLen;
+    a.order = dOrder ? dOrder + at * 32 : nullptr;
+    a.pred = d->dPred.p;
+    a.sPub = d->dbSPub.p;
+    a.s0Next = d->dbS0Next.p;
+    a.tPark = d->dbTPark.p;
+    a.sdPub = d->dbSdPub.p;
+    a.inbox = d->dbInbox.p;
+    a.barrier = d->dbBarrier.p;
+    a.loglike = dLoglike;
+    a.partVal = d->dbPartVal.p;
+    a.partOrig = d->dbPartOrig.p;
+    a.cells = at == 0 ? dCells : nullptr;
+    a.dbg = d->debug ? d->dDbg.p : nullptr;
+    cudaEvent_t e0 = d->ev0, e1 = d->ev1, e2 = d->ev2;
+    const bool pooled = d->timing && !timeIt;
+    if (pooled) {
+      while (d->evPool.size() < d->evUsed + 3) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        d->evPool.push_back(e);
+      }
+      e0 = d->evPool[d->evUsed];
+      e1 = d->evPool[d->evUsed + 1];
+      e2 = d->evPool[d->evUsed + 2];
+      d->evUsed += 3;
+    }
+    const bool rec = timeIt || pooled;
+    if (bp.T > 1) {
+      CUDA_TRY(cudaMemsetAsync(d->dbInbox.p, 0, d->dbInbox.n * sizeof(uint32_t), stream));
+      CUDA_TRY(cudaMemsetAsync(d->dbBarrier.p, 0, d->dbBarrier.n * sizeof(unsigned long long), stream));
+    }
+    if (rec) CUDA_TRY(cudaEventRecord(e0, stream));
+    CUDA_TRY(launchFillBatch(d->btab, a, bp.warps, bp.smemBytes, stream));
+    if (rec) CUDA_TRY(cudaEventRecord(e1, stream));
+    BatchTraceArgs ta{};
+    ta.nSlots = n * 32;
+    ta.maxLen = maxLen;
+    ta.readLen = dReadLen;
+    ta.order = a.order;
+    ta.nReads = nReads;
+    ta.readBase = a.readBase;
+    ta.pred = d->dPred.p;
+    ta.loglike = dLoglike;
+    ta.partVal = d->dbPartVal.p;
+    ta.partOrig = d->dbPartOrig.p;
+    ta.decoded = dDecoded;
+    ta.decodedStride = decodedStride;
+    ta.decodedLen = dDecodedLen;
+    ta.status = dStatus;
+    ta.path = dPath;
+    ta.pathStride = pathStride;
+    ta.pathLen = dPathLen;
+    CUDA_TRY(launchTracebackBatch(d->btrace, ta, stream));
+    if (rec) CUDA_TRY(cudaEventRecord(e2, stream));
+    d->stats.kernel_launches += 2;
+    d->stats.fill_launches += 1;
+    d->stats.traceback_launches += 1;
+  }
+  d->stats.reads += (uint64_t)nReads;
+  return DNAB_OK;
+}
+
 static size_t predBytesPerRead(const dnab_decoder* d, int32_t maxLen) {
   return (size_t)(maxLen + 1) * (d->k + 2) * (size_t)d->plan.C * d->plan.M;
 }
@@ -657,9 +1022,16 @@ static size_t predBytesPerRead(const dnab_decoder* d, int32_t maxLen) {
 static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint8_t* dPacked, const int64_t* dByteOff,
                      const int32_t* dReadLen, double* dLoglike, char* dDecoded, int32_t decodedStride,
                      int32_t* dDecodedLen, int32_t* dStatus, int32_t* dPath, int32_t pathStride, int32_t* dPathLen,
-                     double* dCells, cudaStream_t stream, bool timeIt) {
+                     double* dCells, cudaStream_t stream, bool timeIt, const int32_t* hostLen = nullptr) {
   if (nReads <= 0) return DNAB_OK;
   CUDA_TRY(cudaSetDevice(d->device));
+  if (batchWanted(d)) {
+    const int brc = buildBatchPlan(d);
+    if (brc == DNAB_OK)
+      return runDeviceBatch(d, nReads, maxLen, dPacked, dByteOff, dReadLen, dLoglike, dDecoded, decodedStride, dDecodedLen,
+                            dStatus, dPath, pathStride, dPathLen, dCells, stream, timeIt, hostLen);
+    if (d->wantBatch == 1) return brc;
+  }
   int rc = buildPlan(d, maxLen);
   if (rc != DNAB_OK) return rc;
   const size_t perRead = predBytesPerRead(d, maxLen);
@@ -784,8 +1156,6 @@ dnab_decoder* dnab_decoder_create(const dnab_tables* t, int device) {
     delete d;
     return nullptr;
   }
-  if (const char* e = getenv("DNAB_THIN_N")) d->thinN = (uint32_t)atoi(e);
-  if (const char* e = getenv("DNAB_T_RECOMPUTE")) d->tRecompute = (uint32_t)atoi(e);
   d->smCount = prop.multiProcessorCount;
   d->smemOptin = prop.sharedMemPerBlockOptin;
   size_t freeB = 0, totalB = 0;
@@ -859,19 +1229,88 @@ int dnab_decoder_configure(dnab_decoder* d, uint32_t cluster_size, uint32_t thre
   if (!d) return DNAB_EINVAL;
   d->wantC = cluster_size;
   d->wantThreads = threads_per_cta;
-  d->wantTMode = t_in_smem_mode % 10;
-  if (t_in_smem_mode >= 10) d->idleSleepNs = (t_in_smem_mode / 10) * 20;  // tuning hook: tens digit * 20 ns
+  d->wantTMode = t_in_smem_mode;
   d->plan = LaunchPlan();
   return DNAB_OK;
 }
 
 int dnab_decoder_configure_ex(dnab_decoder* d, uint32_t block_table_mode, uint32_t partition_mode) {
   if (!d) return DNAB_EINVAL;
+  // kept for round-1 callers: decimal digits select two things each; new code uses dnab_decoder_set_option
   d->wantBlockMode = block_table_mode % 10;
-  d->wantSPrevMode = block_table_mode / 10;  // tens digit: S(pos-1) placement (0 auto, 1 shared, 2 global)
+  d->wantSPrevMode = block_table_mode / 10;
   d->wantPartition = partition_mode % 10;
-  d->wantKernel = partition_mode / 10;  // tens digit: 0 push kernel (default), 1 pull kernel
+  d->wantKernel = partition_mode / 10;
   d->plan = LaunchPlan();
+  return DNAB_OK;
+}
+
+int dnab_decoder_set_option(dnab_decoder* d, const char* key, int64_t value) {
+  if (!d || !key || value < 0) {
+    setLastError("dnab_decoder_set_option: bad argument");
+    return DNAB_EINVAL;
+  }
+  const std::string k(key);
+  const uint32_t v = (uint32_t)value;
+  if (k == "kernel") {  // 0 automatic, 1 read-batched, 2 push (one read per cluster), 3 pull
+    if (v > 3) {
+      setLastError("dnab_decoder_set_option: kernel must be 0..3");
+      return DNAB_EINVAL;
+    }
+    d->wantBatch = v == 0 ? -1 : v == 1 ? 1 : 0;
+    d->wantKernel = v == 3 ? 1 : 0;
+  } else if (k == "team_size")
+    d->wantTeam = v;
+  else if (k == "warps_per_cta")
+    d->wantWarps = v;
+  else if (k == "cluster_size")
+    d->wantC = v;
+  else if (k == "threads_per_cta")
+    d->wantThreads = v;
+  else if (k == "t_columns")  // 0 auto, 1 shared memory, 2 global scratch
+    d->wantTMode = v;
+  else if (k == "table")  // 0 auto, 1 shared memory, 2 global memory
+    d->wantBlockMode = v;
+  else if (k == "s_prev")  // 0 auto, 1 shared memory, 2 global scratch
+    d->wantSPrevMode = v;
+  else if (k == "partition")  // 0 auto, 1 index runs, 2 DFS runs unsorted, 3 DFS chunks dealt, 4 DFS runs sorted
+    d->wantPartition = v;
+  else if (k == "thin_n")
+    d->thinN = v;
+  else if (k == "t_recompute")
+    d->tRecompute = v;
+  else if (k == "queue_cap")
+    d->queueCap = v;
+  else if (k == "deal_chunks")
+    d->dealChunks = v;
+  else if (k == "idle_sleep_ns")
+    d->idleSleepNs = v;
+  else if (k == "pred_budget_mb")
+    d->predBudgetBytes = (size_t)value << 20;
+  else {
+    setLastError("dnab_decoder_set_option: unknown option '" + k + "'");
+    return DNAB_EINVAL;
+  }
+  d->plan = LaunchPlan();
+  d->bplan = BatchPlan();
+  return DNAB_OK;
+}
+
+int dnab_decoder_get_batch_info(const dnab_decoder* dc, dnab_batch_info* info) {
+  if (!dc || !info) return DNAB_EINVAL;
+  auto* d = const_cast<dnab_decoder*>(dc);
+  cudaSetDevice(d->device);
+  std::memset(info, 0, sizeof *info);
+  if (!batchWanted(d)) return DNAB_OK;
+  if (buildBatchPlan(d) != DNAB_OK) return d->wantBatch == 1 ? DNAB_EINVAL : DNAB_OK;
+  info->enabled = 1;
+  info->reads_per_group = kBatchReads;
+  info->team_size = d->bplan.T;
+  info->states_per_cta = d->bplan.M;
+  info->warps_per_cta = d->bplan.warps;
+  info->smem_bytes_per_cta = d->bplan.smemBytes;
+  info->n_teams = d->bplan.nTeams;
+  info->cross_cta_transition_fraction = d->bplan.crossFraction;
   return DNAB_OK;
 }
 
@@ -999,7 +1438,7 @@ static int viterbiHost(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   CUDA_TRY(cudaMemcpyAsync(d->dReadLen.p, readLen, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   int rc = runDevice(d, n, maxLen, d->dPacked.p, d->dByteOff.p, d->dReadLen.p, d->dLoglike.p, d->dDecoded.p, decodedStride,
                      d->dDecodedLen.p, d->dStatus.p, path ? d->dPath.p : nullptr, pathStride,
-                     path ? d->dPathLen.p : nullptr, cells ? d->dCells.p : nullptr, stream, true);
+                     path ? d->dPathLen.p : nullptr, cells ? d->dCells.p : nullptr, stream, true, readLen);
   if (rc != DNAB_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(loglike, d->dLoglike.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaMemcpyAsync(decoded, d->dDecoded.p, (size_t)n * decodedStride, cudaMemcpyDeviceToHost, stream));

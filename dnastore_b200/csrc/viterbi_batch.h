@@ -1,0 +1,161 @@
+// Read-batched Viterbi fill (viterbi_fill_batch.cu): table formats, launch arguments and the
+// shared-memory carve-up, shared between the kernel and the host code that plans it (decoder.cu).
+//
+// The reads are the SIMD lanes.  A GROUP of 32 reads walks the machine together: lane r of every warp
+// works on read r of the group, a warp works on ONE state at a time, so a transition is decoded once per
+// warp instead of once per read, a gather is one conflict-free 512-byte row of shared memory, and what is
+// left per lane is the reference's own fp64 adds and compares (src/viterbi.cpp:92-106,118-158,251-286).
+// A TEAM of T CTAs (T = 1 ... the whole GPU) holds the S and D columns of one group in shared memory,
+// M = ceil(N/T) states per CTA; everything that crosses CTAs goes through L2 (published rows, inbox
+// masks, team barriers), so T is not limited by the cluster size.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "viterbi_device.cuh"
+
+namespace dnab {
+
+constexpr uint32_t kBatchReads = 32;       // reads per group = lanes of a warp
+constexpr uint32_t kBatchMaxSlots = 32;    // a warp owns at most this many states (bits of its work mask)
+constexpr uint32_t kBatchAllEdges = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------------------
+// Per-CTA tables (resident in shared memory).  Padded state space Np = T*M; state g = rank*M + i lives
+// in CTA `rank` at local index i; warp (i % W) owns it as its slot (i / W).
+//
+//   header  uint4   x: inOff | outOff << 16        (entry offsets inside the rank's edge arrays)
+//                   y: nEmit | nNull << 8 | nOut << 16 | mdl << 24
+//                   z: ctx (2 bits per duplication index) | hasRemoteOut << 16 | pad << 17
+//                   w: reference state index (0xFFFFFFFF for padding)
+//   in-edge uint2   x: padded index g of the source
+//                   y: symbol id | base << 5 | remote << 7      (emit edges first, reference list order)
+//   out-edge u32    bits 0..15 destination's local index | 16..20 bit of the destination's work mask
+//                   (= index of this transition in the destination's in-edge list, 31 = "31 or later")
+//                   | 21..30 destination's rank | 31 destination lives in another CTA
+// ---------------------------------------------------------------------------
+__host__ __device__ inline uint32_t bhInOff(const uint4& h) { return h.x & 0xFFFFu; }
+__host__ __device__ inline uint32_t bhOutOff(const uint4& h) { return h.x >> 16; }
+__host__ __device__ inline uint32_t bhNEmit(const uint4& h) { return h.y & 0xFFu; }
+__host__ __device__ inline uint32_t bhNNull(const uint4& h) { return (h.y >> 8) & 0xFFu; }
+__host__ __device__ inline uint32_t bhNOut(const uint4& h) { return (h.y >> 16) & 0xFFu; }
+__host__ __device__ inline uint32_t bhMdl(const uint4& h) { return (h.y >> 24) & 0x7u; }
+__host__ __device__ inline uint32_t bhCtx(const uint4& h, uint32_t i) { return (h.z >> (2 * i)) & 3u; }
+__host__ __device__ inline uint32_t bhRemoteOut(const uint4& h) { return (h.z >> 16) & 1u; }
+__host__ __device__ inline uint32_t bhPad(const uint4& h) { return (h.z >> 17) & 1u; }
+__host__ __device__ inline uint32_t beSym(const uint2& e) { return e.y & 31u; }
+__host__ __device__ inline uint32_t beBase(const uint2& e) { return (e.y >> 5) & 3u; }
+__host__ __device__ inline uint32_t beRemote(const uint2& e) { return (e.y >> 7) & 1u; }
+__host__ __device__ inline uint32_t boLocal(uint32_t w) { return w & 0xFFFFu; }
+__host__ __device__ inline uint32_t boBit(uint32_t w) { return (w >> 16) & 31u; }
+__host__ __device__ inline uint32_t boRank(uint32_t w) { return (w >> 21) & 0x3FFu; }
+__host__ __device__ inline uint32_t boRemote(uint32_t w) { return w >> 31; }
+
+struct BatchTables {
+  uint32_t nStates, M, T, k, local, nSyms;
+  uint32_t startRank, startLocal, endRank, endLocal;
+  uint32_t maxIn, maxOut;        // largest per-rank edge counts (shared-memory sizing)
+  const uint4* hdr;              // [T*M]
+  const uint2* inEdges;          // all ranks, rank r at rankInOff[r]
+  const uint32_t* outEdges;      // all ranks, rank r at rankOutOff[r]
+  const uint32_t* rankInOff;     // [T+1]
+  const uint32_t* rankOutOff;    // [T+1]
+  const double* tsE;             // [32 syms][4 bases][4 observed] (score+noGap)+sub: traceback association (src/viterbi.cpp:255)
+  double symScore[kMaxSyms];     // log(symProb) per symbol id (0 for id 0)
+  double tsDext[kMaxSyms];       // score+delExtend (src/viterbi.cpp:272)
+  double tsDopen[kMaxSyms];      // score+delOpen   (src/viterbi.cpp:273)
+  double tsT[8];                 // tanDup+len[i]   (src/viterbi.cpp:286)
+  double len[8];
+  double sub[16];
+  double noGap, delOpen, delExtend, delEnd, tanDup;
+};
+
+struct BatchArgs {
+  int64_t nReads;
+  int64_t readBase;              // identity order: slot i of this launch is read readBase + i
+  int64_t nGroups;
+  uint32_t nTeams;
+  int32_t maxLen;                // record stride: every group owns (maxLen+1) columns
+  const uint8_t* packed;         // 2-bit reads
+  const int64_t* byteOff;        // [nReads]
+  const int32_t* readLen;        // [nReads]
+  const int32_t* order;          // optional [nGroups*32]: slot -> read (-1 = empty lane); null = identity
+  uint8_t* pred;                 // [nGroups][maxLen+1][nStates][k+2][32] predecessor records, 1 byte per DP cell, reference state order
+  double* sPub;                  // [nTeams][2][Np][32] published S columns of the last two positions
+  double* s0Next;                // [nTeams][Np][32] S0 of the next column (emission step fused into the record pass)
+  double* tPark;                 // [nTeams][k][Np][32] duplication columns between positions
+  double2* sdPub;                // [nTeams][2][Np][32] (S,D) rows of states with successors in other CTAs (T > 1), by column parity
+  uint32_t* inbox;               // [nTeams][T][warps*32] work masks set by other CTAs (T > 1), laid out [warp][slot], zeroed before the launch
+  unsigned long long* barrier;   // [nTeams][2] team barrier counters, zeroed before every launch
+  double* loglike;               // [nReads] global mode
+  double* partVal;               // [nGroups][T][32] local mode: per-CTA best final S ...
+  uint32_t* partOrig;            //   ... and its reference state (first maximum in reference order)
+  double* cells;                 // optional dump of slot 0 of group 0: [(L+1)][nStates][k+2]
+  unsigned long long* dbg;       // optional [16] counters
+};
+
+struct BatchLayout {
+  uint32_t sd, maskA, maskB, hdr, inE, outE, tsE, sub, ctl, red, total;
+};
+
+__host__ __device__ inline BatchLayout makeBatchLayout(uint32_t M, uint32_t maxIn, uint32_t maxOut, uint32_t warps) {
+  BatchLayout L;
+  uint32_t at = 0;
+  auto take = [&](uint32_t bytes) {
+    const uint32_t here = at;
+    at += (bytes + 15u) & ~15u;
+    return here;
+  };
+  L.sd = take(M * kBatchReads * 16);
+  L.maskA = take(M * 4);
+  L.maskB = take(M * 4);
+  L.hdr = take(M * 16);
+  L.inE = take((maxIn + 1) * 8);
+  L.outE = take((maxOut + 1) * 4);
+  L.tsE = take(32 * 16 * 8);
+  L.sub = take(16 * 8);
+  L.ctl = take(64 * 4);
+  L.red = take(warps * 32 * 12);
+  L.total = at;
+  return L;
+}
+
+// reference-order CSR tables for the traceback over batch-layout records
+struct BatchTraceTables {
+  uint32_t nStates, k, local, T;
+  const uint32_t* emitOff;
+  const uint32_t* emitSrc;
+  const uint8_t* emitSym;
+  const uint32_t* nullOff;
+  const uint32_t* nullSrc;
+  const uint8_t* nullSym;
+  const uint8_t* symChar;
+};
+
+struct BatchTraceArgs {
+  int64_t nSlots;                // nGroups * 32
+  int32_t maxLen;
+  const int32_t* readLen;
+  const int32_t* order;          // slot -> read, or null
+  int64_t nReads;
+  int64_t readBase;
+  const uint8_t* pred;
+  double* loglike;
+  const double* partVal;
+  const uint32_t* partOrig;
+  char* decoded;
+  int32_t decodedStride;
+  int32_t* decodedLen;
+  int32_t* status;
+  int32_t* path;
+  int32_t pathStride;
+  int32_t* pathLen;
+};
+
+cudaError_t queryBatchTeams(const BatchTables& tb, uint32_t warps, uint32_t smemBytes, int* ctasPerSm);
+cudaError_t launchFillBatch(const BatchTables& tb, const BatchArgs& args, uint32_t warps, uint32_t smemBytes,
+                            cudaStream_t stream);
+cudaError_t launchTracebackBatch(const BatchTraceTables& tb, const BatchTraceArgs& args, cudaStream_t stream);
+
+}  // namespace dnab

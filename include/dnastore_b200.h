@@ -126,6 +126,32 @@ int dnab_decoder_configure(dnab_decoder* d, uint32_t cluster_size, uint32_t thre
  * 2 runs of a depth-first order, unsorted, 3 DFS chunks dealt round-robin + sort, 4 DFS runs + sort. */
 int dnab_decoder_configure_ex(dnab_decoder* d, uint32_t block_table_mode, uint32_t partition_mode);
 
+/* Named options (replace the digit-encoded arguments above and every environment hook); set before the first batch.
+ *   "kernel"          0 automatic (read-batched when the machine fits, else one read per cluster), 1 read-batched
+ *                     (viterbi_fill_batch.cu), 2 push closure, one read per cluster (viterbi_fill_push.cu), 3 pull closure
+ *   "team_size"       read-batched kernel: CTAs holding one group of 32 reads (0 = smallest that fits)
+ *   "warps_per_cta"   read-batched kernel: 8, 16 or 32
+ *   "cluster_size", "threads_per_cta", "t_columns" (1 shared / 2 global), "table" (1 shared / 2 global),
+ *   "s_prev" (1 shared / 2 global), "partition" (1 index runs, 2 DFS runs, 3 DFS chunks dealt, 4 DFS runs sorted):
+ *                     one-read-per-cluster kernels, as dnab_decoder_configure / _configure_ex
+ *   "thin_n", "t_recompute", "queue_cap", "deal_chunks", "idle_sleep_ns": schedule knobs of the push kernel (tests)
+ *   "pred_budget_mb"  device memory the predecessor records of one launch may take
+ * Unknown keys return DNAB_EINVAL. */
+int dnab_decoder_set_option(dnab_decoder* d, const char* key, int64_t value);
+
+typedef struct dnab_batch_info {
+  uint32_t enabled;            /* 1: batches run on the read-batched kernel */
+  uint32_t reads_per_group;    /* 32: the reads of a group are the lanes of a warp */
+  uint32_t team_size;          /* CTAs that hold the S and D columns of one group in shared memory */
+  uint32_t states_per_cta;
+  uint32_t warps_per_cta;
+  uint32_t smem_bytes_per_cta;
+  uint32_t n_teams;            /* groups in flight */
+  uint32_t reserved;
+  double cross_cta_transition_fraction; /* transitions whose source and destination live in different CTAs */
+} dnab_batch_info;
+int dnab_decoder_get_batch_info(const dnab_decoder* d, dnab_batch_info* info);
+
 /* Reads are packed 2 bits per base, A,C,G,T = 0..3 (src/kmer.h:11-13, src/fastseq.cpp:9-15),
  * base i of a read in bits 2*(i%4).. of byte i/4; read r starts at byte
  * read_byte_off[r] (a multiple of 16) and has read_len[r] bases. */

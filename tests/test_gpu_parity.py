@@ -22,11 +22,13 @@ def d():
     return dnastore_b200
 
 
-def _check_against_golden(d, case, configure=None):
+def _check_against_golden(d, case, configure=None, options=None):
     compiled = util.compiled_for_case(case)
     dec = d.Decoder(compiled, device=0)
     if configure:
         dec.configure(**configure)
+    for key, value in (options or {}).items():
+        dec.set_option(key, value)
     reads = [r["seq"] for r in case["reads"]]
     out = dec.viterbi(reads, want_path=True)
     for i, r in enumerate(case["reads"]):
@@ -107,17 +109,15 @@ def test_gpu_two_kernels_agree_at_batch_scale(d, workload, n):
     assert sum(s.startswith("^") and s.endswith("$") for s in a["decoded"]) > 0.9 * n
 
 
-@pytest.mark.parametrize("env", [dict(DNAB_THIN_N="0"), dict(DNAB_THIN_N="48"), dict(DNAB_T_RECOMPUTE="0"),
-                                 dict(DNAB_QUEUE_CAP="40"), dict(DNAB_QUEUE_CAP="40", DNAB_THIN_N="100000")])
+@pytest.mark.parametrize("opts", [dict(thin_n=0), dict(thin_n=48), dict(t_recompute=0),
+                                  dict(queue_cap=40), dict(queue_cap=40, thin_n=100000)])
 @pytest.mark.parametrize("name", ["l4c4_global_mixed", "cfg3_global_indels", "cfg4_global_dels", "cfg2_global_subs"])
-def test_gpu_push_kernel_tuning_knobs_same_bits(d, name, env, monkeypatch):
+def test_gpu_push_kernel_tuning_knobs_same_bits(d, name, opts):
     """How a level's work list is made (bitmap scan, or appended by the previous level's pushers below a size
     threshold -- including a threshold so large that the small append queues overflow), stored (not re-derived)
     duplication cells and a scan queue far smaller than the frontier are schedule / placement choices of the
     push kernel: no bit may change."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    _check_against_golden(d, util.golden_case(name))
+    _check_against_golden(d, util.golden_case(name), options=dict(kernel=2, **opts))
 
 
 @pytest.mark.parametrize("threads", [32, 96, 256, 1024])
