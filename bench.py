@@ -272,6 +272,7 @@ def main():
     ap.add_argument("--tmode", type=int, default=0)
     ap.add_argument("--table-mode", type=int, default=0)
     ap.add_argument("--partition", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="decoder option key=value (dnab_decoder_set_option), repeatable")
     ap.add_argument("--cpu-sample", type=int, default=4, help="reads in the single-core CPU baseline sample (0 = skip)")
     ap.add_argument("--no-indel", action="store_true", help="decode with --error-del-open 0 --error-dup-prob 0 (closure degenerates)")
     ap.add_argument("--mode", default="viterbi", choices=["viterbi", "fwdback"],
@@ -338,9 +339,13 @@ def main():
     dec = d.Decoder(compiled, device=local_rank)
     if args.cluster or args.threads or args.tmode or args.table_mode or args.partition:
         dec.configure(args.cluster, args.threads, args.tmode, args.table_mode, args.partition)
+    for kv in args.opt:
+        key, value = kv.split("=")
+        dec.set_option(key, int(value))
     if args.mode == "fwdback":
         return bench_fwdback(args, w, compiled, dec, rank, local_rank, world, dev, dist, torch, d, util)
-    info = dec.info()
+    binfo = dec.batch_info()
+    info = dec.info() if not binfo["enabled"] else None
     default_rps = {"cfg2": 960, "cfg1": 65536, "cfg3": 4096, "cfg4": 8192, "cfg5": 4096}[args.workload]
     rps = args.reads_per_step or default_rps
 
@@ -452,7 +457,8 @@ def main():
         algo_bytes = my_cells + sum(int(np.sum((batches[b][3].astype(np.int64) + 3) // 4)) for b in range(args.warmup, n_batches)) \
             + int(dec_len_last.sum()) * args.steps + 8 * my_reads
         achieved = algo_bytes / (st["timed_fill_ms"] * 1e-3) / 1e9
-        fill_kernel = "viterbiFillKernel" if args.partition >= 10 else "viterbiFillPushKernel"
+        fill_kernel = ("viterbiFillBatchKernel" if binfo["enabled"] else
+                       "viterbiFillKernel" if args.partition >= 10 else "viterbiFillPushKernel")
         # DRAM traffic of one launch: measured once with `ncu --set full` (profiles/), scaled to this launch
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "r01_fill_traffic.json")
@@ -478,9 +484,17 @@ def main():
             reads_per_sec=tot_reads / (elapsed_ms * 1e-3),
             config=dict(workload=f"{args.workload}: {w['desc']}, --error-global, -l {w['length']}",
                         reads_per_step_per_gpu=rps, n_states=int(t.n_states), k=int(t.k),
-                        cluster_size=info["cluster_size"], states_per_cta=info["states_per_cta"],
-                        threads_per_cta=info["threads_per_cta"], smem_bytes_per_cta=info["smem_bytes_per_cta"],
-                        t_in_smem=info["t_in_smem"], table_in_smem=info["table_in_smem"], reads_in_flight=info["n_clusters"],
+                        **(dict(kernel="read-batched (viterbi_fill_batch.cu): 32 reads per group are the SIMD lanes",
+                                team_size=binfo["team_size"], states_per_cta=binfo["states_per_cta"],
+                                threads_per_cta=32 * binfo["warps_per_cta"], smem_bytes_per_cta=binfo["smem_bytes_per_cta"],
+                                reads_in_flight=32 * binfo["n_teams"],
+                                cross_cta_transition_fraction=round(binfo["cross_cta_transition_fraction"], 4))
+                           if binfo["enabled"] else
+                           dict(kernel="one read per cluster (viterbi_fill_push.cu)",
+                                cluster_size=info["cluster_size"], states_per_cta=info["states_per_cta"],
+                                threads_per_cta=info["threads_per_cta"], smem_bytes_per_cta=info["smem_bytes_per_cta"],
+                                t_in_smem=info["t_in_smem"], table_in_smem=info["table_in_smem"],
+                                reads_in_flight=info["n_clusters"])),
                         l2="working set >> L2: every step streams reads_per_step x ~37 MB of predecessor records "
                            "and uses a distinct read batch" if args.workload == "cfg2" else
                            "distinct read batch per step; predecessor-record stream exceeds L2",

@@ -121,9 +121,9 @@ struct dnab_decoder {
   BatchTraceTables btrace{};
   DevBuf<uint4> dbHdr;
   DevBuf<uint2> dbIn;
-  DevBuf<uint32_t> dbOut, dbRankInOff, dbRankOutOff, dbEmitOff, dbEmitSrc, dbNullOff, dbNullSrc, dbInbox, dbPartOrig;
+  DevBuf<uint32_t> dbOut, dbRankInOff, dbRankOutOff, dbRemoteIn, dbEmitOff, dbEmitSrc, dbNullOff, dbNullSrc, dbTeamState, dbTeamPassive, dbPartOrig;
   DevBuf<uint8_t> dbEmitSym, dbNullSym;
-  DevBuf<double> dbTsE, dbSPub, dbS0Next, dbTPark, dbPartVal;
+  DevBuf<double> dbTsE, dbPriv, dbPartVal;
   DevBuf<double2> dbSdPub;
   DevBuf<unsigned long long> dbBarrier;
   DevBuf<int32_t> dbOrder;
@@ -693,7 +693,7 @@ static int buildBatchPlan(dnab_decoder* d) {
   bp.ready = true;
   bp.feasible = false;
   const uint32_t N = d->nStates, k = d->k;
-  const uint32_t W = d->wantWarps ? (d->wantWarps > 16 ? 32u : d->wantWarps > 8 ? 16u : 8u) : 32u;
+  const uint32_t W = d->wantWarps ? (d->wantWarps > 24 ? 32u : d->wantWarps > 16 ? 24u : 16u) : 32u;
   auto nEmitOf = [&](uint32_t s) { return d->emitOff[s + 1] - d->emitOff[s]; };
   auto nNullOf = [&](uint32_t s) { return d->nullOff[s + 1] - d->nullOff[s]; };
   for (uint32_t s = 0; s < N; ++s) {
@@ -721,20 +721,14 @@ static int buildBatchPlan(dnab_decoder* d) {
   const std::vector<uint32_t> dfs = dfsOrder(d);
   const uint32_t maxTeam = (uint32_t)d->smCount;
   uint32_t T0 = std::max<uint32_t>(1, (uint32_t)(((size_t)N * kBatchReads * 16 + d->smemOptin - 1) / d->smemOptin));
-  if (d->wantTeam) T0 = d->wantTeam;
   std::vector<uint4> hdr;
   std::vector<uint2> inE;
-  std::vector<uint32_t> outE, rankInOff, rankOutOff, newOf(N), origOf;
-  for (uint32_t T = T0; T <= maxTeam; ++T) {
+  std::vector<uint32_t> outE, rankInOff, rankOutOff, newOf(N), origOf, remoteIn;
+  // builds the tables of a team of T CTAs; false when T is infeasible
+  auto tryTeam = [&](uint32_t T) -> bool {
     const uint32_t M = (N + T - 1) / T, Np = T * M;
-    if (M > kBatchMaxSlots * W || M > 65535 || T > 1023) {
-      if (d->wantTeam) break;
-      continue;
-    }
-    if (makeBatchLayout(M, 0, 0, W).total > d->smemOptin) {
-      if (d->wantTeam) break;
-      continue;
-    }
+    if (M > kBatchMaxSlots * W || M > 65535 || T > 1023) return false;
+    if (makeBatchLayout(M, 0, 0, W, T > 1).total > d->smemOptin) return false;
     // CTA assignment: balanced runs of a depth-first order (T > 1); inside a CTA descending in-degree, dealt to the warps
     origOf.assign(Np, 0xFFFFFFFFu);
     for (uint32_t r = 0; r < T; ++r) {
@@ -749,60 +743,63 @@ static int buildBatchPlan(dnab_decoder* d) {
       }
     }
     hdr.assign(Np, make_uint4(0, 0, 1u << 17, 0xFFFFFFFFu));
+    remoteIn.assign(Np, 0);
     inE.clear();
     outE.clear();
     rankInOff.assign(T + 1, 0);
     rankOutOff.assign(T + 1, 0);
     uint32_t maxIn = 0, maxOut = 0;
     uint64_t cross = 0, total = 0;
-    bool ok = true;
-    for (uint32_t r = 0; r < T && ok; ++r) {
+    for (uint32_t r = 0; r < T; ++r) {
       rankInOff[r] = (uint32_t)inE.size();
       rankOutOff[r] = (uint32_t)outE.size();
       for (uint32_t i = 0; i < M; ++i) {
         const uint32_t s = origOf[r * M + i];
         if (s == 0xFFFFFFFFu) continue;
         const uint32_t inOff = (uint32_t)inE.size() - rankInOff[r], outOff = (uint32_t)outE.size() - rankOutOff[r];
-        if (inOff > 65535 || outOff > 65535) {
-          ok = false;
-          break;
-        }
+        if (inOff > 65535 || outOff > 65535) return false;
         const uint32_t nE = nEmitOf(s), nN = nNullOf(s);
+        uint32_t jIn = 0;
         auto pushIn = [&](uint32_t src, uint32_t sym, uint32_t base) {
           const uint32_t sg = newOf[src];
           const bool remote = sg / M != r;
           inE.push_back(make_uint2(sg, sym | (base << 5) | (remote ? 1u << 7 : 0u)));
+          if (remote) remoteIn[r * M + i] |= 1u << std::min(jIn, 31u);
+          ++jIn;
           ++total;
           cross += remote;
         };
         for (uint32_t e = d->emitOff[s]; e < d->emitOff[s + 1]; ++e) pushIn(d->emitSrc[e], d->emitSym[e], d->emitBase[e]);
         for (uint32_t e = d->nullOff[s]; e < d->nullOff[s + 1]; ++e) pushIn(d->nullSrc[e], d->nullSym[e], 0);
         bool remoteOut = (d->local && s == 0 && T > 1);  // local mode: every CTA reads S(start,0) for the (0,0) escape
-        for (const auto& o : outs[s]) {
+        uint32_t nLocal = 0;
+        std::vector<uint32_t> remoteCtas;
+        for (const auto& o : outs[s]) {  // successors in this CTA first, then the other CTAs that own successors
           const uint32_t dg = newOf[o.first];
-          const bool remote = dg / M != r;
-          remoteOut |= remote;
-          outE.push_back((dg % M) | (o.second << 16) | ((dg / M) << 21) | (remote ? 1u << 31 : 0u));
+          if (dg / M != r) {
+            remoteOut = true;
+            remoteCtas.push_back(dg / M);
+            continue;
+          }
+          ++nLocal;
+          outE.push_back((dg % M) | (o.second << 16));
         }
+        std::sort(remoteCtas.begin(), remoteCtas.end());
+        remoteCtas.erase(std::unique(remoteCtas.begin(), remoteCtas.end()), remoteCtas.end());
+        outE.insert(outE.end(), remoteCtas.begin(), remoteCtas.end());
+        const uint32_t nOutEntries = nLocal + (uint32_t)remoteCtas.size();
         uint32_t ctxBits = 0;
         for (uint32_t t = 0; t < d->mdl[s]; ++t) ctxBits |= (uint32_t)(d->ctx[(size_t)s * k + t] & 3u) << (2 * t);
-        hdr[r * M + i] = make_uint4(inOff | (outOff << 16), nE | (nN << 8) | ((uint32_t)outs[s].size() << 16) | ((uint32_t)d->mdl[s] << 24),
-                                    ctxBits | (remoteOut ? 1u << 16 : 0u), s);
+        hdr[r * M + i] = make_uint4(inOff | (outOff << 16), nE | (nN << 8) | (nOutEntries << 16) | ((uint32_t)d->mdl[s] << 24),
+                                    ctxBits | (remoteOut ? 1u << 16 : 0u) | (nLocal << 18), s);
       }
       maxIn = std::max(maxIn, (uint32_t)inE.size() - rankInOff[r]);
       maxOut = std::max(maxOut, (uint32_t)outE.size() - rankOutOff[r]);
     }
     rankInOff[T] = (uint32_t)inE.size();
     rankOutOff[T] = (uint32_t)outE.size();
-    if (!ok) {
-      if (d->wantTeam) break;
-      continue;
-    }
-    const uint32_t smem = makeBatchLayout(M, maxIn, maxOut, W).total;
-    if (smem > d->smemOptin) {
-      if (d->wantTeam) break;
-      continue;
-    }
+    const uint32_t smem = makeBatchLayout(M, maxIn, maxOut, W, T > 1).total;
+    if (smem > d->smemOptin) return false;
     bp.T = T;
     bp.M = M;
     bp.warps = W;
@@ -822,8 +819,20 @@ static int buildBatchPlan(dnab_decoder* d) {
     t.endLocal = newOf[N - 1] % M;
     t.maxIn = maxIn;
     t.maxOut = maxOut;
-    bp.feasible = true;
-    break;
+    return true;
+  };
+  if (d->wantTeam)
+    bp.feasible = tryTeam(d->wantTeam);
+  else {
+    uint32_t Tmin = 0;
+    for (uint32_t T = T0; T <= maxTeam && !Tmin; ++T)
+      if (tryTeam(T)) Tmin = T;
+    if (Tmin) {
+      bp.feasible = true;
+      // the teams that fit at once get all the SMs: fewer states per CTA, the same reads in flight
+      const uint32_t spread = maxTeam / (maxTeam / Tmin);
+      if (spread > Tmin && !tryTeam(spread)) bp.feasible = tryTeam(Tmin);
+    }
   }
   if (!bp.feasible) {
     setLastError("the read-batched kernel cannot take this machine: " + std::to_string(N) +
@@ -838,6 +847,7 @@ static int buildBatchPlan(dnab_decoder* d) {
   CUDA_TRY(d->dbOut.upload(outE));
   CUDA_TRY(d->dbRankInOff.upload(rankInOff));
   CUDA_TRY(d->dbRankOutOff.upload(rankOutOff));
+  CUDA_TRY(d->dbRemoteIn.upload(remoteIn));
   // score tables with the traceback's association, formed once on the host in IEEE fp64 (-ffp-contract=off)
   std::vector<double> tsE(32 * 16, 0.);
   for (uint32_t sym = 0; sym < d->symScore.size(); ++sym)
@@ -852,6 +862,7 @@ static int buildBatchPlan(dnab_decoder* d) {
   t.outEdges = d->dbOut.p;
   t.rankInOff = d->dbRankInOff.p;
   t.rankOutOff = d->dbRankOutOff.p;
+  t.remoteIn = d->dbRemoteIn.p;
   t.tsE = d->dbTsE.p;
   for (int i = 0; i < kMaxSyms; ++i) {
     const double sc = i < (int)d->symScore.size() ? d->symScore[i] : 0.;
@@ -904,12 +915,11 @@ static int buildBatchPlan(dnab_decoder* d) {
     return DNAB_EINVAL;
   }
   const size_t Np = (size_t)bp.T * bp.M;
-  CUDA_TRY(d->dbSPub.ensure((size_t)bp.nTeams * 2 * Np * 32));
-  CUDA_TRY(d->dbS0Next.ensure((size_t)bp.nTeams * Np * 32));
-  CUDA_TRY(d->dbTPark.ensure(std::max<size_t>(1, (size_t)bp.nTeams * k * Np * 32)));
+  CUDA_TRY(d->dbPriv.ensure((size_t)bp.nTeams * Np * (2 + k) * 32));
   CUDA_TRY(d->dbSdPub.ensure(bp.T > 1 ? (size_t)bp.nTeams * 2 * Np * 32 : 1));
-  CUDA_TRY(d->dbInbox.ensure((size_t)bp.nTeams * bp.T * bp.warps * 32));
-  CUDA_TRY(d->dbBarrier.ensure((size_t)bp.nTeams * 2));
+  CUDA_TRY(d->dbTeamState.ensure((size_t)bp.nTeams * bp.T));
+  CUDA_TRY(d->dbTeamPassive.ensure((size_t)bp.nTeams * 2));
+  CUDA_TRY(d->dbBarrier.ensure((size_t)bp.nTeams));
   return DNAB_OK;
 }
 
@@ -953,11 +963,10 @@ static int runDeviceBatch(dnab_decoder* d, int64_t nReads, int32_t maxLen, const
     a.readLen = dReadLen;
     a.order = dOrder ? dOrder + at * 32 : nullptr;
     a.pred = d->dPred.p;
-    a.sPub = d->dbSPub.p;
-    a.s0Next = d->dbS0Next.p;
-    a.tPark = d->dbTPark.p;
+    a.priv = d->dbPriv.p;
     a.sdPub = d->dbSdPub.p;
-    a.inbox = d->dbInbox.p;
+    a.teamState = d->dbTeamState.p;
+    a.teamPassive = d->dbTeamPassive.p;
     a.barrier = d->dbBarrier.p;
     a.loglike = dLoglike;
     a.partVal = d->dbPartVal.p;
@@ -979,7 +988,8 @@ static int runDeviceBatch(dnab_decoder* d, int64_t nReads, int32_t maxLen, const
     }
     const bool rec = timeIt || pooled;
     if (bp.T > 1) {
-      CUDA_TRY(cudaMemsetAsync(d->dbInbox.p, 0, d->dbInbox.n * sizeof(uint32_t), stream));
+      CUDA_TRY(cudaMemsetAsync(d->dbTeamState.p, 0, d->dbTeamState.n * sizeof(uint32_t), stream));
+      CUDA_TRY(cudaMemsetAsync(d->dbTeamPassive.p, 0, d->dbTeamPassive.n * sizeof(uint32_t), stream));
       CUDA_TRY(cudaMemsetAsync(d->dbBarrier.p, 0, d->dbBarrier.n * sizeof(unsigned long long), stream));
     }
     if (rec) CUDA_TRY(cudaEventRecord(e0, stream));

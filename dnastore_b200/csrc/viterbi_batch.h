@@ -27,13 +27,15 @@ constexpr uint32_t kBatchAllEdges = 0xFFFFFFFFu;
 //
 //   header  uint4   x: inOff | outOff << 16        (entry offsets inside the rank's edge arrays)
 //                   y: nEmit | nNull << 8 | nOut << 16 | mdl << 24
-//                   z: ctx (2 bits per duplication index) | hasRemoteOut << 16 | pad << 17
+//                   z: ctx (2 bits per duplication index) | hasRemoteOut << 16 | pad << 17 | nOutLocal << 18
+//                      (successors in this CTA come first in the out-edge list)
 //                   w: reference state index (0xFFFFFFFF for padding)
 //   in-edge uint2   x: padded index g of the source
 //                   y: symbol id | base << 5 | remote << 7      (emit edges first, reference list order)
-//   out-edge u32    bits 0..15 destination's local index | 16..20 bit of the destination's work mask
-//                   (= index of this transition in the destination's in-edge list, 31 = "31 or later")
-//                   | 21..30 destination's rank | 31 destination lives in another CTA
+//   out-edge u32    successors in this CTA: bits 0..15 destination's local index | 16..20 bit of the destination's
+//                   work mask (= index of this transition in the destination's in-edge list, 31 = "31 or later");
+//                   then one entry per OTHER CTA that owns a successor: its rank (the CTA is notified, not the state)
+//   remoteIn u32    per state: the bits of its work mask whose transitions come from other CTAs
 // ---------------------------------------------------------------------------
 __host__ __device__ inline uint32_t bhInOff(const uint4& h) { return h.x & 0xFFFFu; }
 __host__ __device__ inline uint32_t bhOutOff(const uint4& h) { return h.x >> 16; }
@@ -44,6 +46,7 @@ __host__ __device__ inline uint32_t bhMdl(const uint4& h) { return (h.y >> 24) &
 __host__ __device__ inline uint32_t bhCtx(const uint4& h, uint32_t i) { return (h.z >> (2 * i)) & 3u; }
 __host__ __device__ inline uint32_t bhRemoteOut(const uint4& h) { return (h.z >> 16) & 1u; }
 __host__ __device__ inline uint32_t bhPad(const uint4& h) { return (h.z >> 17) & 1u; }
+__host__ __device__ inline uint32_t bhNOutLocal(const uint4& h) { return (h.z >> 18) & 0xFFu; }
 __host__ __device__ inline uint32_t beSym(const uint2& e) { return e.y & 31u; }
 __host__ __device__ inline uint32_t beBase(const uint2& e) { return (e.y >> 5) & 3u; }
 __host__ __device__ inline uint32_t beRemote(const uint2& e) { return (e.y >> 7) & 1u; }
@@ -61,6 +64,7 @@ struct BatchTables {
   const uint32_t* outEdges;      // all ranks, rank r at rankOutOff[r]
   const uint32_t* rankInOff;     // [T+1]
   const uint32_t* rankOutOff;    // [T+1]
+  const uint32_t* remoteIn;      // [T*M]
   const double* tsE;             // [32 syms][4 bases][4 observed] (score+noGap)+sub: traceback association (src/viterbi.cpp:255)
   double symScore[kMaxSyms];     // log(symProb) per symbol id (0 for id 0)
   double tsDext[kMaxSyms];       // score+delExtend (src/viterbi.cpp:272)
@@ -82,12 +86,13 @@ struct BatchArgs {
   const int32_t* readLen;        // [nReads]
   const int32_t* order;          // optional [nGroups*32]: slot -> read (-1 = empty lane); null = identity
   uint8_t* pred;                 // [nGroups][maxLen+1][nStates][k+2][32] predecessor records, 1 byte per DP cell, reference state order
-  double* sPub;                  // [nTeams][2][Np][32] published S columns of the last two positions
-  double* s0Next;                // [nTeams][Np][32] S0 of the next column (emission step fused into the record pass)
-  double* tPark;                 // [nTeams][k][Np][32] duplication columns between positions
+  double* priv;                  // [nTeams][Np][2+k][32] rows private to the owning lane, carried from one column to the next:
+                                 //   S0 of the next column (emission step fused into the record pass), the best emit candidate of
+                                 //   its S record (traceback association), the k parked duplication cells
   double2* sdPub;                // [nTeams][2][Np][32] (S,D) rows of states with successors in other CTAs (T > 1), by column parity
-  uint32_t* inbox;               // [nTeams][T][warps*32] work masks set by other CTAs (T > 1), laid out [warp][slot], zeroed before the launch
-  unsigned long long* barrier;   // [nTeams][2] team barrier counters, zeroed before every launch
+  uint32_t* teamState;           // [nTeams][T] per CTA: 1 passive | 2 notified (T > 1), zeroed before every launch
+  uint32_t* teamPassive;         // [nTeams][2] passive CTAs of the current column, by column parity, zeroed before every launch
+  unsigned long long* barrier;   // [nTeams] team barrier counters (monotonic), zeroed before every launch
   double* loglike;               // [nReads] global mode
   double* partVal;               // [nGroups][T][32] local mode: per-CTA best final S ...
   uint32_t* partOrig;            //   ... and its reference state (first maximum in reference order)
@@ -96,10 +101,10 @@ struct BatchArgs {
 };
 
 struct BatchLayout {
-  uint32_t sd, maskA, maskB, hdr, inE, outE, tsE, sub, ctl, red, total;
+  uint32_t sd, maskA, maskB, remIn, hdr, inE, outE, tsE, sub, ctl, red, total;
 };
 
-__host__ __device__ inline BatchLayout makeBatchLayout(uint32_t M, uint32_t maxIn, uint32_t maxOut, uint32_t warps) {
+__host__ __device__ inline BatchLayout makeBatchLayout(uint32_t M, uint32_t maxIn, uint32_t maxOut, uint32_t warps, bool team) {
   BatchLayout L;
   uint32_t at = 0;
   auto take = [&](uint32_t bytes) {
@@ -110,6 +115,7 @@ __host__ __device__ inline BatchLayout makeBatchLayout(uint32_t M, uint32_t maxI
   L.sd = take(M * kBatchReads * 16);
   L.maskA = take(M * 4);
   L.maskB = take(M * 4);
+  L.remIn = team ? take(M * 4) : 0;
   L.hdr = take(M * 16);
   L.inE = take((maxIn + 1) * 8);
   L.outE = take((maxOut + 1) * 4);

@@ -61,12 +61,6 @@ __device__ __forceinline__ double2 ldPub2(const double2* p) {
 __device__ __forceinline__ void stPub2(double2* p, double s, double d) {
   asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(s), "d"(d) : "memory");
 }
-__device__ __forceinline__ double ldCg(const double* p) {
-  double v;
-  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void stCg(double* p, double v) { asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 // predecessor records are written once and read by another kernel: streaming stores
 __device__ __forceinline__ void stRecord(uint8_t* p, uint32_t v) {
   asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -82,25 +76,35 @@ __device__ __forceinline__ unsigned long long ldAcquire64(const unsigned long lo
   return v;
 }
 
-enum : uint32_t { kCtlFlag = 0, kCtlAny = 4, kCtlSent = 5 };
+enum : uint32_t { kCtlFlag = 0, kCtlWake = 4, kCtlDecision = 8 };
+constexpr uint32_t kKeepRecord = 0x100u;  // "the S record written by the previous column's pass stands"
+constexpr uint32_t kPassive = 1u, kNotified = 2u;  // team state word of a CTA
+
+__device__ __forceinline__ void fenceRelease() { asm volatile("fence.release.gpu;" ::: "memory"); }
+__device__ __forceinline__ void stRecordEarly(uint8_t* p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void stRelaxed32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 }  // namespace
 
-template <int W, bool kDebug>
+// W warps per CTA; KMAX >= k duplication columns unrolled; kTeam: the group's states are spread over T > 1 CTAs.
+template <int W, int KMAX, bool kTeam, bool kDebug>
 __global__ void __launch_bounds__(W * 32, 1)
     viterbiFillBatchKernel(const __grid_constant__ BatchTables tb, const __grid_constant__ BatchArgs args) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr uint32_t nThreads = W * 32;
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t T = tb.T, M = tb.M, k = tb.k, Np = T * M, N = tb.nStates, K2 = k + 2;
-  const uint32_t team = blockIdx.x / T, rank = blockIdx.x - team * T;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, lane16 = lane * 16u;
+  const uint32_t T = kTeam ? tb.T : 1u, M = tb.M, k = tb.k, Np = T * M, N = tb.nStates, K2 = k + 2;
+  const uint32_t team = kTeam ? blockIdx.x / T : blockIdx.x, rank = kTeam ? blockIdx.x - team * T : 0u;
   const uint32_t nSlots = (M + W - 1) / W;
   const double NEG = negInf();
-  const BatchLayout lay = makeBatchLayout(M, tb.maxIn, tb.maxOut, W);
+  const BatchLayout lay = makeBatchLayout(M, tb.maxIn, tb.maxOut, W, kTeam);
 
   const uint32_t aSD = smemAddr(smem + lay.sd);
   uint32_t* maskCur = reinterpret_cast<uint32_t*>(smem + lay.maskA);
   uint32_t* maskNext = reinterpret_cast<uint32_t*>(smem + lay.maskB);
+  uint32_t* remInS = reinterpret_cast<uint32_t*>(smem + lay.remIn);
   uint4* hdrS = reinterpret_cast<uint4*>(smem + lay.hdr);
   uint2* inS = reinterpret_cast<uint2*>(smem + lay.inE);
   uint32_t* outS = reinterpret_cast<uint32_t*>(smem + lay.outE);
@@ -110,15 +114,20 @@ __global__ void __launch_bounds__(W * 32, 1)
   double* redV = reinterpret_cast<double*>(smem + lay.red);
   uint32_t* redO = reinterpret_cast<uint32_t*>(smem + lay.red + W * 32 * 8);
 
-  // ---- the CTA's slice of the tables, resident for the whole launch ----
+  // ---- the CTA's slice of the tables, resident for the whole launch; local sources become row addresses ----
   {
     for (uint32_t i = tid; i < M; i += nThreads) {
       hdrS[i] = tb.hdr[rank * M + i];
+      if (kTeam) remInS[i] = tb.remoteIn[rank * M + i];
       maskCur[i] = 0;
       maskNext[i] = 0;
     }
     const uint32_t inBase = tb.rankInOff[rank], nIn = tb.rankInOff[rank + 1] - inBase;
-    for (uint32_t i = tid; i < nIn; i += nThreads) inS[i] = tb.inEdges[inBase + i];
+    for (uint32_t i = tid; i < nIn; i += nThreads) {
+      uint2 e = tb.inEdges[inBase + i];
+      if (!beRemote(e)) e.x = aSD + (e.x - rank * M) * 512u;
+      inS[i] = e;
+    }
     const uint32_t outBase = tb.rankOutOff[rank], nOut = tb.rankOutOff[rank + 1] - outBase;
     for (uint32_t i = tid; i < nOut; i += nThreads) outS[i] = tb.outEdges[outBase + i];
     for (uint32_t i = tid; i < 512; i += nThreads) tsE[i] = tb.tsE[i];
@@ -127,50 +136,31 @@ __global__ void __launch_bounds__(W * 32, 1)
   }
   __syncthreads();
 
-  double* const sPubT = args.sPub + (size_t)team * 2 * Np * 32;
-  double* const s0T = args.s0Next + (size_t)team * Np * 32;
-  double* const tParkT = args.tPark + (size_t)team * k * Np * 32;
+  // per-state rows private to the owning lane, interleaved: [state][s0 | best emit candidate | k parked T cells][32]
+  const uint32_t privKinds = 2 + k;
+  double* const privT = args.priv + (size_t)team * Np * privKinds * 32 + lane;
   double2* const sdPubT = args.sdPub + (size_t)team * 2 * Np * 32;  // two parities of the column
-  uint32_t* const inboxT = args.inbox + (size_t)team * T * (W * 32);
-  unsigned long long* const bar = args.barrier + (size_t)team * 2;
-  uint32_t barGen = 0, barHigh0 = 0, barHigh1 = 0;
-  bool sentRemote = false;
+  uint32_t* const stateT = args.teamState + (size_t)team * T;  // per CTA: kPassive | kNotified
+  uint32_t* const passiveT = args.teamPassive + (size_t)team * 2;  // passive CTAs of the current column, by parity
+  unsigned long long* const bar = args.barrier + team;
+  unsigned long long barTarget = 0;
+  uint32_t col = 0;
 
-  // Team barrier (T > 1): CTA barrier, one arrival per CTA on an L2 counter (two alternating counters; the high
-  // half counts the CTAs that flagged a remote bit since the last meeting), CTA barrier.  Returns "anybody sent".
-  auto teamBarrier = [&]() -> bool {
-    if (T == 1) {
-      __syncthreads();
-      return false;
-    }
-    const int mine = __syncthreads_or(sentRemote ? 1 : 0);
-    sentRemote = false;
+  // Team barrier: CTA barrier, one arrival per CTA on a monotonic L2 counter, CTA barrier.
+  auto teamBarrier = [&]() {
+    __syncthreads();
+    if (!kTeam) return;
+    barTarget += T;
     if (tid == 0) {
-      unsigned long long* c = bar + (barGen & 1u);
-      __threadfence();
-      atomicAdd(c, 1ull + (mine ? (1ull << 32) : 0ull));
-      const uint32_t target = (barGen / 2 + 1) * T;
-      unsigned long long v;
-      while ((uint32_t)((v = ldAcquire64(c)) & 0xFFFFFFFFull) < target) {
+      fenceRelease();
+      atomicAdd(bar, 1ull);
+      while (ldAcquire64(bar) < barTarget) {
       }
-      const uint32_t high = (uint32_t)(v >> 32);
-      const uint32_t prev = (barGen & 1u) ? barHigh1 : barHigh0;
-      ctl[kCtlAny] = high != prev ? 1u : 0u;
-      ctl[kCtlSent] = high;
     }
     __syncthreads();
-    const uint32_t high = ctl[kCtlSent];
-    if (barGen & 1u)
-      barHigh1 = high;
-    else
-      barHigh0 = high;
-    ++barGen;
-    const bool any = ctl[kCtlAny] != 0;
-    __syncthreads();  // ctl is rewritten by the next meeting
-    return any;
   };
 
-  unsigned long long dbgLevels = 0, dbgVisits = 0, dbgEdges = 0, dbgRounds = 0, dbgClosure = 0, dbgRecord = 0;
+  unsigned long long dbgLevels = 0, dbgVisits = 0, dbgEdges = 0, dbgWakes = 0, dbgClosure = 0, dbgRecord = 0, dbgPassive = 0;
 
   for (int64_t group = team; group < args.nGroups; group += args.nTeams) {
     const int64_t slotIdx = group * 32 + lane;
@@ -185,158 +175,208 @@ __global__ void __launch_bounds__(W * 32, 1)
     for (int sh = 16; sh > 0; sh >>= 1) Lmax = max(Lmax, __shfl_xor_sync(0xFFFFFFFFu, Lmax, sh));
     uint8_t* const predG = args.pred + (size_t)group * (size_t)(args.maxLen + 1) * N * K2 * 32;
     unsigned long long win = 0;
-    uint32_t x = 0, xNext = 0;
+    uint32_t xNext = 0;
 
     for (int32_t pos = 0; pos <= Lmax; ++pos) {
       const bool act = pos <= L;
-      x = xNext;  // observed base pos-1
-      if (pos < L) {
+      if (pos < L) {  // observed base pos: the next column's emission
         if ((pos & 31) == 0) win = *reinterpret_cast<const unsigned long long*>(seq + (size_t)(pos >> 5) * 8);
         xNext = (uint32_t)(win >> (2 * (pos & 31))) & 3u;
       }
-      const uint32_t par = (uint32_t)pos & 1u;
+      const uint32_t par = col & 1u;  // columns are numbered across groups: the parity alternates without a break
+      ++col;
       double2* const sdPubCol = sdPubT + (size_t)par * Np * 32;
+      double2* const sdPubNext = sdPubT + (size_t)(par ^ 1u) * Np * 32;
+      uint32_t* const passiveCol = passiveT + par;
 
       // ---- (1) the column starts from the emission step's result (fused into the previous column's
       //          record pass): S = S0, D = -inf (src/viterbi.cpp:66,75-79,92-106) ----
+#pragma unroll 4
       for (uint32_t sl = 0; sl < nSlots; ++sl) {
         const uint32_t d = sl * W + warp;
-        if (d >= M) break;
-        const uint4 h = hdrS[d];
-        const uint32_t g = rank * M + d;
-        double s0;
-        if (pos == 0)
-          s0 = (!bhPad(h) && (tb.local || (rank == tb.startRank && d == tb.startLocal))) ? 0.0 : NEG;
-        else
-          s0 = s0T[(size_t)g * 32 + lane];
-        stsRow(aSD + (d * 32 + lane) * 16, s0, NEG);
-        if (T > 1 && bhRemoteOut(h)) stPub2(sdPubCol + (size_t)g * 32 + lane, s0, NEG);
+        if (d < M) {
+          double s0;
+          if (pos == 0) {
+            const uint4 h = hdrS[d];
+            s0 = (!bhPad(h) && (tb.local || (rank == tb.startRank && d == tb.startLocal))) ? 0.0 : NEG;
+            if (kTeam && bhRemoteOut(h)) stPub2(sdPubCol + (size_t)(rank * M + d) * 32 + lane, s0, NEG);
+          } else
+            s0 = privT[(size_t)(rank * M + d) * privKinds * 32];
+          stsRow(aSD + d * 512u + lane16, s0, NEG);
+        }
       }
-      if (tid < 3) ctl[kCtlFlag + tid] = 0;
+      if (tid < 8) ctl[tid] = 0;
+      if (kTeam && tid == 0) stRelaxed32(stateT + rank, 0u);  // active, not notified
       teamBarrier();
+      if (kTeam && rank == 0 && tid == 0) stRelaxed32(passiveT + (par ^ 1u), 0u);  // the other parity's count is dead: reset it for the next column
       unsigned long long stamp = 0;
       if (kDebug) stamp = clock64();
 
       // ---- (2) closure (src/viterbi.cpp:97-99,110-159), owner-computes edge relaxation ----
-      // relaxes the flagged in-transitions of state d; when a lane grew: stores the row, publishes it if some
-      // successor lives in another CTA, flags the successors' masks.  Returns "grew" (warp-uniform).
-      auto relax = [&](uint32_t d, uint32_t m) -> bool {
+      uint32_t remotePending = 0;  // slots of this warp that grew and have successors in other CTAs
+      // relaxes the flagged in-transitions of state d (all of them when `allIn` or when there are few); when a lane
+      // grew: stores the row, publishes it if some successor lives in another CTA, flags the local successors' masks.
+      auto relax = [&](uint32_t sl, uint32_t m, bool allIn) -> bool {
+        const uint32_t d = sl * W + warp;
         const uint4 h = hdrS[d];
         const uint32_t inOff = bhInOff(h), nE = bhNEmit(h), nIn = nE + bhNNull(h);
-        const uint32_t aOwn = aSD + (d * 32 + lane) * 16;
+        const uint32_t aOwn = aSD + d * 512u + lane16;
         const double2 own = ldsRow(aOwn);
         double s = own.x, dd = own.y;
-        auto edge = [&](uint32_t j) {
+        auto rowOf = [&](const uint2& e) -> double2 {
+          if (kTeam && beRemote(e)) return ldPub2(sdPubCol + (size_t)e.x * 32 + lane);
+          return ldsRow(e.x + lane16);
+        };
+        auto edgeE = [&](uint32_t j) {
           const uint2 e = inS[inOff + j];
-          const double2 v = (T > 1 && beRemote(e)) ? ldPub2(sdPubCol + (size_t)e.x * 32 + lane)
-                                                   : ldsRow(aSD + ((e.x - rank * M) * 32 + lane) * 16);
-          const double sc = tb.symScore[beSym(e)];
-          if (j < nE) {
-            dd = dmax(dd, dmax(v.y + tb.delExtend, v.x + tb.delOpen) + sc);  // :124-125
-          } else {
-            dd = dmax(dd, v.y + sc);  // :140
-            s = dmax(s, v.x + sc);    // :147 (:98-99)
-          }
+          const double2 v = rowOf(e);
+          dd = dmax(dd, dmax(v.y + tb.delExtend, v.x + tb.delOpen) + tb.symScore[beSym(e)]);  // :124-125
           if (kDebug) ++dbgEdges;
         };
-        if (m == kBatchAllEdges) {
-          for (uint32_t j = 0; j < nIn; ++j) edge(j);
+        auto edgeN = [&](uint32_t j) {
+          const uint2 e = inS[inOff + j];
+          const double2 v = rowOf(e);
+          const double sc = tb.symScore[beSym(e)];
+          dd = dmax(dd, v.y + sc);  // :140
+          s = dmax(s, v.x + sc);    // :147 (:98-99)
+          if (kDebug) ++dbgEdges;
+        };
+        if (allIn || nIn <= 4u) {  // few transitions: relaxing all of them is cheaper than walking the mask
+          uint32_t j = 0;
+          for (; j < nE; ++j) edgeE(j);
+          for (; j < nIn; ++j) edgeN(j);
         } else {
           while (m) {
             const uint32_t j = (uint32_t)__ffs((int)m) - 1u;
             m &= m - 1u;
-            if (j == 31u)
-              for (uint32_t jj = 31; jj < nIn; ++jj) edge(jj);
+            if (j == 31u) {
+              for (uint32_t jj = 31; jj < nIn; ++jj)
+                if (jj < nE)
+                  edgeE(jj);
+                else
+                  edgeN(jj);
+            } else if (j < nE)
+              edgeE(j);
             else
-              edge(j);
+              edgeN(j);
           }
         }
         s = dmax(s, dd + tb.delEnd);  // :119-121
         const bool grew = act && ((s > own.x) || (dd > own.y));
         if (!__any_sync(0xFFFFFFFFu, grew)) return false;
         stsRow(aOwn, s, dd);
-        const uint32_t nOut = bhNOut(h), outOff = bhOutOff(h);
-        if (T > 1 && bhRemoteOut(h)) {
+        if (kTeam && bhRemoteOut(h)) {
           stPub2(sdPubCol + (size_t)(rank * M + d) * 32 + lane, s, dd);
-          __threadfence();
-          __syncwarp();
+          remotePending |= 1u << sl;
         }
-        for (uint32_t o = lane; o < nOut; o += 32) {
+        const uint32_t nLoc = bhNOutLocal(h), outOff = bhOutOff(h);
+        for (uint32_t o = lane; o < nLoc; o += 32) {
           const uint32_t w = outS[outOff + o];
-          if (T > 1 && boRemote(w)) {
-            const uint32_t i2 = boLocal(w);  // the owner's inbox is laid out [warp][slot]
-            atomicOr(inboxT + boRank(w) * (W * 32) + (i2 % W) * 32 + i2 / W, 1u << boBit(w));
-            sentRemote = true;
-          } else
-            atomicOr(maskNext + boLocal(w), 1u << boBit(w));
+          atomicOr(maskNext + boLocal(w), 1u << boBit(w));
         }
         return true;
+      };
+      // after a level: one release fence per warp orders the rows it published before the notifications it sends
+      // now; a notification that finds its target passive takes it out of the passive count on its behalf
+      auto flushRemote = [&]() {
+        if (!kTeam || !remotePending) return;
+        fenceRelease();
+        __syncwarp();
+        while (remotePending) {
+          const uint32_t sl = (uint32_t)__ffs((int)remotePending) - 1u;
+          remotePending &= remotePending - 1u;
+          const uint4 h = hdrS[sl * W + warp];
+          const uint32_t nLoc = bhNOutLocal(h), nOut = bhNOut(h), outOff = bhOutOff(h);
+          for (uint32_t o = nLoc + lane; o < nOut; o += 32) {  // the CTAs that own successors of this state
+            const uint32_t old = atomicOr(stateT + outS[outOff + o], kNotified);
+            if (old == kPassive) atomicSub(passiveCol, 1u);
+          }
+        }
       };
 
       {
         uint32_t lvl = 0;
         bool activated = false;
         // level 0: every transition of every state
-        for (uint32_t sl = 0; sl < nSlots; ++sl) {
-          const uint32_t d = sl * W + warp;
-          if (d >= M) break;
-          activated |= relax(d, kBatchAllEdges);
-        }
+        for (uint32_t sl = 0; sl < nSlots; ++sl)
+          if (sl * W + warp < M) activated |= relax(sl, 0, true);
+        flushRemote();
         for (;;) {
-          // local levels until this CTA is quiet
-          for (;;) {
-            if (activated && lane == 0) ctl[kCtlFlag + (lvl + 1) % 3] = 1u;
-            if (tid == 0) ctl[kCtlFlag + (lvl + 2) % 3] = 0u;
-            __syncthreads();
-            {
-              uint32_t* t = maskCur;
-              maskCur = maskNext;
-              maskNext = t;
-            }
-            ++lvl;
-            if (!ctl[kCtlFlag + lvl % 3]) break;
-            if (kDebug) ++dbgLevels;
-            activated = false;
-            uint32_t mym = 0;
-            {
-              const uint32_t i = lane * W + warp;
-              if (lane < nSlots && i < M) {
-                mym = maskCur[i];
-                if (mym) maskCur[i] = 0;
-              }
-            }
-            uint32_t work = __ballot_sync(0xFFFFFFFFu, mym != 0);
-            while (work) {
-              const uint32_t sl = (uint32_t)__ffs((int)work) - 1u;
-              work &= work - 1u;
-              const uint32_t m = __shfl_sync(0xFFFFFFFFu, mym, sl);
-              if (kDebug) ++dbgVisits;
-              activated |= relax(sl * W + warp, m);
-            }
+          // four flags in rotation: a slow thread may still be reading the ones of this level while the next are set
+          if (activated && lane == 0) ctl[kCtlFlag + ((lvl + 1) & 3u)] = 1u;
+          if (tid == 0) {
+            ctl[kCtlFlag + ((lvl + 2) & 3u)] = 0u;
+            ctl[kCtlWake + ((lvl + 2) & 3u)] = 0u;
           }
-          if (T == 1) break;
-          // quiet: drain the inbox (one coalesced load per warp: word warp*32+slot), else meet the team
-          bool drained = false;
+          __syncthreads();
           {
-            const uint32_t i = lane * W + warp;
-            if (lane < nSlots && i < M) {
-              uint32_t* p = inboxT + rank * (W * 32) + warp * 32 + lane;
-              if (ldVolatileGlobal32(p)) {
-                const uint32_t m = atomicExch(p, 0u);
-                if (m) {
-                  atomicOr(maskNext + i, m);
-                  drained = true;
+            uint32_t* t = maskCur;
+            maskCur = maskNext;
+            maskNext = t;
+          }
+          ++lvl;
+          const bool haveLocal = ctl[kCtlFlag + (lvl & 3u)] != 0;
+          bool wake = kTeam && ctl[kCtlWake + (lvl & 3u)] != 0;
+          if (!haveLocal && !wake) {
+            if (!kTeam) break;
+            // Nothing to do: become passive.  The column's closure is complete when all T CTAs of the team are passive
+            // (a CTA that notifies a passive one takes it out of the count before the target knows).
+            if (tid == 0) {
+              unsigned long long t0 = 0;
+              if (kDebug) t0 = clock64();
+              uint32_t decision;
+              const uint32_t old = atomicCAS(stateT + rank, 0u, kPassive);
+              if (old != 0u) {  // notified since the last check
+                atomicAnd(stateT + rank, ~kNotified);
+                decision = 1;
+              } else {
+                atomicAdd(passiveCol, 1u);
+                for (;;) {
+                  if (ldVolatileGlobal32(stateT + rank) & kNotified) {
+                    atomicExch(stateT + rank, 0u);
+                    decision = 1;
+                    break;
+                  }
+                  if (ldVolatileGlobal32(passiveCol) == T) {
+                    decision = 2;
+                    break;
+                  }
                 }
               }
+              ctl[kCtlDecision] = decision;
+              if (kDebug) dbgPassive += clock64() - t0;
             }
+            __syncthreads();
+            if (ctl[kCtlDecision] == 2u) break;
+            wake = true;
           }
-          activated = __any_sync(0xFFFFFFFFu, drained);
-          if (activated) __threadfence();  // the rows published before those bits were set are read after this point
-          if (__syncthreads_or(activated ? 1 : 0)) continue;  // new local work: back to the levels
-          if (kDebug) ++dbgRounds;
-          if (!teamBarrier()) break;  // nobody flagged a remote bit since the last meeting: fixed point
-          // somebody did: its inbox bits were set before it arrived, so the drain above sees them now
+          if (kDebug && haveLocal) ++dbgLevels;
+          if (kDebug && wake) ++dbgWakes;
           activated = false;
+          uint32_t st = 0;
+          if (kTeam && tid == 0) st = ldVolatileGlobal32(stateT + rank);  // consumed after this level's work
+          const uint32_t iMine = lane * W + warp;
+          uint32_t mym = 0;
+          if (lane < nSlots && iMine < M) {
+            if (haveLocal) {
+              mym = maskCur[iMine];
+              if (mym) maskCur[iMine] = 0;
+            }
+            if (wake) mym |= remInS[iMine];  // a neighbour CTA published new rows: relax every transition that crosses CTAs
+          }
+          uint32_t work = __ballot_sync(0xFFFFFFFFu, mym != 0);
+          while (work) {
+            const uint32_t sl = (uint32_t)__ffs((int)work) - 1u;
+            work &= work - 1u;
+            const uint32_t m = __shfl_sync(0xFFFFFFFFu, mym, sl);
+            if (kDebug) ++dbgVisits;
+            activated |= relax(sl, m, false);
+          }
+          flushRemote();
+          if (kTeam && tid == 0 && (st & kNotified)) {
+            atomicAnd(stateT + rank, ~kNotified);  // cleared BEFORE the rows are read (next level)
+            ctl[kCtlWake + ((lvl + 1) & 3u)] = 1u;
+          }
         }
       }
       if (kDebug) {
@@ -346,60 +386,77 @@ __global__ void __launch_bounds__(W * 32, 1)
       }
 
       // ---- (3) predecessor records with the traceback's arithmetic (src/viterbi.cpp:251-286), (4) duplication
-      //      opens (:161-168), (5) emission step of column pos+1 (:92-106) ----
+      //      opens (:161-168), (5) emission step of column pos+1 (:92-106) and the emit candidates of its S record ----
       {
-        const double* const sPrevCol = sPubT + (size_t)(par ^ 1u) * Np * 32;
-        double* const sCurCol = sPubT + (size_t)par * Np * 32;
         double bv = NEG;  // local mode: first maximum of S(.,L) in reference state order
         uint32_t bo = 0xFFFFFFFFu;
+        double pfB = NEG, pfT[KMAX];
+        auto fetch = [&](uint32_t sl) {
+          const uint32_t d = sl * W + warp;
+          if (d < M && pos > 0) {
+            const double* row = privT + (size_t)(rank * M + d) * privKinds * 32;
+            pfB = row[32];
+#pragma unroll
+            for (uint32_t t = 0; t < (uint32_t)KMAX; ++t)
+              if (t < k) pfT[t] = row[64 + 32 * t];
+          }
+        };
+#pragma unroll
+        for (uint32_t t = 0; t < (uint32_t)KMAX; ++t) pfT[t] = NEG;
+        fetch(0);
         for (uint32_t sl = 0; sl < nSlots; ++sl) {
           const uint32_t d = sl * W + warp;
           if (d >= M) break;
+          const double curB = pfB;
+          double curT[KMAX];
+#pragma unroll
+          for (uint32_t t = 0; t < (uint32_t)KMAX; ++t) curT[t] = pfT[t];
+          if (sl + 1 < nSlots) fetch(sl + 1);
           const uint4 h = hdrS[d];
           if (bhPad(h)) continue;
           const uint32_t inOff = bhInOff(h), nE = bhNEmit(h), nIn = nE + bhNNull(h), mdl = bhMdl(h), orig = h.w;
-          const uint32_t g = rank * M + d;
-          const double2 own = ldsRow(aSD + (d * 32 + lane) * 16);
+          double* const row = privT + (size_t)(rank * M + d) * privKinds * 32;
+          const double2 own = ldsRow(aSD + d * 512u + lane16);
           const double sH = own.x, dH = own.y;
-          double best = NEG, bestD = NEG, s0n = NEG;
-          uint32_t idx = kNoPred, idxD = kNoPred;
-          for (uint32_t j = 0; j < nIn; ++j) {
+          // S record: the emit candidates (:255) were evaluated by the previous column's pass
+          double best = pos > 0 ? curB : NEG, bestD = NEG, s0n = NEG, bEn = NEG;
+          uint32_t idx = pos > 0 ? kKeepRecord : kNoPred, idxD = kNoPred, idxEn = kNoPred;
+          uint32_t j = 0;
+          for (; j < nE; ++j) {
             const uint2 e = inS[inOff + j];
             const uint32_t sym = beSym(e);
-            const double2 v = (T > 1 && beRemote(e)) ? ldPub2(sdPubCol + (size_t)e.x * 32 + lane)
-                                                     : ldsRow(aSD + ((e.x - rank * M) * 32 + lane) * 16);
-            if (j < nE) {
-              const uint32_t sb = sym * 4 + beBase(e);
-              if (pos > 0) {
-                const double c = ldCg(sPrevCol + (size_t)e.x * 32 + lane) + tsE[sb * 4 + x];  // :255
-                if (c > best) {
-                  best = c;
-                  idx = j;
-                }
-              }
-              double c = v.y + tb.tsDext[sym];  // :272
-              if (c > bestD) {
-                bestD = c;
-                idxD = 2 * j;
-              }
-              c = v.x + tb.tsDopen[sym];  // :273
-              if (c > bestD) {
-                bestD = c;
-                idxD = 2 * j + 1;
-              }
-              s0n = dmax(s0n, ((v.x + tb.symScore[sym]) + tb.noGap) + subS[beBase(e) * 4 + xNext]);  // :94-95 of pos+1
-            } else {
-              const double sc = tb.symScore[sym];
-              double c = v.x + sc;  // :257
-              if (c > best) {
-                best = c;
-                idx = j;
-              }
-              c = v.y + sc;  // :276
-              if (c > bestD) {
-                bestD = c;
-                idxD = nE + j;
-              }
+            const double2 v = (kTeam && beRemote(e)) ? ldPub2(sdPubCol + (size_t)e.x * 32 + lane) : ldsRow(e.x + lane16);
+            double c = v.y + tb.tsDext[sym];  // :272
+            if (c > bestD) {
+              bestD = c;
+              idxD = 2 * j;
+            }
+            c = v.x + tb.tsDopen[sym];  // :273
+            if (c > bestD) {
+              bestD = c;
+              idxD = 2 * j + 1;
+            }
+            const uint32_t b4 = beBase(e) * 4 + xNext;
+            s0n = dmax(s0n, ((v.x + tb.symScore[sym]) + tb.noGap) + subS[b4]);  // :94-95 of pos+1
+            c = v.x + tsE[sym * 16 + b4];                                       // :255 of pos+1
+            if (c > bEn) {
+              bEn = c;
+              idxEn = j;
+            }
+          }
+          for (; j < nIn; ++j) {
+            const uint2 e = inS[inOff + j];
+            const double2 v = (kTeam && beRemote(e)) ? ldPub2(sdPubCol + (size_t)e.x * 32 + lane) : ldsRow(e.x + lane16);
+            const double sc = tb.symScore[beSym(e)];
+            double c = v.x + sc;  // :257
+            if (c > best) {
+              best = c;
+              idx = j;
+            }
+            c = v.y + sc;  // :276
+            if (c > bestD) {
+              bestD = c;
+              idxD = nE + j;
             }
           }
           {
@@ -410,16 +467,16 @@ __global__ void __launch_bounds__(W * 32, 1)
             }
           }
           if (mdl > 0 && pos > 0) {
-            const double parked = tParkT[((size_t)(mdl - 1) * Np + g) * 32 + lane];  // T(state,pos-1,0)+sub, :261
+            const double parked = curT[0];  // T(state,pos-1,0)+sub, :261 (slot 0 holds the T -> S candidate)
             if (parked > best) {
               best = parked;
               idx = nIn + 1;
             }
           }
           if (tb.local && pos == 0) {  // :263-264
-            const double2 v0 = (T > 1 && tb.startRank != rank)
+            const double2 v0 = (kTeam && tb.startRank != rank)
                                    ? ldPub2(sdPubCol + (size_t)(tb.startRank * M + tb.startLocal) * 32 + lane)
-                                   : ldsRow(aSD + (tb.startLocal * 32 + lane) * 16);
+                                   : ldsRow(aSD + tb.startLocal * 512u + lane16);
             if (v0.x + 0.0 > best) {
               best = v0.x + 0.0;
               idx = nIn + 2;
@@ -427,21 +484,23 @@ __global__ void __launch_bounds__(W * 32, 1)
           }
           uint8_t* const pr = predG + ((size_t)pos * N + orig) * K2 * 32 + lane;
           if (act) {
-            stRecord(pr, idx);
+            if (idx != kKeepRecord) stRecord(pr, idx);
             stRecord(pr + 32, idxD);
           }
-          double tNow[kMaxK];
+          // duplication cells (:161-168) and their records (:281-286).  Parked layout between columns: slot 0 holds
+          // T(pos,0)+sub (the T -> S candidate of the next column), slot t >= 1 holds T(pos,t)+sub (the shift into t-1).
+          double tNow[KMAX];
 #pragma unroll
-          for (uint32_t t = 0; t < (uint32_t)kMaxK; ++t) {
+          for (uint32_t t = 0; t < (uint32_t)KMAX; ++t) {
             tNow[t] = NEG;
             if (t < k) {
               uint32_t idxT = kNoPred;
               if (pos > 0 && t < mdl) {
                 double shifted = NEG;
-                if (t + 1 < mdl) shifted = tParkT[((size_t)t * Np + g) * 32 + lane];  // T(state,pos-1,t+1)+sub, :285
-                if (t + 1 < mdl && shifted > NEG) idxT = 0;
-                if (sH + tb.tsT[t] > shifted) idxT = 1;                      // :286
-                tNow[t] = dmax(shifted, (sH + tb.tanDup) + tb.len[t]);       // :166-167
+                if (t + 1 < (uint32_t)KMAX && t + 1 < mdl) shifted = curT[t + 1 < (uint32_t)KMAX ? t + 1 : 0];  // T(state,pos-1,t+1)+sub, :285
+                if (shifted > NEG) idxT = 0;
+                if (sH + tb.tsT[t] > shifted) idxT = 1;                  // :286
+                tNow[t] = dmax(shifted, (sH + tb.tanDup) + tb.len[t]);   // :166-167
               }
               if (act) stRecord(pr + (2 + t) * 32, idxT);
             }
@@ -451,20 +510,23 @@ __global__ void __launch_bounds__(W * 32, 1)
             cell[0] = sH;
             cell[1] = dH;
 #pragma unroll
-            for (uint32_t t = 0; t < (uint32_t)kMaxK; ++t)
+            for (uint32_t t = 0; t < (uint32_t)KMAX; ++t)
               if (t < k) cell[2 + t] = tNow[t];
           }
           // column pos+1: T -> S candidate and the T shift (:102-106), parked for the next column
           if (mdl > 0) {
-            const double t2s = tNow[0] + subS[bhCtx(h, 0) * 4 + xNext];
-            s0n = dmax(s0n, t2s);
 #pragma unroll
-            for (uint32_t t = 0; t + 1 < (uint32_t)kMaxK; ++t)
-              if (t + 1 < mdl) tParkT[((size_t)t * Np + g) * 32 + lane] = tNow[t + 1] + subS[bhCtx(h, t + 1) * 4 + xNext];
-            tParkT[((size_t)(mdl - 1) * Np + g) * 32 + lane] = t2s;
+            for (uint32_t t = 0; t < (uint32_t)KMAX; ++t)
+              if (t < mdl) {
+                const double v = tNow[t] + subS[bhCtx(h, t) * 4 + xNext];
+                if (t == 0) s0n = dmax(s0n, v);
+                row[64 + 32 * t] = v;
+              }
           }
-          s0T[(size_t)g * 32 + lane] = s0n;
-          stCg(sCurCol + (size_t)g * 32 + lane, sH);  // the converged column, gathered by the next position's records
+          row[0] = s0n;
+          row[32] = bEn;
+          if (pos < L) stRecordEarly(pr + (size_t)N * K2 * 32, idxEn);  // the emit part of S(state,pos+1)'s record
+          if (kTeam && bhRemoteOut(h)) stPub2(sdPubNext + (size_t)(rank * M + d) * 32 + lane, s0n, NEG);
           if (!tb.local) {
             if (rank == tb.endRank && d == tb.endLocal && pos == L && r >= 0) args.loglike[r] = sH;  // viterbi.h:102
           } else if (sH > bv || (sH == bv && orig < bo)) {
@@ -495,18 +557,16 @@ __global__ void __launch_bounds__(W * 32, 1)
       __syncthreads();  // rows of this column are dead: the next column's S0 may overwrite them
       if (kDebug) dbgRecord += clock64() - stamp;
     }
-    // lanes of an empty slot never reach pos == L; nothing to write for them
   }
-  if (kDebug && args.dbg && lane == 0) {
-    // summed over warps of rank 0 of every team (levels are CTA-uniform: count them once per CTA)
-    if (rank == 0) {
-      if (warp == 0) atomicAdd(&args.dbg[1], dbgLevels);
-      atomicAdd(&args.dbg[2], dbgVisits);
-      atomicAdd(&args.dbg[3], dbgEdges);
-      if (warp == 0) atomicAdd(&args.dbg[4], dbgClosure);
-      if (warp == 0) atomicAdd(&args.dbg[5], dbgRecord);
-      if (warp == 0) atomicAdd(&args.dbg[6], dbgRounds);
-    }
+  if (kDebug && args.dbg && lane == 0 && rank == 0) {
+    // levels and cycles are CTA-uniform: counted by warp 0 of rank 0 of every team; visits and edges by every warp of it
+    if (warp == 0) atomicAdd(&args.dbg[1], dbgLevels);
+    atomicAdd(&args.dbg[2], dbgVisits);
+    atomicAdd(&args.dbg[3], dbgEdges);
+    if (warp == 0) atomicAdd(&args.dbg[4], dbgClosure);
+    if (warp == 0) atomicAdd(&args.dbg[5], dbgRecord);
+    if (warp == 0) atomicAdd(&args.dbg[6], dbgWakes);
+    if (warp == 0) atomicAdd(&args.dbg[7], dbgPassive);
   }
 }
 
@@ -635,30 +695,36 @@ __global__ void viterbiTracebackBatchKernel(const BatchTraceTables tb, const Bat
 // launchers
 // ---------------------------------------------------------------------------
 typedef void (*BatchKernelPtr)(const BatchTables, const BatchArgs);
-static BatchKernelPtr pickBatchKernel(uint32_t warps, bool debug) {
-  if (warps > 16) return debug ? viterbiFillBatchKernel<32, true> : viterbiFillBatchKernel<32, false>;
-  if (warps > 8) return debug ? viterbiFillBatchKernel<16, true> : viterbiFillBatchKernel<16, false>;
-  return debug ? viterbiFillBatchKernel<8, true> : viterbiFillBatchKernel<8, false>;
+template <int W, int KMAX>
+static BatchKernelPtr pickBatchKernelWK(bool team, bool debug) {
+  if (debug) return team ? viterbiFillBatchKernel<W, KMAX, true, true> : viterbiFillBatchKernel<W, KMAX, false, true>;
+  return team ? viterbiFillBatchKernel<W, KMAX, true, false> : viterbiFillBatchKernel<W, KMAX, false, false>;
+}
+static uint32_t batchWarps(uint32_t warps) { return warps > 24 ? 32u : warps > 16 ? 24u : 16u; }
+static BatchKernelPtr pickBatchKernel(const BatchTables& tb, uint32_t warps, bool debug) {
+  const bool team = tb.T > 1;
+  const uint32_t w = batchWarps(warps);
+  if (w == 32) return tb.k <= 2 ? pickBatchKernelWK<32, 2>(team, debug) : pickBatchKernelWK<32, kMaxK>(team, debug);
+  if (w == 24) return tb.k <= 2 ? pickBatchKernelWK<24, 2>(team, debug) : pickBatchKernelWK<24, kMaxK>(team, debug);
+  return tb.k <= 2 ? pickBatchKernelWK<16, 2>(team, debug) : pickBatchKernelWK<16, kMaxK>(team, debug);
 }
 
 cudaError_t queryBatchTeams(const BatchTables& tb, uint32_t warps, uint32_t smemBytes, int* ctasPerSm) {
-  BatchKernelPtr kern = pickBatchKernel(warps, false);
+  BatchKernelPtr kern = pickBatchKernel(tb, warps, false);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
   if (err != cudaSuccess) return err;
-  const uint32_t w = warps > 16 ? 32 : warps > 8 ? 16 : 8;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, kern, (int)(w * 32), smemBytes);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, kern, (int)(batchWarps(warps) * 32), smemBytes);
 }
 
 cudaError_t launchFillBatch(const BatchTables& tb, const BatchArgs& args, uint32_t warps, uint32_t smemBytes,
                             cudaStream_t stream) {
   const bool debug = args.dbg != nullptr || args.cells != nullptr;
-  BatchKernelPtr kern = pickBatchKernel(warps, debug);
+  BatchKernelPtr kern = pickBatchKernel(tb, warps, debug);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
   if (err != cudaSuccess) return err;
-  const uint32_t w = warps > 16 ? 32 : warps > 8 ? 16 : 8;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(args.nTeams * tb.T);
-  cfg.blockDim = dim3(w * 32);
+  cfg.blockDim = dim3(batchWarps(warps) * 32);
   cfg.dynamicSmemBytes = smemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

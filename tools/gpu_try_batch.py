@@ -15,7 +15,33 @@ import dnab_testutil as util  # noqa: E402
 import dnastore_b200 as d  # noqa: E402
 
 
+def agree(workload, n, opts):
+    """batch kernel vs push kernel on n synthetic reads of a bench workload (several groups per team)."""
+    import bench
+    w = bench.WORKLOADS[workload]
+    compiled = util.machine_from_recipe(w["recipe"]).compile(d.ErrorFlags(length=w["length"], global_=True))
+    reads = bench.make_reads(w, n, seed=4242)
+    outs = []
+    for kern in (1, 2):
+        dec = d.Decoder(compiled, device=0)
+        dec.set_option("kernel", kern)
+        if kern == 1:
+            for k, v in opts.items():
+                dec.set_option(k, int(v))
+        t0 = time.time()
+        outs.append(dec.viterbi(reads, want_path=True))
+        print(f"   kernel {kern}: {time.time() - t0:.2f}s", flush=True)
+    a, b = outs
+    bad = sum(1 for i in range(n) if a["loglike"][i].tobytes() != b["loglike"][i].tobytes() or a["decoded"][i] != b["decoded"][i]
+              or a["path"][i].tolist() != b["path"][i].tolist() or a["status"][i] != b["status"][i])
+    print(f"AGREE {workload} n={n} bad={bad}", flush=True)
+    return bad
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--agree":
+        opts = dict(kv.lstrip("-").split("=") for kv in sys.argv[4:] if kv.startswith("--"))
+        return 1 if agree(sys.argv[2], int(sys.argv[3]), opts) else 0
     names = [a for a in sys.argv[1:] if not a.startswith("--")]
     opts = dict(kv.lstrip("-").split("=") for kv in sys.argv[1:] if kv.startswith("--"))
     cases = [c for c in util.load_golden() if not names or c["name"] in names]
