@@ -120,7 +120,7 @@ struct dnab_decoder {
   BatchTables btab{};
   BatchTraceTables btrace{};
   DevBuf<uint4> dbHdr;
-  DevBuf<uint2> dbIn;
+  DevBuf<uint2> dbIn, dbRel, dbHdr2;
   DevBuf<uint32_t> dbOut, dbRankInOff, dbRankOutOff, dbRemoteIn, dbEmitOff, dbEmitSrc, dbNullOff, dbNullSrc, dbTeamState, dbTeamPassive, dbPartOrig;
   DevBuf<uint8_t> dbEmitSym, dbNullSym;
   DevBuf<double> dbTsE, dbPriv, dbPartVal;
@@ -676,6 +676,99 @@ static int buildPlan(dnab_decoder* d, int32_t maxLen) {
 // ---------------------------------------------------------------------------
 // read-batched kernel: partition, tables, scratch (formats: viterbi_batch.h)
 // ---------------------------------------------------------------------------
+// State partition of the read-batched kernel: T parts of at most cap states with few transitions between parts.
+// Greedy graph growing (a part grows from a seed by always taking the unassigned state with the most transitions
+// into the part, seeds in depth-first order) followed by capacity-bounded label propagation.  On the BASELINE
+// machines it leaves 13-22 % of the transitions between CTAs where equal runs of a depth-first order leave 18-53 %.
+static std::vector<uint32_t> growPartition(const dnab_decoder* d, uint32_t T, uint32_t cap, const std::vector<uint32_t>& dfs) {
+  const uint32_t N = d->nStates;
+  std::vector<uint32_t> off(N + 1, 0), nb;
+  auto each = [&](auto&& f) {
+    for (uint32_t dst = 0; dst < N; ++dst) {
+      for (uint32_t e = d->emitOff[dst]; e < d->emitOff[dst + 1]; ++e)
+        if (d->emitSrc[e] != dst) f(d->emitSrc[e], dst);
+      for (uint32_t e = d->nullOff[dst]; e < d->nullOff[dst + 1]; ++e)
+        if (d->nullSrc[e] != dst) f(d->nullSrc[e], dst);
+    }
+  };
+  each([&](uint32_t a, uint32_t b) {
+    ++off[a + 1];
+    ++off[b + 1];
+  });
+  for (uint32_t s = 0; s < N; ++s) off[s + 1] += off[s];
+  nb.resize(off[N]);
+  std::vector<uint32_t> fill(off.begin(), off.end() - 1);
+  each([&](uint32_t a, uint32_t b) {
+    nb[fill[a]++] = b;
+    nb[fill[b]++] = a;
+  });
+  const uint32_t none = 0xFFFFFFFFu;
+  std::vector<uint32_t> part(N, none), conn(N, 0), size(T, 0);
+  const uint32_t target = (N + T - 1) / T;
+  uint32_t ptr = 0;
+  for (uint32_t p = 0; p < T; ++p) {
+    const uint32_t quota = p + 1 < T ? target : cap;
+    std::vector<std::pair<uint32_t, uint32_t>> heap;  // (connections into the part, state), max-heap
+    std::vector<uint32_t> touched;
+    while (size[p] < quota) {
+      if (heap.empty()) {
+        while (ptr < N && part[dfs[ptr]] != none) ++ptr;
+        if (ptr >= N) break;
+        heap.push_back({0u, dfs[ptr]});
+      }
+      std::pop_heap(heap.begin(), heap.end());
+      const auto top = heap.back();
+      heap.pop_back();
+      const uint32_t v = top.second;
+      if (part[v] != none || top.first != conn[v]) continue;  // stale entry
+      part[v] = p;
+      ++size[p];
+      for (uint32_t e = off[v]; e < off[v + 1]; ++e) {
+        const uint32_t u = nb[e];
+        if (part[u] != none) continue;
+        if (!conn[u]) touched.push_back(u);
+        ++conn[u];
+        heap.push_back({conn[u], u});
+        std::push_heap(heap.begin(), heap.end());
+      }
+    }
+    for (uint32_t u : touched) conn[u] = 0;
+  }
+  for (uint32_t s = 0; s < N; ++s)
+    if (part[s] == none) {  // leftovers (cannot happen with cap >= target): the emptiest part
+      const uint32_t p = (uint32_t)(std::min_element(size.begin(), size.end()) - size.begin());
+      part[s] = p;
+      ++size[p];
+    }
+  std::vector<uint32_t> cnt(T, 0), seenParts;
+  for (int sweep = 0; sweep < 8; ++sweep) {
+    uint32_t moved = 0;
+    for (uint32_t s = 0; s < N; ++s) {
+      seenParts.clear();
+      for (uint32_t e = off[s]; e < off[s + 1]; ++e) {
+        const uint32_t p = part[nb[e]];
+        if (!cnt[p]++) seenParts.push_back(p);
+      }
+      const uint32_t cur = part[s];
+      uint32_t best = cur, bc = cnt[cur];
+      for (uint32_t p : seenParts)
+        if (cnt[p] > bc && size[p] < cap) {
+          best = p;
+          bc = cnt[p];
+        }
+      for (uint32_t p : seenParts) cnt[p] = 0;
+      if (best != cur) {
+        --size[cur];
+        ++size[best];
+        part[s] = best;
+        ++moved;
+      }
+    }
+    if (moved * 500 < N) break;
+  }
+  return part;
+}
+
 static bool batchWanted(const dnab_decoder* d) {
   if (d->wantBatch == 0) return false;
   if (d->wantBatch == 1) return true;
@@ -693,7 +786,7 @@ static int buildBatchPlan(dnab_decoder* d) {
   bp.ready = true;
   bp.feasible = false;
   const uint32_t N = d->nStates, k = d->k;
-  const uint32_t W = d->wantWarps ? (d->wantWarps > 24 ? 32u : d->wantWarps > 16 ? 24u : 16u) : 32u;
+  const uint32_t W = d->wantWarps ? (d->wantWarps > 24 ? 32u : d->wantWarps > 16 ? 24u : 16u) : 24u;
   auto nEmitOf = [&](uint32_t s) { return d->emitOff[s + 1] - d->emitOff[s]; };
   auto nNullOf = [&](uint32_t s) { return d->nullOff[s + 1] - d->nullOff[s]; };
   for (uint32_t s = 0; s < N; ++s) {
@@ -707,34 +800,35 @@ static int buildBatchPlan(dnab_decoder* d) {
   std::vector<std::vector<std::pair<uint32_t, uint32_t>>> outs(N);
   for (uint32_t dst = 0; dst < N; ++dst) {
     uint32_t j = 0;
-    for (uint32_t e = d->emitOff[dst]; e < d->emitOff[dst + 1]; ++e, ++j) outs[d->emitSrc[e]].push_back({dst, std::min(j, 31u)});
-    for (uint32_t e = d->nullOff[dst]; e < d->nullOff[dst + 1]; ++e, ++j) outs[d->nullSrc[e]].push_back({dst, std::min(j, 31u)});
+    for (uint32_t e = d->emitOff[dst]; e < d->emitOff[dst + 1]; ++e, ++j) outs[d->emitSrc[e]].push_back({dst, j});
+    for (uint32_t e = d->nullOff[dst]; e < d->nullOff[dst + 1]; ++e, ++j) outs[d->nullSrc[e]].push_back({dst, j});
   }
-  for (auto& o : outs) {
-    std::sort(o.begin(), o.end());
-    o.erase(std::unique(o.begin(), o.end()), o.end());
+  for (auto& o : outs)
     if (o.size() > 255) {
       setLastError("a state has more than 255 outgoing transitions");
       return DNAB_EINVAL;
     }
-  }
   const std::vector<uint32_t> dfs = dfsOrder(d);
+  const uint32_t nSymsB = (uint32_t)d->symChar.size();
   const uint32_t maxTeam = (uint32_t)d->smCount;
   uint32_t T0 = std::max<uint32_t>(1, (uint32_t)(((size_t)N * kBatchReads * 16 + d->smemOptin - 1) / d->smemOptin));
   std::vector<uint4> hdr;
-  std::vector<uint2> inE;
+  std::vector<uint2> inE, relE, hdr2;
   std::vector<uint32_t> outE, rankInOff, rankOutOff, newOf(N), origOf, remoteIn;
   // builds the tables of a team of T CTAs; false when T is infeasible
-  auto tryTeam = [&](uint32_t T) -> bool {
-    const uint32_t M = (N + T - 1) / T, Np = T * M;
+  auto buildTeam = [&](uint32_t T, uint32_t M) -> bool {
+    const uint32_t Np = T * M;
     if (M > kBatchMaxSlots * W || M > 65535 || T > 1023) return false;
-    if (makeBatchLayout(M, 0, 0, W, T > 1).total > d->smemOptin) return false;
-    // CTA assignment: balanced runs of a depth-first order (T > 1); inside a CTA descending in-degree, dealt to the warps
+    if (makeBatchLayout(M, 0, 0, nSymsB, T > 1).total > d->smemOptin) return false;
+    // CTA assignment (T > 1): growPartition; inside a CTA descending in-degree, dealt to the warps
+    std::vector<uint32_t> part;
+    if (T > 1) part = growPartition(d, T, M, dfs);
+    std::vector<std::vector<uint32_t>> members(T);
+    for (uint32_t s = 0; s < N; ++s) members[T > 1 ? part[s] : 0].push_back(s);
     origOf.assign(Np, 0xFFFFFFFFu);
     for (uint32_t r = 0; r < T; ++r) {
-      const uint32_t lo = (uint32_t)((uint64_t)N * r / T), hi = (uint32_t)((uint64_t)N * (r + 1) / T);
-      std::vector<uint32_t> mine;
-      for (uint32_t i = lo; i < hi; ++i) mine.push_back(T > 1 ? dfs[i] : i);
+      std::vector<uint32_t>& mine = members[r];
+      if (mine.size() > M) return false;
       std::stable_sort(mine.begin(), mine.end(),
                        [&](uint32_t a, uint32_t b) { return nEmitOf(a) + nNullOf(a) > nEmitOf(b) + nNullOf(b); });
       for (uint32_t j = 0; j < mine.size(); ++j) {
@@ -743,8 +837,25 @@ static int buildBatchPlan(dnab_decoder* d) {
       }
     }
     hdr.assign(Np, make_uint4(0, 0, 1u << 17, 0xFFFFFFFFu));
+    hdr2.assign(Np, make_uint2(0, 0));
     remoteIn.assign(Np, 0);
+    // position of every in-transition in its destination's relax list: local emit, local null, remote emit, remote null
+    std::vector<std::vector<uint32_t>> relPos(N);
+    for (uint32_t dst = 0; dst < N; ++dst) {
+      const uint32_t nE = nEmitOf(dst), nIn = nE + nNullOf(dst), rD = newOf[dst] / M;
+      std::vector<uint32_t> key(nIn), idx(nIn);
+      for (uint32_t j = 0; j < nIn; ++j) {
+        const uint32_t src = j < nE ? d->emitSrc[d->emitOff[dst] + j] : d->nullSrc[d->nullOff[dst] + (j - nE)];
+        key[j] = (newOf[src] / M != rD ? 2u : 0u) + (j < nE ? 0u : 1u);
+        idx[j] = j;
+      }
+      std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+      relPos[dst].resize(nIn);
+      for (uint32_t q = 0; q < nIn; ++q) relPos[dst][idx[q]] = q;
+    }
     inE.clear();
+    relE.clear();
+
     outE.clear();
     rankInOff.assign(T + 1, 0);
     rankOutOff.assign(T + 1, 0);
@@ -764,13 +875,28 @@ static int buildBatchPlan(dnab_decoder* d) {
           const uint32_t sg = newOf[src];
           const bool remote = sg / M != r;
           inE.push_back(make_uint2(sg, sym | (base << 5) | (remote ? 1u << 7 : 0u)));
-          if (remote) remoteIn[r * M + i] |= 1u << std::min(jIn, 31u);
           ++jIn;
           ++total;
           cross += remote;
         };
         for (uint32_t e = d->emitOff[s]; e < d->emitOff[s + 1]; ++e) pushIn(d->emitSrc[e], d->emitSym[e], d->emitBase[e]);
         for (uint32_t e = d->nullOff[s]; e < d->nullOff[s + 1]; ++e) pushIn(d->nullSrc[e], d->nullSym[e], 0);
+        {
+          // the closure's copy, in relax order
+          const uint32_t nInS = nE + nN, base = (uint32_t)relE.size();
+          relE.resize(base + nInS);
+          uint32_t cnt[4] = {0, 0, 0, 0};
+          remoteIn[r * M + i] = 0;
+          for (uint32_t j = 0; j < nInS; ++j) {
+            const uint32_t src = j < nE ? d->emitSrc[d->emitOff[s] + j] : d->nullSrc[d->nullOff[s] + (j - nE)];
+            const uint32_t sym = j < nE ? d->emitSym[d->emitOff[s] + j] : d->nullSym[d->nullOff[s] + (j - nE)];
+            const bool remote = newOf[src] / M != r;
+            ++cnt[(remote ? 2 : 0) + (j < nE ? 0 : 1)];
+            relE[base + relPos[s][j]] = make_uint2(newOf[src], sym * 8);
+            if (remote) remoteIn[r * M + i] |= 1u << std::min(relPos[s][j], 31u);
+          }
+          hdr2[r * M + i] = make_uint2(base - rankInOff[r], cnt[0] | (cnt[1] << 8) | (cnt[2] << 16) | (cnt[3] << 24));
+        }
         bool remoteOut = (d->local && s == 0 && T > 1);  // local mode: every CTA reads S(start,0) for the (0,0) escape
         uint32_t nLocal = 0;
         std::vector<uint32_t> remoteCtas;
@@ -782,7 +908,7 @@ static int buildBatchPlan(dnab_decoder* d) {
             continue;
           }
           ++nLocal;
-          outE.push_back((dg % M) | (o.second << 16));
+          outE.push_back((dg % M) | (std::min(relPos[o.first][o.second], 31u) << 16));
         }
         std::sort(remoteCtas.begin(), remoteCtas.end());
         remoteCtas.erase(std::unique(remoteCtas.begin(), remoteCtas.end()), remoteCtas.end());
@@ -798,7 +924,7 @@ static int buildBatchPlan(dnab_decoder* d) {
     }
     rankInOff[T] = (uint32_t)inE.size();
     rankOutOff[T] = (uint32_t)outE.size();
-    const uint32_t smem = makeBatchLayout(M, maxIn, maxOut, W, T > 1).total;
+    const uint32_t smem = makeBatchLayout(M, maxIn, maxOut, nSymsB, T > 1).total;
     if (smem > d->smemOptin) return false;
     bp.T = T;
     bp.M = M;
@@ -820,6 +946,20 @@ static int buildBatchPlan(dnab_decoder* d) {
     t.maxIn = maxIn;
     t.maxOut = maxOut;
     return true;
+  };
+  // states per CTA: the balanced share plus 8 % (then 4 %, then nothing) so that the partitioner can trade balance for
+  // fewer transitions between CTAs, as long as columns, tables and the cache of remote rows still fit
+  auto tryTeam = [&](uint32_t T) -> bool {
+    const uint32_t Mbal = (N + T - 1) / T;
+    if (T == 1) return buildTeam(1, Mbal);
+    uint32_t last = 0;
+    for (uint32_t pct : {8u, 4u, 0u}) {
+      const uint32_t M = std::min<uint32_t>(Mbal + (Mbal * pct + 99) / 100, kBatchMaxSlots * W);
+      if (M == last) continue;
+      last = M;
+      if (buildTeam(T, M)) return true;
+    }
+    return false;
   };
   if (d->wantTeam)
     bp.feasible = tryTeam(d->wantTeam);
@@ -844,12 +984,15 @@ static int buildBatchPlan(dnab_decoder* d) {
   outE.push_back(0);
   CUDA_TRY(d->dbHdr.upload(hdr));
   CUDA_TRY(d->dbIn.upload(inE));
+  relE.push_back(make_uint2(0, 0));
+  CUDA_TRY(d->dbRel.upload(relE));
+  CUDA_TRY(d->dbHdr2.upload(hdr2));
   CUDA_TRY(d->dbOut.upload(outE));
   CUDA_TRY(d->dbRankInOff.upload(rankInOff));
   CUDA_TRY(d->dbRankOutOff.upload(rankOutOff));
   CUDA_TRY(d->dbRemoteIn.upload(remoteIn));
   // score tables with the traceback's association, formed once on the host in IEEE fp64 (-ffp-contract=off)
-  std::vector<double> tsE(32 * 16, 0.);
+  std::vector<double> tsE((size_t)kMaxSyms * 16, 0.);
   for (uint32_t sym = 0; sym < d->symScore.size(); ++sym)
     for (uint32_t b = 0; b < 4; ++b)
       for (uint32_t x = 0; x < 4; ++x) {
@@ -863,6 +1006,8 @@ static int buildBatchPlan(dnab_decoder* d) {
   t.rankInOff = d->dbRankInOff.p;
   t.rankOutOff = d->dbRankOutOff.p;
   t.remoteIn = d->dbRemoteIn.p;
+  t.hdr2 = d->dbHdr2.p;
+  t.relEdges = d->dbRel.p;
   t.tsE = d->dbTsE.p;
   for (int i = 0; i < kMaxSyms; ++i) {
     const double sc = i < (int)d->symScore.size() ? d->symScore[i] : 0.;
@@ -892,7 +1037,7 @@ static int buildBatchPlan(dnab_decoder* d) {
   tt.nStates = N;
   tt.k = k;
   tt.local = d->local;
-  tt.T = bp.T;
+  tt.T = bp.T * bp.warps;
   tt.emitOff = d->dbEmitOff.p;
   tt.emitSrc = d->dbEmitSrc.p;
   tt.emitSym = d->dbEmitSym.p;
@@ -936,8 +1081,8 @@ static int runDeviceBatch(dnab_decoder* d, int64_t nReads, int32_t maxLen, const
   chunk = std::min<int64_t>(chunk, nGroups);
   CUDA_TRY(d->dPred.ensure((size_t)chunk * perGroup));
   if (d->local) {
-    CUDA_TRY(d->dbPartVal.ensure((size_t)chunk * bp.T * 32));
-    CUDA_TRY(d->dbPartOrig.ensure((size_t)chunk * bp.T * 32));
+    CUDA_TRY(d->dbPartVal.ensure((size_t)chunk * bp.T * bp.warps * 32));
+    CUDA_TRY(d->dbPartOrig.ensure((size_t)chunk * bp.T * bp.warps * 32));
   }
   const int32_t* dOrder = nullptr;
   if (hostLen && !dCells && nReads > 32) {
@@ -1036,8 +1181,14 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
   if (nReads <= 0) return DNAB_OK;
   CUDA_TRY(cudaSetDevice(d->device));
   if (batchWanted(d)) {
-    const int brc = buildBatchPlan(d);
-    if (brc == DNAB_OK)
+    // Automatic choice (measured on B200): the read-batched kernel when the group's columns fit ONE CTA
+    // (2.1x the one-read-per-cluster kernel on dnastore-l4); larger machines stay on the push kernel, whose cross-CTA
+    // traffic goes through distributed shared memory -- a team over L2 pays ~3 us per cross-CTA hop of a deletion chain
+    // and only ties it on the 46,670-state machine -- unless no 16-CTA cluster can hold the machine.
+    int brc = buildBatchPlan(d);
+    bool use = brc == DNAB_OK;
+    if (use && d->wantBatch != 1 && d->bplan.T > 1 && buildPlan(d, maxLen) == DNAB_OK) use = false;
+    if (use)
       return runDeviceBatch(d, nReads, maxLen, dPacked, dByteOff, dReadLen, dLoglike, dDecoded, decodedStride, dDecodedLen,
                             dStatus, dPath, pathStride, dPathLen, dCells, stream, timeIt, hostLen);
     if (d->wantBatch == 1) return brc;
@@ -1313,7 +1464,7 @@ int dnab_decoder_get_batch_info(const dnab_decoder* dc, dnab_batch_info* info) {
   std::memset(info, 0, sizeof *info);
   if (!batchWanted(d)) return DNAB_OK;
   if (buildBatchPlan(d) != DNAB_OK) return d->wantBatch == 1 ? DNAB_EINVAL : DNAB_OK;
-  info->enabled = 1;
+  info->enabled = (d->wantBatch == 1 || d->bplan.T == 1 || buildPlan(d, 1) != DNAB_OK) ? 1 : 0;
   info->reads_per_group = kBatchReads;
   info->team_size = d->bplan.T;
   info->states_per_cta = d->bplan.M;

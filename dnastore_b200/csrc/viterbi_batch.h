@@ -36,6 +36,11 @@ constexpr uint32_t kBatchAllEdges = 0xFFFFFFFFu;
 //                   work mask (= index of this transition in the destination's in-edge list, 31 = "31 or later");
 //                   then one entry per OTHER CTA that owns a successor: its rank (the CTA is notified, not the state)
 //   remoteIn u32    per state: the bits of its work mask whose transitions come from other CTAs
+//   The closure reads its own copy of the in-transitions, grouped so that its loops have no per-edge branch:
+//   hdr2    uint2   x: offset of the state's relax entries inside the rank's array
+//                   y: local emit | local null << 8 | remote emit << 16 | remote null << 24   (counts, in this order)
+//   relax   uint2   x: padded index g of the source, y: symbol id * 8 (byte offset of its score)
+//   Bit j of a state's work mask is its j-th relax entry (31 = "31 or later").
 // ---------------------------------------------------------------------------
 __host__ __device__ inline uint32_t bhInOff(const uint4& h) { return h.x & 0xFFFFu; }
 __host__ __device__ inline uint32_t bhOutOff(const uint4& h) { return h.x >> 16; }
@@ -65,6 +70,8 @@ struct BatchTables {
   const uint32_t* rankInOff;     // [T+1]
   const uint32_t* rankOutOff;    // [T+1]
   const uint32_t* remoteIn;      // [T*M]
+  const uint2* hdr2;             // [T*M]
+  const uint2* relEdges;         // all ranks, rank r at rankInOff[r] (as many relax entries as in-edges)
   const double* tsE;             // [32 syms][4 bases][4 observed] (score+noGap)+sub: traceback association (src/viterbi.cpp:255)
   double symScore[kMaxSyms];     // log(symProb) per symbol id (0 for id 0)
   double tsDext[kMaxSyms];       // score+delExtend (src/viterbi.cpp:272)
@@ -94,17 +101,17 @@ struct BatchArgs {
   uint32_t* teamPassive;         // [nTeams][2] passive CTAs of the current column, by column parity, zeroed before every launch
   unsigned long long* barrier;   // [nTeams] team barrier counters (monotonic), zeroed before every launch
   double* loglike;               // [nReads] global mode
-  double* partVal;               // [nGroups][T][32] local mode: per-CTA best final S ...
+  double* partVal;               // [nGroups][T*warps][32] local mode: per-warp best final S ...
   uint32_t* partOrig;            //   ... and its reference state (first maximum in reference order)
   double* cells;                 // optional dump of slot 0 of group 0: [(L+1)][nStates][k+2]
   unsigned long long* dbg;       // optional [16] counters
 };
 
 struct BatchLayout {
-  uint32_t sd, maskA, maskB, remIn, hdr, inE, outE, tsE, sub, ctl, red, total;
+  uint32_t sd, maskA, maskB, remIn, hdr, hdr2, inE, relE, outE, tsE, sub, ctl, total;
 };
 
-__host__ __device__ inline BatchLayout makeBatchLayout(uint32_t M, uint32_t maxIn, uint32_t maxOut, uint32_t warps, bool team) {
+__host__ __device__ inline BatchLayout makeBatchLayout(uint32_t M, uint32_t maxIn, uint32_t maxOut, uint32_t nSyms, bool team) {
   BatchLayout L;
   uint32_t at = 0;
   auto take = [&](uint32_t bytes) {
@@ -117,19 +124,20 @@ __host__ __device__ inline BatchLayout makeBatchLayout(uint32_t M, uint32_t maxI
   L.maskB = take(M * 4);
   L.remIn = team ? take(M * 4) : 0;
   L.hdr = take(M * 16);
+  L.hdr2 = take(M * 8);
   L.inE = take((maxIn + 1) * 8);
+  L.relE = take((maxIn + 1) * 8);
   L.outE = take((maxOut + 1) * 4);
-  L.tsE = take(32 * 16 * 8);
+  L.tsE = take(nSyms * 16 * 8);
   L.sub = take(16 * 8);
   L.ctl = take(64 * 4);
-  L.red = take(warps * 32 * 12);
   L.total = at;
   return L;
 }
 
 // reference-order CSR tables for the traceback over batch-layout records
 struct BatchTraceTables {
-  uint32_t nStates, k, local, T;
+  uint32_t nStates, k, local, T;  // T = per-group partial maxima in local mode (CTAs x warps)
   const uint32_t* emitOff;
   const uint32_t* emitSrc;
   const uint8_t* emitSym;

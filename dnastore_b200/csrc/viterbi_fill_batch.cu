@@ -99,25 +99,26 @@ __global__ void __launch_bounds__(W * 32, 1)
   const uint32_t team = kTeam ? blockIdx.x / T : blockIdx.x, rank = kTeam ? blockIdx.x - team * T : 0u;
   const uint32_t nSlots = (M + W - 1) / W;
   const double NEG = negInf();
-  const BatchLayout lay = makeBatchLayout(M, tb.maxIn, tb.maxOut, W, kTeam);
+  const BatchLayout lay = makeBatchLayout(M, tb.maxIn, tb.maxOut, tb.nSyms, kTeam);
 
   const uint32_t aSD = smemAddr(smem + lay.sd);
   uint32_t* maskCur = reinterpret_cast<uint32_t*>(smem + lay.maskA);
   uint32_t* maskNext = reinterpret_cast<uint32_t*>(smem + lay.maskB);
   uint32_t* remInS = reinterpret_cast<uint32_t*>(smem + lay.remIn);
   uint4* hdrS = reinterpret_cast<uint4*>(smem + lay.hdr);
+  uint2* hdr2S = reinterpret_cast<uint2*>(smem + lay.hdr2);
   uint2* inS = reinterpret_cast<uint2*>(smem + lay.inE);
+  uint2* relS = reinterpret_cast<uint2*>(smem + lay.relE);
   uint32_t* outS = reinterpret_cast<uint32_t*>(smem + lay.outE);
   double* tsE = reinterpret_cast<double*>(smem + lay.tsE);
   double* subS = reinterpret_cast<double*>(smem + lay.sub);
   volatile uint32_t* ctl = reinterpret_cast<volatile uint32_t*>(smem + lay.ctl);
-  double* redV = reinterpret_cast<double*>(smem + lay.red);
-  uint32_t* redO = reinterpret_cast<uint32_t*>(smem + lay.red + W * 32 * 8);
 
   // ---- the CTA's slice of the tables, resident for the whole launch; local sources become row addresses ----
   {
     for (uint32_t i = tid; i < M; i += nThreads) {
       hdrS[i] = tb.hdr[rank * M + i];
+      hdr2S[i] = tb.hdr2[rank * M + i];
       if (kTeam) remInS[i] = tb.remoteIn[rank * M + i];
       maskCur[i] = 0;
       maskNext[i] = 0;
@@ -127,10 +128,18 @@ __global__ void __launch_bounds__(W * 32, 1)
       uint2 e = tb.inEdges[inBase + i];
       if (!beRemote(e)) e.x = aSD + (e.x - rank * M) * 512u;
       inS[i] = e;
+      uint2 q = tb.relEdges[inBase + i];  // relax entries: local ones come first (hdr2 counts), remote ones keep g
+      relS[i] = q;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < M; i += nThreads) {
+      const uint2 h2 = hdr2S[i];
+      const uint32_t nLoc = (h2.y & 0xFFu) + ((h2.y >> 8) & 0xFFu);
+      for (uint32_t j = 0; j < nLoc; ++j) relS[h2.x + j].x = aSD + (relS[h2.x + j].x - rank * M) * 512u;
     }
     const uint32_t outBase = tb.rankOutOff[rank], nOut = tb.rankOutOff[rank + 1] - outBase;
     for (uint32_t i = tid; i < nOut; i += nThreads) outS[i] = tb.outEdges[outBase + i];
-    for (uint32_t i = tid; i < 512; i += nThreads) tsE[i] = tb.tsE[i];
+    for (uint32_t i = tid; i < tb.nSyms * 16; i += nThreads) tsE[i] = tb.tsE[i];
     if (tid < 16) subS[tid] = tb.sub[tid];
     if (tid < 64) ctl[tid] = 0;
   }
@@ -219,46 +228,69 @@ __global__ void __launch_bounds__(W * 32, 1)
       auto relax = [&](uint32_t sl, uint32_t m, bool allIn) -> bool {
         const uint32_t d = sl * W + warp;
         const uint4 h = hdrS[d];
-        const uint32_t inOff = bhInOff(h), nE = bhNEmit(h), nIn = nE + bhNNull(h);
+        const uint2 h2 = hdr2S[d];
+        const uint32_t nLE = h2.y & 0xFFu, nLN = (h2.y >> 8) & 0xFFu, nRE = (h2.y >> 16) & 0xFFu, nRN = h2.y >> 24;
+        const uint32_t eLN = nLE + nLN, eRE = eLN + nRE, nIn = eRE + nRN;
+        const uint2* const rel = relS + h2.x;
         const uint32_t aOwn = aSD + d * 512u + lane16;
         const double2 own = ldsRow(aOwn);
         double s = own.x, dd = own.y;
-        auto rowOf = [&](const uint2& e) -> double2 {
-          if (kTeam && beRemote(e)) return ldPub2(sdPubCol + (size_t)e.x * 32 + lane);
-          return ldsRow(e.x + lane16);
-        };
-        auto edgeE = [&](uint32_t j) {
-          const uint2 e = inS[inOff + j];
-          const double2 v = rowOf(e);
-          dd = dmax(dd, dmax(v.y + tb.delExtend, v.x + tb.delOpen) + tb.symScore[beSym(e)]);  // :124-125
+        const char* const scoreBase = reinterpret_cast<const char*>(tb.symScore);
+        auto scoreOf = [&](const uint2& e) { return *reinterpret_cast<const double*>(scoreBase + e.y); };
+        auto emitFrom = [&](const double2 v, const uint2& e) {
+          dd = dmax(dd, dmax(v.y + tb.delExtend, v.x + tb.delOpen) + scoreOf(e));  // :124-125
           if (kDebug) ++dbgEdges;
         };
-        auto edgeN = [&](uint32_t j) {
-          const uint2 e = inS[inOff + j];
-          const double2 v = rowOf(e);
-          const double sc = tb.symScore[beSym(e)];
+        auto nullFrom = [&](const double2 v, const uint2& e) {
+          const double sc = scoreOf(e);
           dd = dmax(dd, v.y + sc);  // :140
           s = dmax(s, v.x + sc);    // :147 (:98-99)
           if (kDebug) ++dbgEdges;
         };
+        auto one = [&](uint32_t j) {
+          const uint2 e = rel[j];
+          if (j < eLN) {
+            const double2 v = ldsRow(e.x + lane16);
+            if (j < nLE)
+              emitFrom(v, e);
+            else
+              nullFrom(v, e);
+          } else if (kTeam) {
+            const double2 v = ldPub2(sdPubCol + (size_t)e.x * 32 + lane);
+            if (j < eRE)
+              emitFrom(v, e);
+            else
+              nullFrom(v, e);
+          }
+        };
         if (allIn || nIn <= 4u) {  // few transitions: relaxing all of them is cheaper than walking the mask
           uint32_t j = 0;
-          for (; j < nE; ++j) edgeE(j);
-          for (; j < nIn; ++j) edgeN(j);
+          for (; j < nLE; ++j) {
+            const uint2 e = rel[j];
+            emitFrom(ldsRow(e.x + lane16), e);
+          }
+          for (; j < eLN; ++j) {
+            const uint2 e = rel[j];
+            nullFrom(ldsRow(e.x + lane16), e);
+          }
+          if (kTeam) {
+            for (; j < eRE; ++j) {
+              const uint2 e = rel[j];
+              emitFrom(ldPub2(sdPubCol + (size_t)e.x * 32 + lane), e);
+            }
+            for (; j < nIn; ++j) {
+              const uint2 e = rel[j];
+              nullFrom(ldPub2(sdPubCol + (size_t)e.x * 32 + lane), e);
+            }
+          }
         } else {
           while (m) {
             const uint32_t j = (uint32_t)__ffs((int)m) - 1u;
             m &= m - 1u;
-            if (j == 31u) {
-              for (uint32_t jj = 31; jj < nIn; ++jj)
-                if (jj < nE)
-                  edgeE(jj);
-                else
-                  edgeN(jj);
-            } else if (j < nE)
-              edgeE(j);
+            if (j == 31u)
+              for (uint32_t jj = 31; jj < nIn; ++jj) one(jj);
             else
-              edgeN(j);
+              one(j);
           }
         }
         s = dmax(s, dd + tb.delEnd);  // :119-121
@@ -534,24 +566,9 @@ __global__ void __launch_bounds__(W * 32, 1)
             bo = orig;
           }
         }
-        if (tb.local && __any_sync(0xFFFFFFFFu, pos == L)) {  // :171-173, :240-242 (uniform over the CTA: L is per lane)
-          redV[warp * 32 + lane] = bv;
-          redO[warp * 32 + lane] = bo;
-          __syncthreads();
-          if (warp == 0) {
-            for (uint32_t w = 1; w < (uint32_t)W; ++w) {
-              const double v = redV[w * 32 + lane];
-              const uint32_t o = redO[w * 32 + lane];
-              if (v > bv || (v == bv && o < bo)) {
-                bv = v;
-                bo = o;
-              }
-            }
-            if (pos == L) {
-              args.partVal[((size_t)group * T + rank) * 32 + lane] = bv;
-              args.partOrig[((size_t)group * T + rank) * 32 + lane] = bo;
-            }
-          }
+        if (tb.local && pos == L) {  // :171-173, :240-242: this warp's share; the traceback kernel reduces over warps and CTAs
+          args.partVal[((size_t)group * T * W + rank * W + warp) * 32 + lane] = bv;
+          args.partOrig[((size_t)group * T * W + rank * W + warp) * 32 + lane] = bo;
         }
       }
       __syncthreads();  // rows of this column are dead: the next column's S0 may overwrite them

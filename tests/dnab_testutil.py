@@ -29,6 +29,21 @@ def load_golden():
     return cases
 
 
+@functools.lru_cache(maxsize=None)
+def load_golden_r2():
+    """Round-2 golden set (make_golden_r2.py): the benchmark read distributions at full length, run through the
+    unmodified reference -- dict(cases=[...], cells=[...])."""
+    import gzip
+    return json.load(gzip.open(os.path.join(GOLDEN, "viterbi_golden_r2.json.gz"), "rt"))
+
+
+def golden_r2_case(name):
+    for c in load_golden_r2()["cases"]:
+        if c["name"] == name:
+            return c
+    raise KeyError(name)
+
+
 def golden_case(name):
     for c in load_golden():
         if c["name"] == name:

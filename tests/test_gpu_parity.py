@@ -195,3 +195,114 @@ def test_gpu_cli_matches_reference_cli_output(d, tmp_path):
                           "--error-sub-prob", "0", "--error-dup-prob", "0", "--error-del-open", "0", "--error-global",
                           "--raw"], capture_output=True, text=True, check=True).stdout
     assert out == case["reads"][0]["decoded"] + "\n"
+
+
+# ----------------------------------------------------------------------------------------------
+# round 2: the read-batched kernel (viterbi_fill_batch.cu, option kernel=1) and the benchmark-scale goldens
+# ----------------------------------------------------------------------------------------------
+R2_CASES = [c["name"] for c in util.load_golden_r2()["cases"]]
+
+
+def _check_reads(d, dec, case, tag):
+    reads = [r["seq"] for r in case["reads"]]
+    out = dec.viterbi(reads, want_path=True)
+    for i, r in enumerate(case["reads"]):
+        assert out["decoded"][i] == r["decoded"], (tag, r["name"])
+        assert util.hexf(out["loglike"][i]) == util.hexf(r["loglike_hex"]), (tag, r["name"])
+        assert out["path"][i].tolist() == r["path"], (tag, r["name"])
+        assert out["status"][i] == (d.READ_NO_DECODING if r["loglike"] == "-inf" else d.READ_OK), (tag, r["name"])
+
+
+@pytest.mark.parametrize("name", R2_CASES)
+def test_gpu_round2_goldens_default_kernel(d, name):
+    """The benchmark read distributions at full length -- 64 reads of the headline 46,670-state workload, 32 of each
+    other BASELINE machine, 8 of dnastore-l10 -- against the UNMODIFIED reference: log-likelihood bits, decoded string,
+    traceback path, through whichever kernel the decoder picks by itself."""
+    case = util.golden_r2_case(name)
+    _check_reads(d, d.Decoder(util.compiled_for_case(case), device=0), case, name)
+
+
+@pytest.mark.parametrize("name", CASES + R2_CASES)
+def test_gpu_batch_kernel_matches_reference_golden(d, name):
+    """Every golden case through the read-batched kernel (32 reads are the lanes of a warp; teams of 1-148 CTAs)."""
+    case = util.golden_case(name) if name in CASES else util.golden_r2_case(name)
+    dec = d.Decoder(util.compiled_for_case(case), device=0)
+    dec.set_option("kernel", 1)
+    try:
+        info = dec.batch_info()
+    except d.DnabError as e:
+        pytest.skip(f"machine does not fit the shared memory of the GPU at 32 reads per group: {e}")
+    assert info["enabled"] == 1 and info["reads_per_group"] == 32
+    _check_reads(d, dec, case, (name, info["team_size"]))
+
+
+@pytest.mark.parametrize("team,warps", [(1, 16), (1, 32), (2, 24), (3, 16), (7, 32), (16, 24)])
+@pytest.mark.parametrize("name", ["l4c4_global_mixed", "l4c4_local_mixed", "l4c4_len12_local", "mr2l4c4_local"])
+def test_gpu_batch_kernel_every_team_size(d, name, team, warps):
+    """How many CTAs share a group (and how their states are partitioned), and how many warps a CTA has, are
+    placement choices: no bit may change."""
+    case = util.golden_case(name)
+    dec = d.Decoder(util.compiled_for_case(case), device=0)
+    dec.set_option("kernel", 1)
+    dec.set_option("team_size", team)
+    dec.set_option("warps_per_cta", warps)
+    try:
+        info = dec.batch_info()
+    except d.DnabError:
+        pytest.skip("this team size cannot hold the machine")
+    assert info["team_size"] == team
+    _check_reads(d, dec, case, (name, team, warps))
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_gpu_cfg2_cells_hash(d, kernel):
+    """Every DP cell of a short read on the 46,670-state machine (global and local mode) hashes to the reference's
+    matrix: cell-exactness on a 4-CTA cluster (push kernel) and on a 148-CTA team (read-batched kernel)."""
+    import hashlib
+    for c in util.load_golden_r2()["cells"]:
+        dec = d.Decoder(util.compiled_for(c["recipe"], c["flags"], c["global_"]), device=0)
+        dec.set_option("kernel", kernel)
+        ll, cells = dec.viterbi_cells(c["seq"])
+        assert cells.size == c["n_cells"]
+        assert hashlib.sha256(cells.tobytes()).hexdigest() == c["sha256"], (c["name"], kernel)
+        assert util.hexf(ll) == util.hexf(c["loglike_hex"])
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_gpu_production_kernel_end_cells_by_prefix(d, kernel):
+    """The cell dump runs an instrumented instantiation; the PRODUCTION instantiation is held to the reference's cells
+    through a debug-free path: the log-likelihood of the p-base prefix of a read is the cell S(end, p) of the full
+    read's matrix (global mode), so decoding every prefix in one batch checks one cell per column, bit for bit."""
+    z = np.load(f"{util.GOLDEN}/cells_l4c4_global.npz")
+    flags = json.loads(str(z["flags"]))
+    compiled = util.compiled_for([str(x) for x in z["recipe"]], flags, True)
+    seq = str(z["seq"])
+    n, k = compiled.t.n_states, compiled.t.k
+    cells = z["cells"].reshape(len(seq) + 1, n, k + 2)
+    dec = d.Decoder(compiled, device=0)
+    dec.set_option("kernel", kernel)
+    out = dec.viterbi([seq[:p] for p in range(len(seq) + 1)])
+    for p in range(len(seq) + 1):
+        assert util.hexf(out["loglike"][p]) == util.hexf(float(cells[p, n - 1, 0])), p
+
+
+@pytest.mark.parametrize("workload,n", [("cfg1", 3000), ("cfg4", 400), ("cfg2", 99), ("cfg5", 300)])
+def test_gpu_batch_and_push_kernels_agree_at_batch_scale(d, workload, n):
+    """Read-batched kernel (groups of 32 reads sorted by length, several groups per team, ragged last group) against
+    the one-read-per-cluster push kernel on a batch far larger than the goldens: same bits, same strings, same paths."""
+    import bench
+    w = bench.WORKLOADS[workload]
+    compiled = util.machine_from_recipe(w["recipe"]).compile(d.ErrorFlags(length=w["length"], global_=True))
+    reads = bench.make_reads(w, n, seed=777)
+    reads[3] = reads[3][:17]  # ragged: short, empty and long reads share groups
+    reads[5] = ""
+    outs = []
+    for kern in (1, 2):
+        dec = d.Decoder(compiled, device=0)
+        dec.set_option("kernel", kern)
+        outs.append(dec.viterbi(reads, want_path=True))
+    a, b = outs
+    assert a["loglike"].tobytes() == b["loglike"].tobytes()
+    assert a["decoded"] == b["decoded"]
+    assert (a["status"] == b["status"]).all()
+    assert all(x.tolist() == y.tolist() for x, y in zip(a["path"], b["path"]))

@@ -58,3 +58,28 @@ def test_oracle_empty_read():
     compiled = util.compiled_for(["l4c4"], dict(length=4), True)
     o = util.oracle_viterbi(compiled, "")
     assert o["rc"] == 0 and o["decoded"] == "^$" and o["loglike"] < 0
+
+
+@pytest.mark.parametrize("name,n", [("cfg1_bench", 64), ("cfg4_bench", 6), ("cfg3_bench", 3), ("cfg5_bench", 3), ("cfg2_bench", 1)])
+def test_oracle_matches_round2_goldens(name, n):
+    """The benchmark read distributions at full length (make_golden_r2.py, unmodified reference): the oracle
+    reproduces log-likelihood, decoded string and traceback path bit for bit (a bounded sample per machine keeps
+    the CPU suite short; the GPU tests check every read)."""
+    case = util.golden_r2_case(name)
+    compiled = util.compiled_for_case(case)
+    for r in case["reads"][:n]:
+        o = util.oracle_viterbi(compiled, r["seq"])
+        assert o["decoded"] == r["decoded"], (name, r["name"])
+        assert util.hexf(o["loglike"]) == util.hexf(r["loglike_hex"]), (name, r["name"])
+        assert o["path"] == r["path"], (name, r["name"])
+
+
+def test_oracle_cfg2_cells_hash():
+    """Every DP cell of a short read on the 46,670-state machine: the oracle's matrix hashes to the reference's."""
+    import hashlib
+    for c in util.load_golden_r2()["cells"]:
+        compiled = util.compiled_for(c["recipe"], c["flags"], c["global_"])
+        o = util.oracle_viterbi(compiled, c["seq"], want_cells=True)
+        assert o["cells"].size == c["n_cells"]
+        assert hashlib.sha256(o["cells"].tobytes()).hexdigest() == c["sha256"], c["name"]
+        assert util.hexf(o["loglike"]) == util.hexf(c["loglike_hex"])
