@@ -12,6 +12,7 @@ from ._capi import (  # noqa: F401
     ErrorFlags,
     Compiled,
     Decoder,
+    MultiDecoder,
     Tables,
     lib,
     lib_path,
@@ -34,7 +35,7 @@ from ._capi import (  # noqa: F401
 )
 
 __all__ = [
-    "DnabError", "Machine", "ErrorFlags", "Compiled", "Decoder", "Tables", "lib", "lib_path", "pack_reads", "MutatorParams", "MutatorCounts", "PairDb",
+    "DnabError", "Machine", "ErrorFlags", "Compiled", "Decoder", "MultiDecoder", "Tables", "lib", "lib_path", "pack_reads", "MutatorParams", "MutatorCounts", "PairDb",
     "pairhmm_fb_batch", "expected_counts", "baum_welch",
     "ExactDecoder", "exact_decode_bits", "exact_decode_string", "exact_decode_fasta", "pack_decoded_symbols",
     "READ_OK", "READ_NO_DECODING", "READ_OVERFLOW", "READ_TRACEBACK_FAILED",

@@ -63,6 +63,11 @@ class BatchInfo(C.Structure):
                                           "smem_bytes_per_cta", "n_teams", "reserved")] + [("cross_cta_transition_fraction", C.c_double)]
 
 
+class PipelineStats(C.Structure):
+    _fields_ = [("reads", C.c_int64), ("chunks", C.c_int64), ("overflow_reruns", C.c_int64), ("parse_seconds", C.c_double),
+                ("decode_busy_seconds", C.c_double), ("wall_seconds", C.c_double)]
+
+
 class DecoderStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("fill_launches", C.c_uint64), ("traceback_launches", C.c_uint64),
                 ("reads", C.c_uint64), ("cells", C.c_uint64), ("last_fill_ms", C.c_double), ("last_traceback_ms", C.c_double),
@@ -177,6 +182,14 @@ _sig("dnab_expected_counts", C.c_int, C.c_int, C.POINTER(MutatorParams), _vp, C.
 _sig("dnab_baum_welch", C.c_int, C.c_int, C.POINTER(MutatorParams), _vp, C.c_int, C.POINTER(MutatorParams),
      C.POINTER(C.c_int32))
 _sig("dnab_decode_fasta", _vp, _vp, C.c_char_p)
+_sig("dnab_multi_decoder_create", _vp, _vp, _vp, C.c_int)
+_sig("dnab_multi_decoder_destroy", None, _vp)
+_sig("dnab_multi_decoder_count", C.c_int, _vp)
+_sig("dnab_multi_decoder_at", _vp, _vp, C.c_int)
+_sig("dnab_multi_decoder_set_option", C.c_int, _vp, C.c_char_p, C.c_int64)
+_sig("dnab_viterbi_batch_multi", C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp)
+_sig("dnab_decode_fasta_multi", _vp, _vp, C.c_char_p)
+_sig("dnab_multi_decoder_last_stats", C.c_int, _vp, _vp)
 _sig("dnab_decoded_count", C.c_int64, _vp)
 _sig("dnab_decoded_name", C.c_char_p, _vp, C.c_int64)
 _sig("dnab_decoded_seq", C.c_char_p, _vp, C.c_int64)
@@ -646,4 +659,66 @@ class Decoder:
     def __del__(self):
         if getattr(self, "_h", None):
             lib.dnab_decoder_destroy(self._h)
+            self._h = None
+
+
+def _decoded_set(s):
+    if not s:
+        raise _err()
+    try:
+        return [(lib.dnab_decoded_name(s, i).decode(), lib.dnab_decoded_seq(s, i).decode("latin1"),
+                 lib.dnab_decoded_loglike(s, i), lib.dnab_decoded_status(s, i))
+                for i in range(lib.dnab_decoded_count(s))]
+    finally:
+        lib.dnab_decoded_free(s)
+
+
+class MultiDecoder:
+    """One decoder per listed device (a device may be listed twice), one host thread each; batches are cut into chunks
+    handed out dynamically, results come back in input order (include/dnastore_b200.h dnab_multi_decoder)."""
+
+    def __init__(self, compiled, devices):
+        self._compiled = compiled
+        devs = np.asarray(list(devices), dtype=np.int32)
+        h = lib.dnab_multi_decoder_create(compiled.tables, _ptr(devs), len(devs))
+        if not h:
+            raise _err(-2)
+        self._h = h
+        self.devices = [int(x) for x in devs]
+
+    def set_option(self, key, value):
+        """"chunk_reads", "decoded_slot_bytes", or any decoder option (applied to every device)."""
+        rc = lib.dnab_multi_decoder_set_option(self._h, key.encode(), int(value))
+        if rc:
+            raise _err(rc)
+
+    def stats(self):
+        s = PipelineStats()
+        lib.dnab_multi_decoder_last_stats(self._h, C.byref(s))
+        return {n: getattr(s, n) for n, _ in PipelineStats._fields_}
+
+    def viterbi(self, reads, decoded_stride=None):
+        packed, byte_off, read_len = pack_reads(reads)
+        return self.viterbi_packed(packed, byte_off, read_len, decoded_stride)
+
+    def viterbi_packed(self, packed, byte_off, read_len, decoded_stride=None, out=None):
+        n = len(read_len)
+        max_len = int(read_len.max()) if n else 0
+        stride = int(decoded_stride or (8 * max_len + 1024))
+        if out is None:
+            out = dict(loglike=np.zeros(n, dtype=np.float64), raw=np.zeros((n, stride), dtype=np.uint8),
+                       decoded_len=np.zeros(n, dtype=np.int32), status=np.zeros(n, dtype=np.int32))
+        rc = lib.dnab_viterbi_batch_multi(self._h, n, _ptr(packed), _ptr(byte_off), _ptr(read_len), _ptr(out["loglike"]),
+                                          _ptr(out["raw"]), stride, _ptr(out["decoded_len"]), _ptr(out["status"]))
+        if rc:
+            raise _err(rc)
+        out["decoded"] = [bytes(out["raw"][i, :out["decoded_len"][i]]).decode("latin1") for i in range(n)]
+        return out
+
+    def decode_fasta(self, path):
+        return _decoded_set(lib.dnab_decode_fasta_multi(self._h, os.fspath(path).encode()))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.dnab_multi_decoder_destroy(self._h)
             self._h = None

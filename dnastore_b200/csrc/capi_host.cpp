@@ -10,6 +10,7 @@
 
 #include "../../include/dnastore_b200.h"
 #include "capi_error.h"
+#include "capi_types.h"
 #include "host/exact_decoder.h"
 #include "host/fasta.h"
 #include "host/machine.h"
@@ -35,11 +36,6 @@ struct dnab_exact_decoder {
 };
 struct dnab_pair_db {
   std::vector<PairAlignment> aligns;
-};
-struct dnab_decoded_set {
-  std::vector<std::string> names, seqs;
-  std::vector<double> loglike;
-  std::vector<int32_t> status;
 };
 
 template <class F>
@@ -156,63 +152,6 @@ int dnab_pack_reads(const char* bases, const int64_t* base_off, int64_t n_reads,
   return DNAB_OK;
 }
 
-dnab_decoded_set* dnab_decode_fasta(dnab_decoder* d, const char* fasta_path) {
-  if (!d || !fasta_path) {
-    setLastError("dnab_decode_fasta: null argument");
-    return nullptr;
-  }
-  return guarded(
-      [&]() -> dnab_decoded_set* {
-        const std::vector<FastSeq> reads = readFastSeqs(fasta_path);
-        const int64_t n = (int64_t)reads.size();
-        auto* out = new dnab_decoded_set();
-        if (n == 0) return out;
-        std::string bases;
-        std::vector<int64_t> baseOff(n + 1, 0);
-        for (int64_t r = 0; r < n; ++r) {
-          bases += reads[r].seq;
-          baseOff[r + 1] = (int64_t)bases.size();
-        }
-        std::vector<int32_t> len(n);
-        for (int64_t r = 0; r < n; ++r) len[r] = (int32_t)reads[r].seq.size();
-        std::vector<uint8_t> packed(packedSize(len.data(), n));
-        std::vector<int64_t> byteOff(n);
-        char bad = 0;
-        const int64_t badRead = packReads(bases.data(), baseOff.data(), n, packed.data(), byteOff.data(), len.data(), &bad);
-        if (badRead >= 0) {
-          delete out;
-          throw std::runtime_error(std::string("Unknown symbol ") + bad + " in sequence " + reads[badRead].name +
-                                   " (alphabet is ACGT)");
-        }
-        int32_t maxLen = 0;
-        for (int32_t l : len) maxLen = std::max(maxLen, l);
-        int32_t stride = 8 * maxLen + 1024;
-        std::vector<double> ll(n);
-        std::vector<int32_t> decLen(n), status(n);
-        std::vector<char> dec;
-        for (int attempt = 0; attempt < 4; ++attempt) {
-          dec.assign((size_t)n * stride, 0);
-          const int rc = dnab_viterbi_batch(d, n, packed.data(), byteOff.data(), len.data(), ll.data(), dec.data(), stride,
-                                            decLen.data(), status.data(), nullptr, 0, nullptr);
-          if (rc != DNAB_OK) {
-            delete out;
-            throw std::runtime_error(dnab_last_error());
-          }
-          bool overflow = false;
-          for (int32_t s : status) overflow |= (s == DNAB_READ_OVERFLOW);
-          if (!overflow) break;
-          stride *= 8;
-        }
-        out->loglike = ll;
-        out->status = status;
-        for (int64_t r = 0; r < n; ++r) {
-          out->names.push_back(reads[r].name);
-          out->seqs.emplace_back(dec.data() + (size_t)r * stride, (size_t)decLen[r]);
-        }
-        return out;
-      },
-      (dnab_decoded_set*)nullptr);
-}
 int64_t dnab_decoded_count(const dnab_decoded_set* s) { return s ? (int64_t)s->seqs.size() : 0; }
 const char* dnab_decoded_name(const dnab_decoded_set* s, int64_t i) { return s->names[i].c_str(); }
 const char* dnab_decoded_seq(const dnab_decoded_set* s, int64_t i) { return s->seqs[i].c_str(); }

@@ -16,6 +16,7 @@
 //   --error-del-open (.001) --error-del-ext (.01) --error-global  -F/--error-file
 //   -v/--verbose N                accepted (0 = quiet); >=2 prints decoder info to stderr
 //   --device N                    CUDA ordinal (new)
+//   --devices A,B,...             decode on several GPUs of this node, reads sharded over them, output in input order (new)
 // Machine construction (-l without -L), the exact codec (-e/-d/-E/-D/-b/-B) and error
 // model fitting are outside this build's scope and are reported as such.
 #include <cstdio>
@@ -40,6 +41,7 @@ int main(int argc, char** argv) {
   std::vector<std::string> composes;
   bool raw = false;
   int verbose = 2, device = 0;
+  std::vector<int> devices;
 
   auto longName = [](const std::string& a, std::string& name, std::string& val, bool& hasVal) {
     name = a.substr(2);
@@ -96,6 +98,17 @@ int main(int argc, char** argv) {
     else if (name == "error-file") errorFile = need();
     else if (name == "verbose") verbose = std::atoi(need().c_str());
     else if (name == "device") device = std::atoi(need().c_str());
+    else if (name == "devices") {
+      std::string list = need(), item;
+      for (size_t p = 0; p <= list.size(); ++p) {
+        if (p == list.size() || list[p] == ',') {
+          if (!item.empty()) devices.push_back(std::atoi(item.c_str()));
+          item.clear();
+        } else
+          item.push_back(list[p]);
+      }
+      if (devices.empty()) die("--devices needs a comma-separated list of CUDA ordinals");
+    }
     else if (name == "nocolor") {}
     else if (name == "log") (void)need();
     else
@@ -194,8 +207,10 @@ int main(int argc, char** argv) {
       std::cerr << msg << std::endl;
       return msg.find("cyclic") != std::string::npos ? 0 : 1;
     }
-    dnab_decoder* dec = dnab_decoder_create(dnab_compiled_tables(compiled), device);
-    if (!dec) die(dnab_last_error(), 3);
+    if (devices.empty()) devices.push_back(device);
+    dnab_multi_decoder* multi = dnab_multi_decoder_create(dnab_compiled_tables(compiled), devices.data(), (int)devices.size());
+    if (!multi) die(dnab_last_error(), 3);
+    dnab_decoder* dec = dnab_multi_decoder_at(multi, 0);
     if (verbose >= 3) {
       dnab_decoder_info info;
       if (dnab_decoder_get_info(dec, &info) == DNAB_OK)
@@ -203,7 +218,7 @@ int main(int argc, char** argv) {
                   << " CTAs x " << info.threads_per_cta << " threads, " << info.states_per_cta << " states/CTA, "
                   << info.smem_bytes_per_cta << " B smem, " << info.n_clusters << " reads in flight" << std::endl;
     }
-    dnab_decoded_set* out = dnab_decode_fasta(dec, viterbiFile.c_str());
+    dnab_decoded_set* out = dnab_decode_fasta_multi(multi, viterbiFile.c_str());
     if (!out) die(dnab_last_error(), 3);
     const int64_t n = dnab_decoded_count(out);
     for (int64_t i = 0; i < n; ++i) {
@@ -217,7 +232,14 @@ int main(int argc, char** argv) {
       }
     }
     dnab_decoded_free(out);
-    dnab_decoder_destroy(dec);
+    if (verbose >= 3) {
+      dnab_pipeline_stats ps;
+      if (dnab_multi_decoder_last_stats(multi, &ps) == DNAB_OK)
+        std::cerr << "pipeline: " << ps.reads << " reads in " << ps.chunks << " chunks on " << devices.size() << " device(s), parse "
+                  << ps.parse_seconds << " s, decode " << ps.decode_busy_seconds << " s (summed), wall " << ps.wall_seconds << " s, "
+                  << ps.overflow_reruns << " overflow re-decodes" << std::endl;
+    }
+    dnab_multi_decoder_destroy(multi);
     dnab_compiled_free(compiled);
   }
   dnab_machine_free(machine);

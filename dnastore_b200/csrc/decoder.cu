@@ -1307,6 +1307,20 @@ dnab_decoder* dnab_decoder_create(const dnab_tables* t, int device) {
     setLastError("duplication depth k=" + std::to_string(t->k) + " exceeds the supported maximum " + std::to_string(kMaxK));
     return nullptr;
   }
+  for (uint32_t e = 0; e < t->n_emit; ++e)
+    if (t->emit_src[e] >= t->n_states || t->emit_base[e] > 3) {
+      setLastError("dnab_decoder_create: emitting transition " + std::to_string(e) + " has a source or base out of range");
+      return nullptr;
+    }
+  for (uint32_t e = 0; e < t->n_null; ++e)
+    if (t->null_src[e] >= t->n_states) {
+      setLastError("dnab_decoder_create: null transition " + std::to_string(e) + " has a source out of range");
+      return nullptr;
+    }
+  if (t->emit_off[t->n_states] != t->n_emit || t->null_off[t->n_states] != t->n_null) {
+    setLastError("dnab_decoder_create: CSR offsets do not end at the transition counts");
+    return nullptr;
+  }
   auto* d = new dnab_decoder();
   d->device = device;
   cudaSetDevice(device);
@@ -1572,6 +1586,10 @@ static int viterbiHost(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   size_t packedBytes = 0;
   uint64_t cellsTotal = 0;
   for (int64_t r = 0; r < n; ++r) {
+    if (readLen[r] < 0 || byteOff[r] < 0 || (byteOff[r] & 15)) {
+      setLastError("dnab_viterbi_batch: read " + std::to_string(r) + " has a negative length or an offset that is not a multiple of 16");
+      return DNAB_EINVAL;
+    }
     maxLen = std::max(maxLen, readLen[r]);
     packedBytes = std::max<size_t>(packedBytes, (size_t)byteOff[r] + ((((size_t)readLen[r] + 3) / 4 + 15) & ~(size_t)15));
     cellsTotal += (uint64_t)d->nStates * (uint64_t)(readLen[r] + 1) * (d->k + 2);
@@ -1687,6 +1705,10 @@ static int forwardImpl(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   int32_t maxLen = 0;
   size_t packedBytes = 0;
   for (int64_t r = 0; r < n; ++r) {
+    if (readLen[r] < 0 || byteOff[r] < 0 || (byteOff[r] & 15)) {
+      setLastError("dnab_forward_batch: read " + std::to_string(r) + " has a negative length or an offset that is not a multiple of 16");
+      return DNAB_EINVAL;
+    }
     maxLen = std::max(maxLen, readLen[r]);
     packedBytes = std::max<size_t>(packedBytes, (size_t)byteOff[r] + ((((size_t)readLen[r] + 3) / 4 + 15) & ~(size_t)15));
   }

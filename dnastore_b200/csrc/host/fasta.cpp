@@ -52,12 +52,22 @@ void appendNonSpace(std::string& dst, const std::string& line) {
 
 }  // namespace
 
-std::vector<FastSeq> readFastSeqs(const std::string& filename) {
-  GzLines in(filename);
-  std::vector<FastSeq> seqs;
+struct FastSeqStream::Impl {
+  GzLines in;
   std::string line;
-  bool have = in.next(line);
-  while (have) {
+  bool have;
+  explicit Impl(const std::string& filename) : in(filename) { have = in.next(line); }
+};
+
+FastSeqStream::FastSeqStream(const std::string& filename) : impl(new Impl(filename)) {}
+FastSeqStream::~FastSeqStream() { delete impl; }
+
+bool FastSeqStream::next(size_t maxReads, size_t maxBases, std::vector<FastSeq>& out) {
+  GzLines& in = impl->in;
+  std::string& line = impl->line;
+  bool& have = impl->have;
+  size_t nReads = 0, nBases = 0;
+  while (have && nReads < maxReads && nBases < maxBases) {
     if (line.empty() || (line[0] != '>' && line[0] != '@')) {  // junk before a header
       have = in.next(line);
       continue;
@@ -77,7 +87,17 @@ std::vector<FastSeq> readFastSeqs(const std::string& filename) {
       while (fs.qual.size() < fs.seq.size() && (have = in.next(line))) appendNonSpace(fs.qual, line);
       have = in.next(line);
     }
-    seqs.push_back(std::move(fs));
+    ++nReads;
+    nBases += fs.seq.size();
+    out.push_back(std::move(fs));
+  }
+  return nReads > 0;
+}
+
+std::vector<FastSeq> readFastSeqs(const std::string& filename) {
+  FastSeqStream in(filename);
+  std::vector<FastSeq> seqs;
+  while (in.next(1u << 20, (size_t)1 << 30, seqs)) {
   }
   return seqs;
 }

@@ -16,6 +16,22 @@ struct FastSeq {
 };
 
 std::vector<FastSeq> readFastSeqs(const std::string& filename);
+
+// The same parser as readFastSeqs, one bounded chunk at a time (the ingest side of the decode pipeline): next()
+// appends records until it holds maxReads of them or maxBases bases and returns false once the file is exhausted
+// and nothing was appended.
+class FastSeqStream {
+ public:
+  explicit FastSeqStream(const std::string& filename);
+  ~FastSeqStream();
+  FastSeqStream(const FastSeqStream&) = delete;
+  FastSeqStream& operator=(const FastSeqStream&) = delete;
+  bool next(size_t maxReads, size_t maxBases, std::vector<FastSeq>& out);
+
+ private:
+  struct Impl;
+  Impl* impl;
+};
 void writeFastaSeqs(std::ostream& out, const std::vector<FastSeq>& seqs, size_t lineWidth = 50);
 
 // A,C,G,T -> 0..3 (case-insensitive); -1 otherwise.

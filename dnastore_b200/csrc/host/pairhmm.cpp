@@ -181,15 +181,17 @@ std::string MutatorCounts::asJSON() const {
 }
 
 const std::vector<double>& logSumExpLookupTable() {
-  static std::vector<double> table;
-  if (table.empty()) {
+  // a function-local static is initialised exactly once even when several host threads (one per device) make
+  // their first forward / pair-HMM call together
+  static const std::vector<double> table = []() {
     const int entries = ((int)(10 / .0001)) + 1;
-    table.resize(entries);
+    std::vector<double> t((size_t)entries);
     for (int n = 0; n < entries; ++n) {
       const double x = n * .0001;
-      table[n] = std::log(1. + std::exp(-x));
+      t[(size_t)n] = std::log(1. + std::exp(-x));
     }
-  }
+    return t;
+  }();
   return table;
 }
 

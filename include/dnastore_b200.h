@@ -259,6 +259,35 @@ double dnab_decoded_loglike(const dnab_decoded_set* s, int64_t i);
 int32_t dnab_decoded_status(const dnab_decoded_set* s, int64_t i);
 void dnab_decoded_free(dnab_decoded_set* s);
 
+/* ------------------------------------------------------------------------
+ * Several GPUs of one node, and the ingest/egress pipeline.  Reads are independent
+ * (src/viterbi.cpp:312-318 carries no state between them), so a batch is cut into chunks that one host thread
+ * per device decodes with its own decoder; no collective; results come back in input order.
+ * dnab_decode_fasta above is the one-device form of the same pipeline: the file is parsed and packed in bounded
+ * chunks by a producer thread (plain or gzip FASTA/FASTQ, src/fastseq.cpp:123-148) into page-locked buffers while the
+ * previous chunk is being copied and decoded, and only reads whose decoded string overflowed their slot are re-decoded.
+ * ---------------------------------------------------------------------- */
+typedef struct dnab_multi_decoder dnab_multi_decoder;
+dnab_multi_decoder* dnab_multi_decoder_create(const dnab_tables* t, const int* devices, int n_devices);
+void dnab_multi_decoder_destroy(dnab_multi_decoder* m);
+int dnab_multi_decoder_count(const dnab_multi_decoder* m);
+dnab_decoder* dnab_multi_decoder_at(dnab_multi_decoder* m, int i);            /* for dnab_decoder_set_option / stats */
+/* "chunk_reads" (0 = automatic), "decoded_slot_bytes" (bytes reserved per decoded string on the first attempt,
+ * 0 = 2*maxLen+256; overflowing reads are re-decoded with 4x); any other key goes to every device's decoder. */
+int dnab_multi_decoder_set_option(dnab_multi_decoder* m, const char* key, int64_t value);
+/* dnab_viterbi_batch over all devices of m: same buffers and meaning, host memory, path output not available. */
+int dnab_viterbi_batch_multi(dnab_multi_decoder* m, int64_t n_reads, const uint8_t* packed, const int64_t* read_byte_off,
+                             const int32_t* read_len, double* loglike, char* decoded, int32_t decoded_stride,
+                             int32_t* decoded_len, int32_t* status);
+dnab_decoded_set* dnab_decode_fasta_multi(dnab_multi_decoder* m, const char* fasta_path);
+typedef struct dnab_pipeline_stats {
+  int64_t reads, chunks, overflow_reruns;
+  double parse_seconds;        /* producer thread: parsing + 2-bit packing */
+  double decode_busy_seconds;  /* summed over the device threads: copies + kernels */
+  double wall_seconds;
+} dnab_pipeline_stats;
+int dnab_multi_decoder_last_stats(const dnab_multi_decoder* m, dnab_pipeline_stats* s);
+
 
 /* ------------------------------------------------------------------------
  * Exact (error-free) decoding on the host: dnastore's -d/--decode-file, --decode-string and

@@ -306,3 +306,90 @@ def test_gpu_batch_and_push_kernels_agree_at_batch_scale(d, workload, n):
     assert a["decoded"] == b["decoded"]
     assert (a["status"] == b["status"]).all()
     assert all(x.tolist() == y.tolist() for x, y in zip(a["path"], b["path"]))
+
+
+# ----------------------------------------------------------------------------------------------
+# several devices and the ingest pipeline (dnab_multi_decoder, dnab_decode_fasta[_multi])
+# ----------------------------------------------------------------------------------------------
+def _two_devices():
+    import torch
+    return [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]  # the same GPU twice still runs two decoders and two host threads
+
+
+def test_gpu_multi_decoder_matches_goldens(d):
+    """The product's multi-GPU entry (dnab_viterbi_batch_multi: chunks handed to one host thread and decoder per
+    device, results in input order) against the reference goldens, with two devices when the box has them."""
+    for name in ("cfg1_bench", "cfg4_bench", "cfg2_bench"):
+        case = util.golden_r2_case(name)
+        md = d.MultiDecoder(util.compiled_for_case(case), _two_devices())
+        md.set_option("chunk_reads", 8)  # many small chunks: both decoders get work, order must survive
+        reads = [r["seq"] for r in case["reads"]]
+        out = md.viterbi(reads)
+        assert md.stats()["chunks"] == (len(reads) + 7) // 8
+        for i, r in enumerate(case["reads"]):
+            assert out["decoded"][i] == r["decoded"], (name, i)
+            assert util.hexf(out["loglike"][i]) == util.hexf(r["loglike_hex"]), (name, i)
+
+
+def test_gpu_fasta_pipeline_chunks_gzip_fastq_and_overflow(d, tmp_path):
+    """dnab_decode_fasta_multi: the file is parsed in bounded chunks by a producer thread while earlier chunks are
+    decoded; gzip + FASTQ + multi-line records; a decoded-string slot far too small on the first attempt makes every
+    read overflow and be decoded again with a larger slot (only those reads).  Names, order and bits as the reference."""
+    import gzip
+    case = util.golden_r2_case("cfg1_bench")
+    fq = tmp_path / "reads.fq.gz"
+    with gzip.open(fq, "wt") as f:
+        for r in case["reads"]:
+            s = r["seq"]
+            f.write(f"@{r['name']} comment\n{s[:50]}\n{s[50:].lower()}\n+\n{'I' * len(s)}\n")
+    md = d.MultiDecoder(util.compiled_for_case(case), _two_devices())
+    md.set_option("chunk_reads", 5)
+    md.set_option("decoded_slot_bytes", 16)
+    got = md.decode_fasta(fq)
+    st = md.stats()
+    assert st["reads"] == len(case["reads"]) and st["chunks"] == (len(case["reads"]) + 4) // 5
+    assert st["overflow_reruns"] >= len(case["reads"])
+    assert [g[0] for g in got] == [r["name"] for r in case["reads"]]
+    for g, r in zip(got, case["reads"]):
+        assert g[1] == r["decoded"] and util.hexf(g[2]) == util.hexf(r["loglike_hex"]) and g[3] == d.READ_OK
+    # one device, default chunking, through dnab_decode_fasta
+    got1 = d.Decoder(util.compiled_for_case(case), device=0).decode_fasta(fq)
+    assert got1 == got
+
+
+def test_gpu_fasta_pipeline_reports_bad_base(d, tmp_path):
+    """A non-ACGT character terminates the reference (src/fastseq.cpp:25-39); here it is an error from the producer
+    thread that names the record."""
+    fa = tmp_path / "bad.fa"
+    fa.write_text(">ok\nACGT\n>broken\nACGNT\n")
+    dec = d.Decoder(util.compiled_for(["l4c4"], dict(length=4), True), device=0)
+    with pytest.raises(d.DnabError, match="Unknown symbol N in sequence broken"):
+        dec.decode_fasta(fa)
+
+
+def test_gpu_cli_devices_flag(d, tmp_path):
+    import os
+    import subprocess
+    case = util.golden_r2_case("cfg1_bench")
+    fa = tmp_path / "r.fa"
+    fa.write_text("".join(f">{r['name']}\n{r['seq']}\n" for r in case["reads"]))
+    exe = os.path.join(util.ROOT, "bin", "dnastore-b200")
+    devs = ",".join(str(x) for x in _two_devices())
+    out = subprocess.run([exe, "-v0", "-l", "4", "--load-machine", util.machine_path("l4c4"), "--decode-viterbi", str(fa),
+                          "--error-global", "--raw", "--devices", devs], capture_output=True, text=True, check=True).stdout
+    assert out.split("\n")[:-1] == [r["decoded"] for r in case["reads"]]
+
+
+def test_gpu_rejects_malformed_batches(d):
+    """Caller arrays are validated on the host before any launch (a misaligned offset would fault the context)."""
+    dec = d.Decoder(util.compiled_for(["l4c4"], dict(length=4), True), device=0)
+    packed, off, ln = d.pack_reads(["ACGTACGT", "TTTT"])
+    bad = off.copy()
+    bad[1] += 4
+    with pytest.raises(d.DnabError):
+        dec.viterbi_packed(packed, bad, ln)
+    neg = ln.copy()
+    neg[0] = -3
+    with pytest.raises(d.DnabError):
+        dec.viterbi_packed(packed, off, neg)
+    assert dec.viterbi(["ACGTACGT"])["status"][0] == d.READ_OK  # the handle is still usable
