@@ -454,9 +454,11 @@ def main():
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
+        host_group = dist.new_group(backend="gloo")  # host-side waits that leave no kernel spinning on an idle GPU
     dev = torch.device("cuda", local_rank)
     import dnab_testutil as util
     import dnastore_b200 as d
@@ -572,6 +574,12 @@ def main():
     dec = None
     torch.cuda.empty_cache()
     barrier()
+
+    def host_barrier():  # the other ranks' GPUs must be idle while rank 0 drives them: wait on the host (gloo), not in a NCCL kernel
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
+    host_barrier()
     if rank == 0:
         md = d.MultiDecoder(compiled, list(range(world)))
         for kv in args.opt:
@@ -592,7 +600,8 @@ def main():
         e2e_d2h = int(out["loglike"].nbytes + out["raw"].nbytes + out["decoded_len"].nbytes + out["status"].nbytes)
         e2e_ok = out["decoded"] == gathered_dec and out["loglike"].tolist() == gathered_ll and bool((out["status"] == 0).all())
         assert e2e_ok, "the multi-GPU entry and the sharded device path disagree"
-    barrier()
+        md = None
+    host_barrier()
 
     # ---- reduce over ranks: max time, summed work -------------------------------------------------------
     vals = torch.tensor([elapsed_ms, st["timed_fill_ms"], st["timed_traceback_ms"]], dtype=torch.float64, device=dev)

@@ -151,6 +151,8 @@ _sig("dnab_decoder_configure_ex", C.c_int, _vp, C.c_uint32, C.c_uint32)
 _sig("dnab_decoder_get_stats", C.c_int, _vp, C.POINTER(DecoderStats))
 _sig("dnab_decoder_set_timing", C.c_int, _vp, C.c_int)
 _sig("dnab_decoder_reset_timing", C.c_int, _vp)
+_sig("dnab_posterior_classes", C.c_int, _vp, C.c_char_p, C.c_size_t)
+_sig("dnab_posterior_batch", C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp)
 _sig("dnab_decoder_set_option", C.c_int, _vp, C.c_char_p, C.c_int64)
 _sig("dnab_decoder_get_batch_info", C.c_int, _vp, _vp)
 _sig("dnab_decoder_set_debug", C.c_int, _vp, C.c_int)
@@ -635,6 +637,33 @@ class Decoder:
         if rc:
             raise _err(rc)
         return dict(loglike=ll, loglike_back=llb, counts=counts, status=status)
+
+    def posterior_classes(self):
+        buf = C.create_string_buffer(64)
+        n = lib.dnab_posterior_classes(self._h, buf, 64)
+        if n < 0:
+            raise _err(n)
+        return buf.value.decode("latin1")
+
+    def posterior(self, reads, max_sweeps=0):
+        """Soft decoding (dnab_posterior_batch): per read an [L, n_classes] array of the posterior of the class of the move
+        that emitted each base, the per-base most probable class as a string, the forward log-likelihood."""
+        classes = self.posterior_classes()
+        packed, byte_off, read_len = pack_reads(reads)
+        n = len(read_len)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(read_len, out=off[1:])
+        post = np.zeros((int(off[-1]), len(classes)), dtype=np.float64)
+        dec = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+        ll = np.zeros(n, dtype=np.float64)
+        status = np.zeros(n, dtype=np.int32)
+        rc = lib.dnab_posterior_batch(self._h, n, _ptr(packed), _ptr(byte_off), _ptr(read_len), int(max_sweeps), _ptr(off),
+                                      _ptr(ll), _ptr(post), _ptr(dec), _ptr(status))
+        if rc:
+            raise _err(rc)
+        return dict(classes=classes, loglike=ll, status=status,
+                    post=[post[off[r]:off[r + 1]] for r in range(n)],
+                    decoded=[bytes(dec[off[r]:off[r + 1]]).decode("latin1") for r in range(n)])
 
     def viterbi_device(self, n_reads, max_read_len, d_packed, d_byte_off, d_read_len, d_loglike, d_decoded, decoded_stride,
                        d_decoded_len, d_status, stream=0):

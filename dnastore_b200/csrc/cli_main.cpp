@@ -17,8 +17,11 @@
 //   -v/--verbose N                accepted (0 = quiet); >=2 prints decoder info to stderr
 //   --device N                    CUDA ordinal (new)
 //   --devices A,B,...             decode on several GPUs of this node, reads sharded over them, output in input order (new)
-// Machine construction (-l without -L), the exact codec (-e/-d/-E/-D/-b/-B) and error
-// model fitting are outside this build's scope and are reported as such.
+//   -f/--fit-error STK            Baum-Welch fit of the error model on a Stockholm database of pairwise alignments (pair-HMM
+//                                 forward-backward on the GPU), fitted parameters as JSON on stdout (t/dnastore.cpp:135-140)
+//   --error-counts STK            posterior expected counts of the error events as JSON on stdout (t/dnastore.cpp:142-146)
+//   --strict-guides               treat the alignments as strict truth, not hints
+// Machine construction (-l without -L) and the encoder (-e/-E/-b) are outside this build's scope and are reported as such.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -36,7 +39,8 @@ static void die(const std::string& msg, int code = 1) {
 int main(int argc, char** argv) {
   dnab_error_flags ef;
   dnab_error_flags_default(&ef);
-  std::string loadMachine, saveMachine, viterbiFile, errorFile, exactFile, exactString, exactBits;
+  std::string loadMachine, saveMachine, viterbiFile, errorFile, exactFile, exactString, exactBits, fitFile, countsFile;
+  bool strictGuides = false;
   bool haveExactString = false, haveExactBits = false;
   std::vector<std::string> composes;
   bool raw = false;
@@ -96,6 +100,9 @@ int main(int argc, char** argv) {
     else if (name == "error-del-ext") ef.del_ext = std::atof(need().c_str());
     else if (name == "error-global") ef.global = 1;
     else if (name == "error-file") errorFile = need();
+    else if (name == "fit-error") fitFile = need();
+    else if (name == "error-counts") countsFile = need();
+    else if (name == "strict-guides") strictGuides = true;
     else if (name == "verbose") verbose = std::atoi(need().c_str());
     else if (name == "device") device = std::atoi(need().c_str());
     else if (name == "devices") {
@@ -115,6 +122,31 @@ int main(int argc, char** argv) {
       die("option '--" + name + "' is outside the scope of dnastore-b200 (Viterbi decoding path only)", 2);
   }
   if (ef.length > 31) die("Maximum context is 31 bases");
+  // error-model training comes first and needs no machine (t/dnastore.cpp:135-149)
+  if (!fitFile.empty() || !countsFile.empty()) {
+    if (!errorFile.empty()) die("--error-file together with --fit-error / --error-counts is outside the scope of dnastore-b200", 2);
+    dnab_mutator_params params;
+    dnab_mutator_params_from_flags(&ef, &params);
+    dnab_pair_db* db = dnab_pair_db_load((fitFile.empty() ? countsFile : fitFile).c_str());
+    if (!db) die(dnab_last_error());
+    char* text = nullptr;
+    if (!fitFile.empty()) {
+      dnab_mutator_params fitted;
+      int32_t iters = 0;
+      if (dnab_baum_welch(device, &params, db, strictGuides ? 1 : 0, &fitted, &iters) != DNAB_OK) die(dnab_last_error(), 3);
+      text = dnab_mutator_params_json(&fitted);
+    } else {
+      dnab_mutator_counts counts;
+      double ll = 0;
+      if (dnab_expected_counts(device, &params, db, strictGuides ? 1 : 0, &counts, &ll) != DNAB_OK) die(dnab_last_error(), 3);
+      text = dnab_mutator_counts_json(&counts);
+    }
+    if (!text) die(dnab_last_error());
+    std::fputs(text, stdout);
+    dnab_free(text);
+    dnab_pair_db_free(db);
+    return 0;
+  }
   if (loadMachine.empty()) die("dnastore-b200 needs --load-machine (machine construction is out of scope; "
                                "machines are reproducible only as JSON)", 2);
 

@@ -109,7 +109,8 @@ struct dnab_decoder {
   DevBuf<double> dFwdLse, dFwdScratch, dFwdF, dFwdCounts, dFwdLLBack;
   DevBuf<uint32_t> dFwdOutEmitOff, dFwdOutEmitDst, dFwdOutNullOff, dFwdOutNullDst;
   DevBuf<uint8_t> dFwdOutEmitMeta, dFwdOutNullSym;
-  DevBuf<long long> dFwdSweepsBack;
+  DevBuf<long long> dFwdSweepsBack, dFwdPostOff;
+  DevBuf<double> dFwdPost;
   DevBuf<long long> dFwdSweeps;
   bool debug = false;
   // read-batched kernel: 32 reads per group are the SIMD lanes (viterbi_fill_batch.cu)
@@ -1650,7 +1651,7 @@ int dnab_viterbi_batch(dnab_decoder* d, int64_t n_reads, const uint8_t* packed, 
 
 static int forwardImpl(dnab_decoder* d, int64_t n, const uint8_t* packed, const int64_t* byteOff, const int32_t* readLen,
                        int32_t maxSweeps, double* loglike, int64_t* sweeps, int32_t* status, double* cells,
-                       double* loglikeBack, double* counts) {
+                       double* loglikeBack, double* counts, double* post = nullptr, const int64_t* postOff = nullptr) {
   if (!d || n < 0 || !loglike) {
     setLastError("dnab_forward_batch: bad argument");
     return DNAB_EINVAL;
@@ -1742,6 +1743,13 @@ static int forwardImpl(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   CUDA_TRY(d->dFwdSweeps.ensure((size_t)n));
   CUDA_TRY(d->dFwdScratch.ensure((size_t)nBlocks * (10 + 2 * k) * N));
   CUDA_TRY(d->dNextRead.ensure(1));
+  size_t postRows = 0;
+  const uint32_t nClasses = (uint32_t)d->symChar.size() + 1;
+  if (post) {
+    for (int64_t r = 0; r < n; ++r) postRows = std::max<size_t>(postRows, (size_t)postOff[r] + (size_t)readLen[r]);
+    CUDA_TRY(d->dFwdPost.ensure(std::max<size_t>(1, postRows * nClasses)));
+    CUDA_TRY(d->dFwdPostOff.ensure((size_t)n));
+  }
   size_t cellCount = 0;
   if (cells) {
     cellCount = (size_t)(readLen[0] + 1) * N * (k + 2);
@@ -1752,6 +1760,12 @@ static int forwardImpl(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   CUDA_TRY(cudaMemcpyAsync(d->dByteOff.p, byteOff, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
   CUDA_TRY(cudaMemcpyAsync(d->dReadLen.p, readLen, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   CUDA_TRY(cudaMemsetAsync(d->dNextRead.p, 0, sizeof(unsigned long long), stream));
+  std::vector<long long> postOffLL;
+  if (post) {
+    postOffLL.assign(postOff, postOff + n);
+    CUDA_TRY(cudaMemcpyAsync(d->dFwdPostOff.p, postOffLL.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemsetAsync(d->dFwdPost.p, 0, postRows * nClasses * sizeof(double), stream));
+  }
   ForwardTables ft{};
   ft.nStates = N;
   ft.k = k;
@@ -1797,6 +1811,8 @@ static int forwardImpl(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
   fa.counts = counts ? d->dFwdCounts.p : nullptr;
   fa.loglikeBack = counts ? d->dFwdLLBack.p : nullptr;
   fa.sweepsBack = counts ? d->dFwdSweepsBack.p : nullptr;
+  fa.post = post ? d->dFwdPost.p : nullptr;
+  fa.postOff = post ? d->dFwdPostOff.p : nullptr;
   CUDA_TRY(cudaEventRecord(d->ev0, stream));
   CUDA_TRY(launchForward(ft, fa, nBlocks, fwdThreads, stream));
   CUDA_TRY(cudaEventRecord(d->ev1, stream));
@@ -1810,6 +1826,7 @@ static int forwardImpl(dnab_decoder* d, int64_t n, const uint8_t* packed, const 
     CUDA_TRY(cudaMemcpyAsync(counts, d->dFwdCounts.p, (size_t)n * nc * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (loglikeBack) CUDA_TRY(cudaMemcpyAsync(loglikeBack, d->dFwdLLBack.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
   }
+  if (post) CUDA_TRY(cudaMemcpyAsync(post, d->dFwdPost.p, postRows * nClasses * sizeof(double), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
   for (size_t r = 0; r < sw.size(); ++r) sweeps[r] = (int64_t)sw[r];
   float ms = 0;
@@ -1829,6 +1846,50 @@ int dnab_fwdback_counts_batch(dnab_decoder* d, int64_t n, const uint8_t* packed,
     return DNAB_EINVAL;
   }
   return forwardImpl(d, n, packed, byteOff, readLen, maxSweeps, loglike, nullptr, status, nullptr, loglikeBack, counts);
+}
+
+int dnab_posterior_classes(const dnab_decoder* d, char* classes, size_t cap) {
+  if (!d || !classes) return DNAB_EINVAL;
+  const size_t n = d->symChar.size() + 1;
+  if (n > (size_t)kPostClasses) {
+    setLastError("posterior decoding tells at most " + std::to_string(kPostClasses - 1) + " input symbols apart; this machine has " +
+                 std::to_string(d->symChar.size() - 1));
+    return DNAB_EINVAL;
+  }
+  if (cap < n + 1) {
+    setLastError("dnab_posterior_classes: buffer too small");
+    return DNAB_EINVAL;
+  }
+  classes[0] = '-';
+  for (size_t i = 1; i < d->symChar.size(); ++i) classes[i] = (char)d->symChar[i];
+  classes[n - 1] = '+';
+  classes[n] = 0;
+  return (int)n;
+}
+
+int dnab_posterior_batch(dnab_decoder* d, int64_t n, const uint8_t* packed, const int64_t* byteOff, const int32_t* readLen,
+                         int32_t maxSweeps, const int64_t* postOff, double* loglike, double* post, char* decoded, int32_t* status) {
+  if (!d || !post || !postOff || !loglike) {
+    setLastError("dnab_posterior_batch: null argument");
+    return DNAB_EINVAL;
+  }
+  char classes[kPostClasses + 1];
+  const int nc = dnab_posterior_classes(d, classes, sizeof classes);
+  if (nc < 0) return nc;
+  std::vector<double> counts((size_t)std::max<int64_t>(n, 1) * (5 + d->k + 16)), llBack((size_t)std::max<int64_t>(n, 1));
+  const int rc = forwardImpl(d, n, packed, byteOff, readLen, maxSweeps, loglike, nullptr, status, nullptr, llBack.data(), counts.data(),
+                             post, postOff);
+  if (rc != DNAB_OK) return rc;
+  if (decoded)
+    for (int64_t r = 0; r < n; ++r)
+      for (int32_t p = 0; p < readLen[r]; ++p) {
+        const double* row = post + ((size_t)postOff[r] + (size_t)p) * (size_t)nc;
+        int best = 0;
+        for (int c = 1; c < nc; ++c)
+          if (row[c] > row[best]) best = c;
+        decoded[(size_t)postOff[r] + (size_t)p] = classes[best];
+      }
+  return DNAB_OK;
 }
 
 int dnab_viterbi_cells(dnab_decoder* d, const uint8_t* packed, int32_t read_len, double* loglike, double* cells) {

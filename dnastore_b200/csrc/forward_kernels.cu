@@ -286,6 +286,13 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
       double* S2[2] = {bbase + N, bbase + 2 * (size_t)N};
       double* D2[2] = {bbase + 3 * (size_t)N, bbase + 4 * (size_t)N};
       constexpr int kMaxCounts = 5 + kMaxK + 16;
+      // posterior classes of the move that emits a read base: input-symbol id 0 (no input symbol) .. nSyms-1, then
+      // "tandem duplication" (dnab_posterior_batch); at most kPostClasses, accumulated in registers
+      double pacc[kPostClasses];
+#pragma unroll
+      for (int c = 0; c < kPostClasses; ++c) pacc[c] = 0.;
+      const uint32_t dupClass = tb.nSyms;
+      __shared__ double redP[32 * kPostClasses];
       double cnt[kMaxCounts];
 #pragma unroll
       for (int i = 0; i < kMaxCounts; ++i) cnt[i] = 0.;
@@ -461,6 +468,11 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
               const double u = post(fS, (sc + tb.noGap) + tb.sub[bs * 4 + xn], Bn[(size_t)d * W]);
               cnt[2] += u;
               cnt[5 + k + bs * 4 + xn] += u;
+              if (args.post) {
+                const uint32_t sy = meta & 31u;
+#pragma unroll
+                for (int c = 0; c < kPostClasses; ++c) pacc[c] += ((uint32_t)c == sy) ? u : 0.;
+              }
             }
           }
           cnt[4] += post(fD, tb.delEnd, bc[0]);
@@ -473,14 +485,38 @@ __global__ void __launch_bounds__(1024, 1) forwardKernel(const ForwardTables tb,
           if (pos < L && mdl > 0) {
             const double* bn = Bn + (size_t)s * W;
             const uint32_t c0 = __ldg(tb.ctx + (size_t)s * k);
-            cnt[5 + k + c0 * 4 + xn] += post(__ldcs(fc + 2), tb.sub[c0 * 4 + xn], bn[0]);
+            double dupU = post(__ldcs(fc + 2), tb.sub[c0 * 4 + xn], bn[0]);
+            cnt[5 + k + c0 * 4 + xn] += dupU;
             for (uint32_t i = 0; i + 1 < mdl; ++i) {
               const uint32_t ci = __ldg(tb.ctx + (size_t)s * k + i + 1);
-              cnt[5 + k + ci * 4 + xn] += post(__ldcs(fc + 2 + i + 1), tb.sub[ci * 4 + xn], bn[2 + i]);
+              const double u = post(__ldcs(fc + 2 + i + 1), tb.sub[ci * 4 + xn], bn[2 + i]);
+              cnt[5 + k + ci * 4 + xn] += u;
+              dupU += u;
+            }
+            if (args.post) {
+#pragma unroll
+              for (int c = 0; c < kPostClasses; ++c) pacc[c] += ((uint32_t)c == dupClass) ? dupU : 0.;
             }
           }
         }
         __syncthreads();
+        if (args.post) {
+          // who emitted read base `pos`: block reduction in a fixed order (warp tree, then the warps in order)
+#pragma unroll
+          for (int c = 0; c < kPostClasses; ++c) {
+            double v = pacc[c];
+            for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, sh);
+            if ((tid & 31u) == 0) redP[(tid >> 5) * kPostClasses + c] = v;
+            pacc[c] = 0.;
+          }
+          __syncthreads();
+          if (tid <= dupClass && pos < L) {
+            double v = 0.;
+            for (uint32_t w = 0; w < (nThreads + 31) / 32; ++w) v += redP[w * kPostClasses + tid];
+            args.post[((size_t)args.postOff[read] + pos) * (dupClass + 1) + tid] = v;
+          }
+          __syncthreads();
+        }
         double* tmp = Bn;
         Bn = Bc;
         Bc = tmp;

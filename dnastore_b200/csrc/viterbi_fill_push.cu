@@ -589,12 +589,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         bool sent = false, fromAppend = false;
         // (one-CTA machines only: with peers, their flags would wait for the next scan and cost extra cluster rounds --
         // measured -4 % ... -20 % on config 2, against +23 % / +5 % on configs 4 / 3)
-        if (!kCluster) {
-          if (tid < 3) sts32(aTailA + 4 * tid, 0u);
-          __syncthreads();
-        }
+        // every column starts with empty scan-queue tails (a tail is otherwise only zeroed by a scan of the opposite
+        // parity, and the level counter restarts at 0: a stale count would replay old queue entries)
+        if (tid < 2) sts32(aTail + 4 * tid, 0u);
+        if (!kCluster && tid < 3) sts32(aTailA + 4 * tid, 0u);
+        __syncthreads();
         for (uint32_t levels = 0;; ++levels) {
           const uint32_t par = levels & 1;
+          const bool scanned = kCluster || !fromAppend;
           const uint32_t tANext = tA == 2 ? 0u : tA + 1, tAAfter = tANext == 2 ? 0u : tANext + 1;
           dbgStamp(2);
           bool flagged = false, deferred = false;
@@ -680,6 +682,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
           dbgLap(2, 10);
           // every push of this level has flagged or queued its successors
           const uint32_t needScan = (uint32_t)__syncthreads_or((flagged || deferred) ? 1 : 0);
+          if (scanned && tid == 0) sts32(aTail + 4 * par, 0u);  // consumed: the next scan of this parity starts empty
           tA = tANext;
           dbgLap(2, 12);
           if (needScan) {  // (a scan also takes the bits of whatever was appended meanwhile: that list is dropped)

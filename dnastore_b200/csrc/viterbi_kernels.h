@@ -227,7 +227,11 @@ struct ForwardArgs {
   int32_t* status;               // [nReads] 0 ok, 1 a closure did not settle within maxSweeps
   unsigned long long* nextRead;  // zeroed before the launch
   double* cells;                 // optional dump of read 0: [(L+1)][N][k+2]
+  double* post;                  // optional [sum of L][nSyms+1]: per read base, posterior of the class of the move that emitted it
+  const long long* postOff;      // [nReads] row of read r's first base in post
 };
+
+constexpr int kPostClasses = 8;  // input-symbol ids + "duplication" that dnab_posterior_batch can tell apart
 
 cudaError_t launchForward(const ForwardTables& tb, const ForwardArgs& args, uint32_t nBlocks, uint32_t threads,
                           cudaStream_t stream);

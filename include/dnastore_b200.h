@@ -219,6 +219,22 @@ int dnab_fwdback_counts_batch(dnab_decoder* d, int64_t n_reads, const uint8_t* p
                               const int32_t* read_len, int32_t max_sweeps, double* loglike, double* loglike_back,
                               double* counts, int32_t* status);
 
+/* Posterior (soft) decoding over the machine lattice (BASELINE config 5): for every base of every
+ * read, the posterior probability, summed over ALL paths (forward x transition x backward / likelihood -- the formula of
+ * FwdBackMatrix, src/fwdback.h:92-113, applied to the machine lattice), of the CLASS of the move that emitted it:
+ *   class 0        a transition that consumes no input symbol (padding / control-word bases)
+ *   class 1..s     a transition that consumes input symbol classes[i] ('0', '1', control letters, ...)
+ *   class s+1      a tandem duplication (the base repeats an earlier one, src/viterbi.cpp:102-106)
+ * dnab_posterior_classes writes the class characters ("-" + the machine's input symbols + "+") and returns their number.
+ * post: row post_off[r] + p, column c = P(class c emitted base p of read r | read); every row sums to 1 up to the accuracy
+ * of the reference's table log_sum_exp (2e-3).  decoded (optional, one char per base, same offsets): the most probable
+ * class per base -- a soft output for an outer code (doc/trans.tex:947-952,1148-1154), not the Viterbi input string.
+ * NOT IN THE REFERENCE; specified by oracle/forward_oracle.c (dnab_oracle_backward_posterior), parity unpinned. */
+int dnab_posterior_classes(const dnab_decoder* d, char* classes, size_t cap);
+int dnab_posterior_batch(dnab_decoder* d, int64_t n_reads, const uint8_t* packed, const int64_t* read_byte_off,
+                         const int32_t* read_len, int32_t max_sweeps, const int64_t* post_off, double* loglike, double* post,
+                         char* decoded, int32_t* status);
+
 /* Counters since creation: kernels launched by this library and DP cells filled. */
 typedef struct dnab_decoder_stats {
   uint64_t kernel_launches;

@@ -192,9 +192,19 @@ int dnab_oracle_forward(const dnab_tables* t, const uint8_t* seq, int L, int max
  * no cell.  ll_back = B_S(start,0) (global) must agree with the forward value up to the table's accuracy.
  * counts: [nDelOpen, nTanDup, nNoGap, nDelExtend, nDelEnd, nLen[k], nSub[16]] (the order of pairhmm_oracle.c).
  * F: the forward cells of dnab_oracle_forward (ViterbiMatrix layout). */
-int dnab_oracle_backward_counts(const dnab_tables* t, const uint8_t* seq, int L, int max_sweeps, const double* F,
-                                double ll, double* ll_back, double* counts, long* total_sweeps) {
+/* classes/post (optional): posterior, per read base, of the class of the move that emitted it -- classes[0] = '-' (a
+ * transition without input symbol), classes[1..] the input symbols, the last class '+' = tandem duplication;
+ * post[p * n_classes + c], p = 0..L-1.  The same posterior weights as the counts, binned by position and symbol. */
+int dnab_oracle_backward_posterior(const dnab_tables* t, const uint8_t* seq, int L, int max_sweeps, const double* F,
+                                   double ll, double* ll_back, double* counts, long* total_sweeps, const char* classes,
+                                   int n_classes, double* post) {
   const uint32_t n = t->n_states, k = t->k;
+  int class_of[256];
+  for (int c = 0; c < 256; ++c) class_of[c] = 0;
+  if (post) {
+    for (int c = 1; c + 1 < n_classes; ++c) class_of[(unsigned char)classes[c]] = c;
+    for (size_t i = 0; i < (size_t)L * (size_t)n_classes; ++i) post[i] = 0.;
+  }
   lse_table_init();
   /* outgoing lists, built from the destination-indexed tables (order: destination ascending, list order) */
   uint32_t* eoff = (uint32_t*)calloc(n + 2, sizeof(uint32_t));
@@ -312,6 +322,7 @@ int dnab_oracle_backward_counts(const dnab_tables* t, const uint8_t* seq, int L,
           const double u = POST(fS, (sc + t->noGap) + t->sub[b * 4 + xn], Bn[(size_t)d * W]);
           counts[2] += u;                   /* nNoGap */
           counts[5 + k + b * 4 + xn] += u; /* nSub */
+          if (post) post[(size_t)pos * n_classes + class_of[t->emit_in[e]]] += u;
         }
       }
       counts[4] += POST(fD, t->delEnd, bc[0]); /* nDelEnd */
@@ -324,11 +335,15 @@ int dnab_oracle_backward_counts(const dnab_tables* t, const uint8_t* seq, int L,
       if (pos < L && mdl > 0) {
         const double* bn = Bn + (size_t)s * W;
         const int c0 = t->ctx[(size_t)s * k];
-        counts[5 + k + c0 * 4 + xn] += POST(FC(pos, s, 2), t->sub[c0 * 4 + xn], bn[0]);
+        double dupU = POST(FC(pos, s, 2), t->sub[c0 * 4 + xn], bn[0]);
+        counts[5 + k + c0 * 4 + xn] += dupU;
         for (uint32_t i = 0; i + 1 < mdl; ++i) {
           const int ci = t->ctx[(size_t)s * k + i + 1];
-          counts[5 + k + ci * 4 + xn] += POST(FC(pos, s, 2 + i + 1), t->sub[ci * 4 + xn], bn[2 + i]);
+          const double u = POST(FC(pos, s, 2 + i + 1), t->sub[ci * 4 + xn], bn[2 + i]);
+          counts[5 + k + ci * 4 + xn] += u;
+          dupU += u;
         }
+        if (post) post[(size_t)pos * n_classes + (n_classes - 1)] += dupU;
       }
     }
     double* tmp = Bn;
@@ -346,4 +361,9 @@ int dnab_oracle_backward_counts(const dnab_tables* t, const uint8_t* seq, int L,
   free(eoff); free(noff); free(eedge); free(edst); free(nedge); free(ndst);
   free(Bn); free(Bc); free(base); free(S[0]); free(S[1]); free(D[0]); free(D[1]);
   return rc;
+}
+
+int dnab_oracle_backward_counts(const dnab_tables* t, const uint8_t* seq, int L, int max_sweeps, const double* F,
+                                double ll, double* ll_back, double* counts, long* total_sweeps) {
+  return dnab_oracle_backward_posterior(t, seq, L, max_sweeps, F, ll, ll_back, counts, total_sweeps, NULL, 0, NULL);
 }

@@ -133,6 +133,10 @@ def forward_oracle_lib():
     lib.dnab_oracle_forward.restype = C.c_int
     lib.dnab_oracle_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double),
                                         C.POINTER(C.c_long), C.c_void_p]
+    lib.dnab_oracle_backward_posterior.restype = C.c_int
+    lib.dnab_oracle_backward_posterior.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double,
+                                                   C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_long), C.c_char_p, C.c_int,
+                                                   C.c_void_p]
     lib.dnab_oracle_backward_counts.restype = C.c_int
     lib.dnab_oracle_backward_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double,
                                                 C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_long)]
@@ -153,6 +157,34 @@ def oracle_fwdback(compiled, seq, max_sweeps=4096, tables=None):
                                                           counts.ctypes.data, C.byref(sw))
     return dict(rc=rc | f["rc"], loglike=f["loglike"], loglike_back=llb.value, counts=counts, sweeps_back=sw.value,
                 sweeps=f["sweeps"])
+
+
+def posterior_classes(compiled):
+    """'-' + the input symbols in the order the decoder numbers them (first appearance in the emit list, then the
+    null list) + '+': the classes of dnab_posterior_batch."""
+    t = compiled.t
+    seen = []
+    for arr, n in ((t.emit_in, t.n_emit), (t.null_in, t.n_null)):
+        for e in range(n):
+            ch = arr[e]
+            if ch and ch not in seen:
+                seen.append(ch)
+    return "-" + "".join(chr(c) for c in seen) + "+"
+
+
+def oracle_posterior(compiled, seq, classes, max_sweeps=4096):
+    """The posterior specification (oracle/forward_oracle.c: dnab_oracle_backward_posterior): [L, n_classes]."""
+    t = compiled.t
+    f = oracle_forward(compiled, seq, want_cells=True, max_sweeps=max_sweeps)
+    tok = tokens(seq)
+    counts = np.zeros(5 + t.k + 16, dtype=np.float64)
+    post = np.zeros((len(seq), len(classes)), dtype=np.float64)
+    llb = C.c_double(0)
+    sw = C.c_long(0)
+    rc = forward_oracle_lib().dnab_oracle_backward_posterior(C.addressof(t), tok.ctypes.data, len(seq), max_sweeps,
+                                                             f["cells"].ctypes.data, f["loglike"], C.byref(llb), counts.ctypes.data,
+                                                             C.byref(sw), classes.encode("latin1"), len(classes), post.ctypes.data)
+    return dict(rc=rc | f["rc"], loglike=f["loglike"], post=post, counts=counts)
 
 
 def oracle_forward(compiled, seq, want_cells=False, max_sweeps=4096, tables=None):

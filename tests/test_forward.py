@@ -201,3 +201,136 @@ def test_gpu_fwdback_counts_match_specification(name, n, cut):
         assert util.hexf(out["loglike"][i]) == util.hexf(o["loglike"]), (name, i)
         assert util.hexf(out["loglike_back"][i]) == util.hexf(o["loglike_back"]), (name, i)
         np.testing.assert_allclose(out["counts"][i], o["counts"], rtol=1e-9, atol=1e-12, err_msg=f"{name} read {i}")
+
+
+# ----------------------------------------------------------------------------------------------
+# posterior (soft) decoding: per read base, the posterior of the class of the move that emitted it
+# ----------------------------------------------------------------------------------------------
+def brute_force_posterior(compiled, seq, classes, floor=1e-13):
+    """Every path of the lattice, enumerated explicitly in probability space (exact exp, no table, no closure
+    solve): returns (likelihood, [L, n_classes] posterior of the class of the move that emits each base).  Only
+    for tiny machines and reads: deletion cycles make the path set infinite, paths lighter than `floor` are cut."""
+    import sys
+    t = compiled.t
+    N, k = t.n_states, t.k
+    eo, no = _arr(t.emit_off, N + 1, np.int64), _arr(t.null_off, N + 1, np.int64)
+    es, ns = _arr(t.emit_src, t.n_emit, np.int64), _arr(t.null_src, t.n_null, np.int64)
+    esc, nsc = _arr(t.emit_score, t.n_emit, np.float64), _arr(t.null_score, t.n_null, np.float64)
+    eb, ein = _arr(t.emit_base, t.n_emit, np.int64), _arr(t.emit_in, t.n_emit, np.int64)
+    ctx = _arr(t.ctx, N * k, np.int64).reshape(N, k) if k else np.zeros((N, 0), np.int64)
+    mdl = _arr(t.mdl, N, np.int64)
+    sub = np.exp(np.array(list(t.sub))).reshape(4, 4)
+    ln = np.exp(_arr(t.len, k, np.float64)) if k else np.zeros(0)
+    pNoGap, pOpen, pExt, pEnd, pDup = (np.exp(v) for v in (t.noGap, t.delOpen, t.delExtend, t.delEnd, t.tanDup))
+    out_e = [[] for _ in range(N)]
+    out_n = [[] for _ in range(N)]
+    for dst in range(N):
+        for e in range(eo[dst], eo[dst + 1]):
+            out_e[es[e]].append((dst, np.exp(esc[e]), int(eb[e]), classes.index(chr(ein[e])) if ein[e] else 0))
+        for e in range(no[dst], no[dst + 1]):
+            out_n[ns[e]].append((dst, np.exp(nsc[e])))
+    tok = util.tokens(seq)
+    L = len(seq)
+    dup = len(classes) - 1
+    acc = np.zeros((L, len(classes)))
+    total = [0.0]
+    sys.setrecursionlimit(100000)
+
+    def walk(s, pos, mut, p, labels):
+        if p < floor:
+            return
+        if mut == 0 and pos == L and (t.local or s == N - 1):
+            total[0] += p
+            for q, c in enumerate(labels):
+                acc[q, c] += p
+            if not t.local:
+                pass  # the end state may still have outgoing moves: keep walking
+        if mut == 0:
+            if pos < L:
+                for dst, w, b, c in out_e[s]:
+                    walk(dst, pos + 1, 0, p * w * pNoGap * sub[b, tok[pos]], labels + [c])
+            for dst, w in out_n[s]:
+                walk(dst, pos, 0, p * w, labels)
+            for dst, w, _b, _c in out_e[s]:
+                walk(dst, pos, 1, p * w * pOpen, labels)
+            if pos > 0:
+                for i in range(mdl[s]):
+                    walk(s, pos, 2 + i, p * pDup * ln[i], labels)
+        elif mut == 1:
+            for dst, w, _b, _c in out_e[s]:
+                walk(dst, pos, 1, p * w * pExt, labels)
+            for dst, w in out_n[s]:
+                walk(dst, pos, 1, p * w, labels)
+            walk(s, pos, 0, p * pEnd, labels)
+        elif pos < L:
+            i = mut - 2
+            w = sub[ctx[s, i], tok[pos]]
+            if i == 0:
+                walk(s, pos + 1, 0, p * w, labels + [dup])
+            else:
+                walk(s, pos + 1, 2 + i - 1, p * w, labels + [dup])
+
+    starts = range(N) if t.local else [0]
+    for s0 in starts:
+        walk(s0, 0, 0, 1.0, [])
+    return total[0], acc / total[0] if total[0] > 0 else acc
+
+
+@pytest.mark.parametrize("machine,global_,reads", [("l1c0t0", True, ["ACG", "TT", "GATC"]), ("l1c0t0", False, ["CA"]),
+                                                    ("echobits", True, None)])
+def test_posterior_specification_against_path_enumeration(machine, global_, reads):
+    """The posterior of the class of the move that emits each base (oracle/forward_oracle.c) against an explicit
+    enumeration of every lattice path in exact arithmetic: equal within the table log_sum_exp's accuracy, rows sum to 1."""
+    import dnastore_b200 as d
+    try:
+        m = util.machine_from_recipe((machine,))
+        compiled = m.compile(d.ErrorFlags(length=2, global_=global_, sub_prob=.05, dup_prob=.02, del_open=.02, del_ext=.1))
+    except d.DnabError as e:
+        pytest.skip(f"{machine} is not a DNA-output machine for the decoder: {e}")
+    if compiled.t.n_states > 64:
+        pytest.skip("too large for path enumeration")
+    classes = util.posterior_classes(compiled)
+    for seq in reads or ["AC", "GGT"]:
+        o = util.oracle_posterior(compiled, seq, classes)
+        like, exact = brute_force_posterior(compiled, seq, classes)
+        if like <= 0:
+            continue
+        assert abs(np.log(like) - o["loglike"]) < 3e-3, (machine, seq)
+        np.testing.assert_allclose(o["post"], exact, atol=4e-3)
+        np.testing.assert_allclose(o["post"].sum(axis=1), 1.0, atol=4e-3)
+
+
+@pytest.mark.parametrize("name", ["l4c4_global_mixed", "l4c4_local_mixed"])
+def test_posterior_rows_sum_to_one_and_match_counts(name):
+    case = util.golden_case(name)
+    compiled = util.compiled_for_case(case)
+    classes = util.posterior_classes(compiled)
+    k = compiled.t.k
+    for r in case["reads"][:3]:
+        o = util.oracle_posterior(compiled, r["seq"], classes)
+        np.testing.assert_allclose(o["post"].sum(axis=1), 1.0, atol=3e-3)
+        # the same posterior weights, binned differently: sum over positions of the non-duplication classes = nNoGap,
+        # everything = sum of nSub
+        assert abs(o["post"][:, :-1].sum() - o["counts"][2]) < 1e-9 * max(1.0, o["counts"][2])
+        assert abs(o["post"].sum() - o["counts"][5 + k:].sum()) < 1e-9 * len(r["seq"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["l4c4_global_mixed", "l4c4_local_mixed", "mr2l4c4_local", "cfg5_l8_global"])
+def test_gpu_posterior_matches_specification(name):
+    """dnab_posterior_batch on B200 against the specification: same log-likelihood bits, posteriors within 1e-9
+    (the kernel sums the states in a different, fixed order), per-base decision = argmax."""
+    import dnastore_b200 as d
+    case = util.golden_case(name)
+    compiled = util.compiled_for_case(case)
+    dec = d.Decoder(compiled, device=0)
+    classes = dec.posterior_classes()
+    assert classes == util.posterior_classes(compiled)
+    reads = [r["seq"] for r in case["reads"][:4]]
+    out = dec.posterior(reads)
+    for i, seq in enumerate(reads):
+        o = util.oracle_posterior(compiled, seq, classes)
+        assert util.hexf(out["loglike"][i]) == util.hexf(o["loglike"])
+        np.testing.assert_allclose(out["post"][i], o["post"], rtol=1e-9, atol=1e-12)
+        assert out["decoded"][i] == "".join(classes[j] for j in o["post"].argmax(axis=1))
+        assert set(out["decoded"][i]) <= set(classes)

@@ -144,3 +144,25 @@ def test_gpu_expected_counts_reference_goldens(tmp_path):
     total, ll = d.expected_counts(params_for(c), load_db(c, tmp_path), strict=False)
     txt = total.to_json()
     assert '"nTanDup": 1.25882,' in txt and '"nNoGap": 29,' in txt and '"nMatch": 31.2588,' in txt
+
+
+@pytest.mark.gpu
+def test_gpu_cli_error_counts_and_fit_error(tmp_path):
+    """bin/dnastore-b200 --error-counts / --fit-error (reference t/dnastore.cpp:135-149, Makefile:157-163): the CLI prints
+    what the C ABI returns, in the reference's JSON layout."""
+    import subprocess
+    exe = os.path.join(util.ROOT, "bin", "dnastore-b200")
+    c = case("dup.sub")
+    stk = tmp_path / "dup.sub.stk"
+    stk.write_text(c["stk"])
+    out = subprocess.run([exe, "-v0", "-l6", "--error-sub-prob", "1e-9", "--error-dup-prob", "1e-9", "--error-del-open", "1e-9",
+                          "--error-counts", str(stk)], capture_output=True, text=True, check=True).stdout
+    total, _ll = d.expected_counts(params_for(c), load_db(c, tmp_path), strict=False)
+    assert out == total.to_json()
+    assert '"nTanDup": 1.25882,' in out and '"nMatch": 31.2588,' in out
+    c = case("tiny_fit")
+    stk = tmp_path / "tiny.stk"
+    stk.write_text(c["stk"])
+    out = subprocess.run([exe, "-v0", "--fit-error", str(stk), "--strict-guides"], capture_output=True, text=True, check=True).stdout
+    fitted, _it = d.baum_welch(params_for(c), load_db(c, tmp_path), strict=True)
+    assert out == fitted.to_json()
