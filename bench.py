@@ -417,6 +417,40 @@ def short_fwdback(d, util, n_reads=296):
                 max_abs_loglike_back_minus_forward=float(np.abs(out["loglike_back"] - out["loglike"]).max()))
 
 
+def short_pairhmm(d, n_distinct=1024, copies=32, seed=77):
+    """Batched pair-HMM forward + backward + expected counts on synthetic alignments:
+    reference-encoded ~200-nt strands mutated by the errdecode.pl simulator with the alignment kept
+    (benchdata/synth.mutate_aligned), n_distinct alignments repeated `copies` times. DP cells = envelope cells x (2 + k);
+    16 algorithmic bytes per DP cell (the forward cell is written once and read once by the counts pass)."""
+    from benchdata import synth
+    rng = np.random.default_rng(seed)
+    pool = synth.load_pool("cfg1_l4c4_200b")
+    rows = []
+    for i in range(n_distinct):
+        a, b = synth.mutate_aligned(pool[i % len(pool)], rng, sub_rate=0.02, dup_rate=0.01, max_dup=3, del_rate=0.01, max_del=4)
+        rows.append(f"# STOCKHOLM 1.0\nin  {a}\nout {b}\n//\n")
+    tf = tempfile.NamedTemporaryFile("w", suffix=".stk", delete=False)
+    tf.write("".join(rows))
+    tf.close()
+    db = d.PairDb(tf.name)
+    os.unlink(tf.name)
+    params = d.MutatorParams.from_flags(d.ErrorFlags(length=12, sub_prob=.02, dup_prob=.01, del_open=.01, del_ext=.3))
+    base = [db.alignment(i) for i in range(len(db))]
+    aligns = base * copies
+    k = params.max_dup_len
+    cells = 0
+    for tin, tout, ea, eb in base:
+        cells += int((np.abs(ea[:, None] - eb[None, :]) <= k).sum())
+    cells *= copies * (2 + k)
+    d.pairhmm_fb_batch(params, base, strict=False)  # warm-up
+    fwd, back, _counts, ms = d.pairhmm_fb_batch(params, aligns, strict=False)
+    peak, _ = measured_peak()
+    return dict(workload=f"pair-HMM forward + backward + expected counts, {len(aligns)} alignments of ~200-nt strands, k = {k}, banded envelope",
+                alignments=len(aligns), dp_cells=cells, kernel_ms=ms, alignments_per_sec=len(aligns) / (ms * 1e-3),
+                cells_per_sec=cells / (ms * 1e-3), roofline_frac=16.0 * cells / (ms * 1e-3) / 1e9 / peak, kernel="pairHmmFwdBackKernel",
+                max_abs_back_minus_fwd=float(np.abs(np.asarray(fwd) - np.asarray(back)).max()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -429,7 +463,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="reads in the single-core CPU baseline sample (0 = skip)")
     ap.add_argument("--others", type=int, default=-1, help="other_workloads: 1 on, 0 off, -1 = on for N = 1 and the default workload")
     ap.add_argument("--no-indel", action="store_true", help="decode with --error-del-open 0 --error-dup-prob 0 (closure degenerates)")
-    ap.add_argument("--mode", default="viterbi", choices=["viterbi", "fwdback"],
+    ap.add_argument("--mode", default="viterbi", choices=["viterbi", "fwdback", "pairhmm"],
                     help="fwdback: forward + backward + posterior counts over the machine lattice (weak scaling, one batch per GPU)")
     args = ap.parse_args()
 
@@ -451,6 +485,11 @@ def main():
     import __graft_entry__ as g
     if rank == 0:
         g.build()
+    if args.mode == "pairhmm":
+        if rank == 0:
+            import dnastore_b200 as d
+            print(json.dumps(short_pairhmm(d, copies=max(1, args.reads_per_step // 1024) if args.reads_per_step else 32)), flush=True)
+        return
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -659,6 +698,7 @@ def main():
                 if name != args.workload:
                     others[name] = short_run(d, util, torch, dev, name, n)
             others["cfg5_fwdback"] = short_fwdback(d, util)
+            others["pairhmm"] = short_pairhmm(d)
         kernel_cfg = (dict(kernel="read-batched (viterbi_fill_batch.cu): 32 reads per group are the SIMD lanes",
                            team_size=binfo["team_size"], states_per_cta=binfo["states_per_cta"],
                            threads_per_cta=32 * binfo["warps_per_cta"], smem_bytes_per_cta=binfo["smem_bytes_per_cta"],

@@ -118,6 +118,8 @@ struct dnab_decoder {
   uint32_t wantTeam = 0;        // CTAs per team (0 = smallest that fits)
   uint32_t wantWarps = 0;       // warps per CTA (0 = 32)
   BatchPlan bplan;
+  uint32_t wantPersist = 1;     // carried rows in the persisting part of L2 (option "persist_l2")
+  size_t persistBytes = 0;
   BatchTables btab{};
   BatchTraceTables btrace{};
   DevBuf<uint4> dbHdr;
@@ -1062,6 +1064,19 @@ static int buildBatchPlan(dnab_decoder* d) {
   }
   const size_t Np = (size_t)bp.T * bp.M;
   CUDA_TRY(d->dbPriv.ensure((size_t)bp.nTeams * Np * (2 + k) * 32));
+  {
+    // L2 set-aside for the carried rows: as much of them as the device lets a window and the set-aside hold
+    cudaDeviceProp prop{};
+    d->persistBytes = 0;
+    if (d->wantPersist && cudaGetDeviceProperties(&prop, d->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+      const size_t want = d->dbPriv.n * sizeof(double);
+      const size_t setAside = std::min<size_t>(want, (size_t)prop.persistingL2CacheMaxSize);
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside) == cudaSuccess)
+        d->persistBytes = std::min<size_t>(setAside, (size_t)prop.accessPolicyMaxWindowSize);
+      else
+        cudaGetLastError();
+    }
+  }
   CUDA_TRY(d->dbSdPub.ensure(bp.T > 1 ? (size_t)bp.nTeams * 2 * Np * 32 : 1));
   CUDA_TRY(d->dbTeamState.ensure((size_t)bp.nTeams * bp.T));
   CUDA_TRY(d->dbTeamPassive.ensure((size_t)bp.nTeams * 2));
@@ -1139,7 +1154,7 @@ static int runDeviceBatch(dnab_decoder* d, int64_t nReads, int32_t maxLen, const
       CUDA_TRY(cudaMemsetAsync(d->dbBarrier.p, 0, d->dbBarrier.n * sizeof(unsigned long long), stream));
     }
     if (rec) CUDA_TRY(cudaEventRecord(e0, stream));
-    CUDA_TRY(launchFillBatch(d->btab, a, bp.warps, bp.smemBytes, stream));
+    CUDA_TRY(launchFillBatch(d->btab, a, bp.warps, bp.smemBytes, stream, d->persistBytes));
     if (rec) CUDA_TRY(cudaEventRecord(e1, stream));
     BatchTraceArgs ta{};
     ta.nSlots = n * 32;
@@ -1461,6 +1476,8 @@ int dnab_decoder_set_option(dnab_decoder* d, const char* key, int64_t value) {
     d->dealChunks = v;
   else if (k == "idle_sleep_ns")
     d->idleSleepNs = v;
+  else if (k == "persist_l2")
+    d->wantPersist = v;
   else if (k == "pred_budget_mb")
     d->predBudgetBytes = (size_t)value << 20;
   else {

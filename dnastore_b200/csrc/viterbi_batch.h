@@ -168,8 +168,9 @@ struct BatchTraceArgs {
 };
 
 cudaError_t queryBatchTeams(const BatchTables& tb, uint32_t warps, uint32_t smemBytes, int* ctasPerSm);
+// persistBytes > 0: the first persistBytes of args.priv get a persisting L2 access-policy window for this launch
 cudaError_t launchFillBatch(const BatchTables& tb, const BatchArgs& args, uint32_t warps, uint32_t smemBytes,
-                            cudaStream_t stream);
+                            cudaStream_t stream, size_t persistBytes);
 cudaError_t launchTracebackBatch(const BatchTraceTables& tb, const BatchTraceArgs& args, cudaStream_t stream);
 
 }  // namespace dnab

@@ -734,7 +734,7 @@ cudaError_t queryBatchTeams(const BatchTables& tb, uint32_t warps, uint32_t smem
 }
 
 cudaError_t launchFillBatch(const BatchTables& tb, const BatchArgs& args, uint32_t warps, uint32_t smemBytes,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, size_t persistBytes) {
   const bool debug = args.dbg != nullptr || args.cells != nullptr;
   BatchKernelPtr kern = pickBatchKernel(tb, warps, debug);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
@@ -744,11 +744,26 @@ cudaError_t launchFillBatch(const BatchTables& tb, const BatchArgs& args, uint32
   cfg.blockDim = dim3(batchWarps(warps) * 32);
   cfg.dynamicSmemBytes = smemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;  // the CTAs of a team meet at barriers in L2: all must be resident
-  attr[0].val.cooperative = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned nAttr = 0;
+  if (tb.T > 1) {
+    attr[nAttr].id = cudaLaunchAttributeCooperative;  // the CTAs of a team meet at barriers in L2: all must be resident
+    attr[nAttr].val.cooperative = 1;
+    ++nAttr;
+  }
+  if (persistBytes) {
+    // the rows carried from one column to the next (rewritten in place every column) stay in the persisting part of L2
+    // instead of being written back to HBM behind the record stream
+    attr[nAttr].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[nAttr].val.accessPolicyWindow.base_ptr = args.priv;
+    attr[nAttr].val.accessPolicyWindow.num_bytes = persistBytes;
+    attr[nAttr].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[nAttr].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[nAttr].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++nAttr;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = tb.T > 1 ? 1 : 0;
+  cfg.numAttrs = nAttr;
   return cudaLaunchKernelEx(&cfg, kern, tb, args);
 }
 
