@@ -118,6 +118,7 @@ struct dnab_decoder {
   uint32_t wantTeam = 0;        // CTAs per team (0 = smallest that fits)
   uint32_t wantWarps = 0;       // warps per CTA (0 = 32)
   BatchPlan bplan;
+  uint32_t teamSlackPct = 8;    // states per CTA above the balanced share that the partitioner may use (option "team_slack_pct")
   uint32_t wantPersist = 1;     // carried rows in the persisting part of L2 (option "persist_l2")
   size_t persistBytes = 0;
   BatchTables btab{};
@@ -789,7 +790,10 @@ static int buildBatchPlan(dnab_decoder* d) {
   bp.ready = true;
   bp.feasible = false;
   const uint32_t N = d->nStates, k = d->k;
-  const uint32_t W = d->wantWarps ? (d->wantWarps > 24 ? 32u : d->wantWarps > 16 ? 24u : 16u) : 24u;
+  // warps per CTA (measured on B200): 24 when one CTA holds the group (80 registers, no spills: 349k vs 315k reads/s on
+  // dnastore-l4), 32 in a team (more states relaxed side by side per level: 1,120 vs 1,060 reads/s on the 46,670-state machine)
+  const uint32_t wantW = d->wantWarps ? (d->wantWarps > 24 ? 32u : d->wantWarps > 16 ? 24u : 16u) : 0u;
+  uint32_t W = wantW ? wantW : 24u;
   auto nEmitOf = [&](uint32_t s) { return d->emitOff[s + 1] - d->emitOff[s]; };
   auto nNullOf = [&](uint32_t s) { return d->nullOff[s + 1] - d->nullOff[s]; };
   for (uint32_t s = 0; s < N; ++s) {
@@ -820,6 +824,7 @@ static int buildBatchPlan(dnab_decoder* d) {
   std::vector<uint32_t> outE, rankInOff, rankOutOff, newOf(N), origOf, remoteIn;
   // builds the tables of a team of T CTAs; false when T is infeasible
   auto buildTeam = [&](uint32_t T, uint32_t M) -> bool {
+    W = wantW ? wantW : (T > 1 ? 32u : 24u);
     const uint32_t Np = T * M;
     if (M > kBatchMaxSlots * W || M > 65535 || T > 1023) return false;
     if (makeBatchLayout(M, 0, 0, nSymsB, T > 1).total > d->smemOptin) return false;
@@ -956,8 +961,8 @@ static int buildBatchPlan(dnab_decoder* d) {
     const uint32_t Mbal = (N + T - 1) / T;
     if (T == 1) return buildTeam(1, Mbal);
     uint32_t last = 0;
-    for (uint32_t pct : {8u, 4u, 0u}) {
-      const uint32_t M = std::min<uint32_t>(Mbal + (Mbal * pct + 99) / 100, kBatchMaxSlots * W);
+    for (uint32_t pct : {d->teamSlackPct, d->teamSlackPct / 2, 0u}) {
+      const uint32_t M = std::min<uint32_t>(Mbal + (Mbal * pct + 99) / 100, kBatchMaxSlots * 16u);
       if (M == last) continue;
       last = M;
       if (buildTeam(T, M)) return true;
@@ -1197,13 +1202,14 @@ static int runDevice(dnab_decoder* d, int64_t nReads, int32_t maxLen, const uint
   if (nReads <= 0) return DNAB_OK;
   CUDA_TRY(cudaSetDevice(d->device));
   if (batchWanted(d)) {
-    // Automatic choice (measured on B200, DESIGN.md 6): the read-batched kernel when the group's columns fit ONE CTA
-    // (2.1x the one-read-per-cluster kernel on dnastore-l4); larger machines stay on the push kernel, whose cross-CTA
-    // traffic goes through distributed shared memory -- a team over L2 pays ~3 us per cross-CTA hop of a deletion chain
-    // and only ties it on the 46,670-state machine -- unless no 16-CTA cluster can hold the machine.
+    // Automatic choice (measured on B200, DESIGN.md 5.3, 6): the read-batched kernel when the group's columns fit ONE CTA
+    // (2x the one-read-per-cluster kernel on dnastore-l4) and when the push kernel would need a cluster of 4 or more CTAs
+    // per read (the 46,670-state machine: a 148-CTA team decodes 1,120 reads/s, 33 clusters of 4 decode 1,010); machines in
+    // between (7-12k states, one CTA per read in the push kernel) stay on the push kernel -- a team over L2 pays ~3 us per
+    // cross-CTA hop of their long, thin deletion chains (3.3k vs 7.1k reads/s on watermark64.1*l4).
     int brc = buildBatchPlan(d);
     bool use = brc == DNAB_OK;
-    if (use && d->wantBatch != 1 && d->bplan.T > 1 && buildPlan(d, maxLen) == DNAB_OK) use = false;
+    if (use && d->wantBatch != 1 && d->bplan.T > 1 && buildPlan(d, maxLen) == DNAB_OK && d->plan.C < 4) use = false;
     if (use)
       return runDeviceBatch(d, nReads, maxLen, dPacked, dByteOff, dReadLen, dLoglike, dDecoded, decodedStride, dDecodedLen,
                             dStatus, dPath, pathStride, dPathLen, dCells, stream, timeIt, hostLen);
@@ -1476,6 +1482,8 @@ int dnab_decoder_set_option(dnab_decoder* d, const char* key, int64_t value) {
     d->dealChunks = v;
   else if (k == "idle_sleep_ns")
     d->idleSleepNs = v;
+  else if (k == "team_slack_pct")
+    d->teamSlackPct = v;
   else if (k == "persist_l2")
     d->wantPersist = v;
   else if (k == "pred_budget_mb")
@@ -1496,7 +1504,7 @@ int dnab_decoder_get_batch_info(const dnab_decoder* dc, dnab_batch_info* info) {
   std::memset(info, 0, sizeof *info);
   if (!batchWanted(d)) return DNAB_OK;
   if (buildBatchPlan(d) != DNAB_OK) return d->wantBatch == 1 ? DNAB_EINVAL : DNAB_OK;
-  info->enabled = (d->wantBatch == 1 || d->bplan.T == 1 || buildPlan(d, 1) != DNAB_OK) ? 1 : 0;
+  info->enabled = (d->wantBatch == 1 || d->bplan.T == 1 || buildPlan(d, 1) != DNAB_OK || d->plan.C >= 4) ? 1 : 0;
   info->reads_per_group = kBatchReads;
   info->team_size = d->bplan.T;
   info->states_per_cta = d->bplan.M;

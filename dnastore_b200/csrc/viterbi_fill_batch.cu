@@ -264,20 +264,26 @@ __global__ void __launch_bounds__(W * 32, 1)
           }
         };
         if (allIn || nIn <= 4u) {  // few transitions: relaxing all of them is cheaper than walking the mask
+          // (rolled on purpose: a state has 1-3 in-transitions; the compiler's 8-way unrolling with its remainder
+          // scaffolding costs more instructions than the loops execute)
           uint32_t j = 0;
+#pragma unroll 1
           for (; j < nLE; ++j) {
             const uint2 e = rel[j];
             emitFrom(ldsRow(e.x + lane16), e);
           }
+#pragma unroll 1
           for (; j < eLN; ++j) {
             const uint2 e = rel[j];
             nullFrom(ldsRow(e.x + lane16), e);
           }
           if (kTeam) {
+#pragma unroll 1
             for (; j < eRE; ++j) {
               const uint2 e = rel[j];
               emitFrom(ldPub2(sdPubCol + (size_t)e.x * 32 + lane), e);
             }
+#pragma unroll 1
             for (; j < nIn; ++j) {
               const uint2 e = rel[j];
               nullFrom(ldPub2(sdPubCol + (size_t)e.x * 32 + lane), e);
@@ -302,6 +308,7 @@ __global__ void __launch_bounds__(W * 32, 1)
           remotePending |= 1u << sl;
         }
         const uint32_t nLoc = bhNOutLocal(h), outOff = bhOutOff(h);
+#pragma unroll 1
         for (uint32_t o = lane; o < nLoc; o += 32) {
           const uint32_t w = outS[outOff + o];
           atomicOr(maskNext + boLocal(w), 1u << boBit(w));
@@ -454,6 +461,7 @@ __global__ void __launch_bounds__(W * 32, 1)
           double best = pos > 0 ? curB : NEG, bestD = NEG, s0n = NEG, bEn = NEG;
           uint32_t idx = pos > 0 ? kKeepRecord : kNoPred, idxD = kNoPred, idxEn = kNoPred;
           uint32_t j = 0;
+#pragma unroll 1
           for (; j < nE; ++j) {
             const uint2 e = inS[inOff + j];
             const uint32_t sym = beSym(e);
@@ -476,6 +484,7 @@ __global__ void __launch_bounds__(W * 32, 1)
               idxEn = j;
             }
           }
+#pragma unroll 1
           for (; j < nIn; ++j) {
             const uint2 e = inS[inOff + j];
             const double2 v = (kTeam && beRemote(e)) ? ldPub2(sdPubCol + (size_t)e.x * 32 + lane) : ldsRow(e.x + lane16);
