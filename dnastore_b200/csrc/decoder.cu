@@ -118,6 +118,8 @@ struct dnab_decoder {
   uint32_t wantTeam = 0;        // CTAs per team (0 = smallest that fits)
   uint32_t wantWarps = 0;       // warps per CTA (0 = 32)
   BatchPlan bplan;
+  uint32_t batchIdleNs = 100;   // option "batch_idle_ns"
+  uint32_t asyncClosure = 2;    // read-batched kernel: closure without level barriers: 0 off, 1 on, 2 automatic = in a team (option "async_closure")
   uint32_t teamSlackPct = 8;    // states per CTA above the balanced share that the partitioner may use (option "team_slack_pct")
   uint32_t wantPersist = 1;     // carried rows in the persisting part of L2 (option "persist_l2")
   size_t persistBytes = 0;
@@ -1124,6 +1126,10 @@ static int runDeviceBatch(dnab_decoder* d, int64_t nReads, int32_t maxLen, const
     a.nGroups = n;
     a.nTeams = (uint32_t)std::min<int64_t>(bp.nTeams, n);
     a.maxLen = maxLen;
+    // measured on B200: without level barriers a team gains 10-60 % (1,250 vs 1,130 reads/s on the 46,670-state machine, 5.9k vs
+    // 3.6k on watermark64.1*l4); a single CTA loses 5 % (331k vs 349k reads/s on dnastore-l4: its levels are short and dense)
+    a.asyncClosure = d->asyncClosure == 2 ? (bp.T > 1 ? 1u : 0u) : d->asyncClosure;
+    a.idleNs = d->batchIdleNs;
     a.packed = dPacked;
     a.byteOff = dByteOff;
     a.readLen = dReadLen;
@@ -1482,6 +1488,10 @@ int dnab_decoder_set_option(dnab_decoder* d, const char* key, int64_t value) {
     d->dealChunks = v;
   else if (k == "idle_sleep_ns")
     d->idleSleepNs = v;
+  else if (k == "batch_idle_ns")
+    d->batchIdleNs = v;
+  else if (k == "async_closure")
+    d->asyncClosure = v;
   else if (k == "team_slack_pct")
     d->teamSlackPct = v;
   else if (k == "persist_l2")

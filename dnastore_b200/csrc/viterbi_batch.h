@@ -88,6 +88,8 @@ struct BatchArgs {
   int64_t nGroups;
   uint32_t nTeams;
   int32_t maxLen;                // record stride: every group owns (maxLen+1) columns
+  uint32_t idleNs;               // asynchronous closure: back-off of a warp that found no work
+  uint32_t asyncClosure;         // 1: closure without level barriers (work counter), 0: breadth-first levels
   const uint8_t* packed;         // 2-bit reads
   const int64_t* byteOff;        // [nReads]
   const int32_t* readLen;        // [nReads]

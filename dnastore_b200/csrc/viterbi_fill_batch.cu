@@ -76,12 +76,14 @@ __device__ __forceinline__ unsigned long long ldAcquire64(const unsigned long lo
   return v;
 }
 
-enum : uint32_t { kCtlFlag = 0, kCtlWake = 4, kCtlDecision = 8 };
+enum : uint32_t { kCtlFlag = 0, kCtlWake = 4, kCtlDecision = 8, kCtlPending = 16, kCtlPhase = 17 };
 constexpr uint32_t kKeepRecord = 0x100u;  // "the S record written by the previous column's pass stands"
-constexpr uint32_t kPassive = 1u, kNotified = 2u;  // team state word of a CTA
 
 __device__ __forceinline__ void fenceRelease() { asm volatile("fence.release.gpu;" ::: "memory"); }
 __device__ __forceinline__ void stRecordEarly(uint8_t* p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void redAdd32(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void stRelaxed32(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -149,8 +151,13 @@ __global__ void __launch_bounds__(W * 32, 1)
   const uint32_t privKinds = 2 + k;
   double* const privT = args.priv + (size_t)team * Np * privKinds * 32 + lane;
   double2* const sdPubT = args.sdPub + (size_t)team * 2 * Np * 32;  // two parities of the column
-  uint32_t* const stateT = args.teamState + (size_t)team * T;  // per CTA: kPassive | kNotified
-  uint32_t* const passiveT = args.teamPassive + (size_t)team * 2;  // passive CTAs of the current column, by parity
+  // Team protocol (no returning atomic, no flag to clear): notifyT[c] counts the notifications ever sent to CTA c;
+  // passiveT[parity] = (CTAs of this column that are passive) - (notifications sent and not yet consumed).  A sender
+  // subtracts 1 BEFORE the fence that precedes its notification; a receiver adds what it consumed when it consumes it;
+  // so the count can only reach T when every CTA is passive and nothing is undelivered.
+  uint32_t* const notifyT = args.teamState + (size_t)team * T;
+  uint32_t* const passiveT = args.teamPassive + (size_t)team * 2;
+  uint32_t notifySeen = 0;  // (thread 0) notifications consumed so far; the counters are zeroed before the launch
   unsigned long long* const bar = args.barrier + team;
   unsigned long long barTarget = 0;
   uint32_t col = 0;
@@ -215,13 +222,18 @@ __global__ void __launch_bounds__(W * 32, 1)
         }
       }
       if (tid < 8) ctl[tid] = 0;
-      if (kTeam && tid == 0) stRelaxed32(stateT + rank, 0u);  // active, not notified
+      if (tid == 0) {
+        ctl[kCtlPending] = M;  // asynchronous closure: every state is scheduled for its first relaxation
+        ctl[kCtlPhase] = 0u;
+      }
       teamBarrier();
       if (kTeam && rank == 0 && tid == 0) stRelaxed32(passiveT + (par ^ 1u), 0u);  // the other parity's count is dead: reset it for the next column
       unsigned long long stamp = 0;
       if (kDebug) stamp = clock64();
 
       // ---- (2) closure (src/viterbi.cpp:97-99,110-159), owner-computes edge relaxation ----
+      const bool asyncClosure = args.asyncClosure != 0;
+      uint32_t* const pendingS = const_cast<uint32_t*>(reinterpret_cast<volatile uint32_t*>(ctl) + kCtlPending);
       uint32_t remotePending = 0;  // slots of this warp that grew and have successors in other CTAs
       // relaxes the flagged in-transitions of state d (all of them when `allIn` or when there are few); when a lane
       // grew: stores the row, publishes it if some successor lives in another CTA, flags the local successors' masks.
@@ -308,10 +320,23 @@ __global__ void __launch_bounds__(W * 32, 1)
           remotePending |= 1u << sl;
         }
         const uint32_t nLoc = bhNOutLocal(h), outOff = bhOutOff(h);
+        if (!asyncClosure) {
 #pragma unroll 1
-        for (uint32_t o = lane; o < nLoc; o += 32) {
-          const uint32_t w = outS[outOff + o];
-          atomicOr(maskNext + boLocal(w), 1u << boBit(w));
+          for (uint32_t o = lane; o < nLoc; o += 32) {
+            const uint32_t w = outS[outOff + o];
+            atomicOr(maskNext + boLocal(w), 1u << boBit(w));
+          }
+        } else if (nLoc) {
+          // the count of states with work may never be transiently low: add first, give back what was already flagged
+          if (lane == 0) atomicAdd(pendingS, nLoc);
+          uint32_t already = 0;
+#pragma unroll 1
+          for (uint32_t o = lane; o < nLoc; o += 32) {
+            const uint32_t w = outS[outOff + o];
+            already += atomicOr(maskCur + boLocal(w), 1u << boBit(w)) != 0u;
+          }
+          already = __reduce_add_sync(0xFFFFFFFFu, already);
+          if (lane == 0 && already) atomicSub(pendingS, already);
         }
         return true;
       };
@@ -319,6 +344,14 @@ __global__ void __launch_bounds__(W * 32, 1)
       // now; a notification that finds its target passive takes it out of the passive count on its behalf
       auto flushRemote = [&]() {
         if (!kTeam || !remotePending) return;
+        // count the notifications of this flush out of the passive count first, then ONE release fence per warp orders that
+        // and the published rows before the notifications themselves (fire-and-forget adds on the targets' counters)
+        uint32_t nNotes = 0;
+        for (uint32_t rp = remotePending; rp; rp &= rp - 1u) {
+          const uint4 h = hdrS[((uint32_t)__ffs((int)rp) - 1u) * W + warp];
+          nNotes += bhNOut(h) - bhNOutLocal(h);
+        }
+        if (lane == 0) redAdd32(passiveCol, 0u - nNotes);
         fenceRelease();
         __syncwarp();
         while (remotePending) {
@@ -326,13 +359,110 @@ __global__ void __launch_bounds__(W * 32, 1)
           remotePending &= remotePending - 1u;
           const uint4 h = hdrS[sl * W + warp];
           const uint32_t nLoc = bhNOutLocal(h), nOut = bhNOut(h), outOff = bhOutOff(h);
-          for (uint32_t o = nLoc + lane; o < nOut; o += 32) {  // the CTAs that own successors of this state
-            const uint32_t old = atomicOr(stateT + outS[outOff + o], kNotified);
-            if (old == kPassive) atomicSub(passiveCol, 1u);
-          }
+          for (uint32_t o = nLoc + lane; o < nOut; o += 32) redAdd32(notifyT + outS[outOff + o], 1u);  // the CTAs that own successors
         }
       };
 
+      if (asyncClosure) {
+        // Asynchronous closure: no level barrier.  Every warp keeps relaxing whichever of its own states are flagged
+        // (one mask array; the owner takes a mask with an exchange), ctl[kCtlPending] counts the states that are flagged,
+        // scheduled or being relaxed (notifications included: a visit is released only after its notifications are out),
+        // and the CTA is quiet exactly when that count is zero.
+        const uint32_t iMine = lane * W + warp;
+        const bool mineValid = lane < nSlots && iMine < M;
+        // first relaxation of every state: all transitions; flags that arrived earlier are covered by it
+        {
+          uint32_t release = 0;
+          for (uint32_t sl = 0; sl < nSlots; ++sl) {
+            const uint32_t d = sl * W + warp;
+            if (d >= M) break;
+            uint32_t old = 0;
+            if (lane == 0) old = atomicExch(maskCur + d, 0u);
+            old = __shfl_sync(0xFFFFFFFFu, old, 0);
+            relax(sl, 0, true);
+            release += 1u + (old != 0u);
+          }
+          flushRemote();
+          if (lane == 0 && release) atomicSub(pendingS, release);
+        }
+        for (;;) {
+          uint32_t mym = 0;
+          if (mineValid) mym = reinterpret_cast<volatile uint32_t*>(maskCur)[iMine];
+          uint32_t work = __ballot_sync(0xFFFFFFFFu, mym != 0);
+          if (work) {
+            uint32_t release = 0;
+            while (work) {
+              const uint32_t sl = (uint32_t)__ffs((int)work) - 1u;
+              work &= work - 1u;
+              uint32_t m = 0;
+              if (lane == 0) m = atomicExch(maskCur + sl * W + warp, 0u);
+              m = __shfl_sync(0xFFFFFFFFu, m, 0);
+              if (m) {
+                if (kDebug) ++dbgVisits;
+                relax(sl, m, false);
+                ++release;
+              }
+            }
+            flushRemote();
+            if (lane == 0 && release) atomicSub(pendingS, release);
+            continue;
+          }
+          if (ctl[kCtlPhase] != 0u) break;
+          if (warp != 0) {
+            if (args.idleNs) __nanosleep(args.idleNs);
+            continue;
+          }
+          // warp 0, idle: termination / notifications
+          uint32_t action = 0;  // 1: a neighbour CTA published new rows, 2: the column's closure is complete
+          if (lane == 0) {
+            const bool quiet = ctl[kCtlPending] == 0u;
+            if (!kTeam) {
+              if (quiet) action = 2;
+            } else {
+              uint32_t c = ldVolatileGlobal32(notifyT + rank);
+              if (c != notifySeen) {  // new rows published by neighbours: consume (this CTA is not counted passive now)
+                redAdd32(passiveCol, c - notifySeen);
+                notifySeen = c;
+                action = 1;
+              } else if (quiet) {
+                unsigned long long t0 = 0;
+                if (kDebug) t0 = clock64();
+                redAdd32(passiveCol, 1u);  // passive
+                for (;;) {
+                  c = ldVolatileGlobal32(notifyT + rank);
+                  if (c != notifySeen) {
+                    redAdd32(passiveCol, c - notifySeen - 1u);  // active again, and these notifications are consumed
+                    notifySeen = c;
+                    action = 1;
+                    break;
+                  }
+                  if (ldVolatileGlobal32(passiveCol) == T) {
+                    action = 2;
+                    break;
+                  }
+                }
+                if (kDebug) dbgPassive += clock64() - t0;
+              }
+            }
+          }
+          action = __shfl_sync(0xFFFFFFFFu, action, 0);
+          if (action == 2) {
+            if (lane == 0) ctl[kCtlPhase] = 1u;
+          } else if (action == 1) {
+            if (kDebug) ++dbgWakes;
+            // every state with transitions from other CTAs relaxes them again
+            for (uint32_t i = lane; i < M; i += 32) {
+              const uint32_t rm = remInS[i];
+              if (rm) {
+                atomicAdd(pendingS, 1u);
+                if (atomicOr(maskCur + i, rm) != 0u) atomicSub(pendingS, 1u);
+              }
+            }
+          } else if (args.idleNs)
+            __nanosleep(args.idleNs / 2);
+        }
+        __syncthreads();
+      } else
       {
         uint32_t lvl = 0;
         bool activated = false;
@@ -364,22 +494,18 @@ __global__ void __launch_bounds__(W * 32, 1)
               unsigned long long t0 = 0;
               if (kDebug) t0 = clock64();
               uint32_t decision;
-              const uint32_t old = atomicCAS(stateT + rank, 0u, kPassive);
-              if (old != 0u) {  // notified since the last check
-                atomicAnd(stateT + rank, ~kNotified);
-                decision = 1;
-              } else {
-                atomicAdd(passiveCol, 1u);
-                for (;;) {
-                  if (ldVolatileGlobal32(stateT + rank) & kNotified) {
-                    atomicExch(stateT + rank, 0u);
-                    decision = 1;
-                    break;
-                  }
-                  if (ldVolatileGlobal32(passiveCol) == T) {
-                    decision = 2;
-                    break;
-                  }
+              redAdd32(passiveCol, 1u);  // passive
+              for (;;) {
+                const uint32_t c = ldVolatileGlobal32(notifyT + rank);
+                if (c != notifySeen) {
+                  redAdd32(passiveCol, c - notifySeen - 1u);  // active again, and these notifications are consumed
+                  notifySeen = c;
+                  decision = 1;
+                  break;
+                }
+                if (ldVolatileGlobal32(passiveCol) == T) {
+                  decision = 2;
+                  break;
                 }
               }
               ctl[kCtlDecision] = decision;
@@ -393,7 +519,7 @@ __global__ void __launch_bounds__(W * 32, 1)
           if (kDebug && wake) ++dbgWakes;
           activated = false;
           uint32_t st = 0;
-          if (kTeam && tid == 0) st = ldVolatileGlobal32(stateT + rank);  // consumed after this level's work
+          if (kTeam && tid == 0) st = ldVolatileGlobal32(notifyT + rank);  // consumed after this level's work
           const uint32_t iMine = lane * W + warp;
           uint32_t mym = 0;
           if (lane < nSlots && iMine < M) {
@@ -412,8 +538,9 @@ __global__ void __launch_bounds__(W * 32, 1)
             activated |= relax(sl, m, false);
           }
           flushRemote();
-          if (kTeam && tid == 0 && (st & kNotified)) {
-            atomicAnd(stateT + rank, ~kNotified);  // cleared BEFORE the rows are read (next level)
+          if (kTeam && tid == 0 && st != notifySeen) {
+            redAdd32(passiveCol, st - notifySeen);  // consumed: the rows are read at the next level
+            notifySeen = st;
             ctl[kCtlWake + ((lvl + 1) & 3u)] = 1u;
           }
         }

@@ -135,6 +135,8 @@ int dnab_decoder_configure_ex(dnab_decoder* d, uint32_t block_table_mode, uint32
  *   "s_prev" (1 shared / 2 global), "partition" (1 index runs, 2 DFS runs, 3 DFS chunks dealt, 4 DFS runs sorted):
  *                     one-read-per-cluster kernels, as dnab_decoder_configure / _configure_ex
  *   "thin_n", "t_recompute", "queue_cap", "deal_chunks", "idle_sleep_ns": schedule knobs of the push kernel (tests)
+ *   "async_closure"   read-batched kernel: 0 breadth-first levels with a CTA barrier each, 1 no level barriers (work counter), 2 (default)
+ *                     automatic = 1 in a team, 0 in a single CTA; "batch_idle_ns" back-off of an idle warp; "team_slack_pct"
  *   "persist_l2"      read-batched kernel: 1 (default) keeps the rows carried between columns in the persisting part of L2
  *   "pred_budget_mb"  device memory the predecessor records of one launch may take
  * Unknown keys return DNAB_EINVAL. */

@@ -222,12 +222,15 @@ def test_gpu_round2_goldens_default_kernel(d, name):
     _check_reads(d, d.Decoder(util.compiled_for_case(case), device=0), case, name)
 
 
+@pytest.mark.parametrize("async_closure", [0, 1])
 @pytest.mark.parametrize("name", CASES + R2_CASES)
-def test_gpu_batch_kernel_matches_reference_golden(d, name):
-    """Every golden case through the read-batched kernel (32 reads are the lanes of a warp; teams of 1-148 CTAs)."""
+def test_gpu_batch_kernel_matches_reference_golden(d, name, async_closure):
+    """Every golden case through the read-batched kernel (32 reads are the lanes of a warp; teams of 1-148 CTAs), with
+    the closure in breadth-first levels and without level barriers."""
     case = util.golden_case(name) if name in CASES else util.golden_r2_case(name)
     dec = d.Decoder(util.compiled_for_case(case), device=0)
     dec.set_option("kernel", 1)
+    dec.set_option("async_closure", async_closure)
     try:
         info = dec.batch_info()
     except d.DnabError as e:
@@ -236,16 +239,18 @@ def test_gpu_batch_kernel_matches_reference_golden(d, name):
     _check_reads(d, dec, case, (name, info["team_size"]))
 
 
+@pytest.mark.parametrize("async_closure", [0, 1])
 @pytest.mark.parametrize("team,warps", [(1, 16), (1, 32), (2, 24), (3, 16), (7, 32), (16, 24)])
 @pytest.mark.parametrize("name", ["l4c4_global_mixed", "l4c4_local_mixed", "l4c4_len12_local", "mr2l4c4_local"])
-def test_gpu_batch_kernel_every_team_size(d, name, team, warps):
-    """How many CTAs share a group (and how their states are partitioned), and how many warps a CTA has, are
-    placement choices: no bit may change."""
+def test_gpu_batch_kernel_every_team_size(d, name, team, warps, async_closure):
+    """How many CTAs share a group (and how their states are partitioned), how many warps a CTA has, and whether the
+    closure runs in breadth-first levels or without level barriers are placement / schedule choices: no bit may change."""
     case = util.golden_case(name)
     dec = d.Decoder(util.compiled_for_case(case), device=0)
     dec.set_option("kernel", 1)
     dec.set_option("team_size", team)
     dec.set_option("warps_per_cta", warps)
+    dec.set_option("async_closure", async_closure)
     try:
         info = dec.batch_info()
     except d.DnabError:
