@@ -1128,7 +1128,7 @@ static int runDeviceBatch(dnab_decoder* d, int64_t nReads, int32_t maxLen, const
     a.maxLen = maxLen;
     // measured on B200: without level barriers a team gains 10-60 % (1,250 vs 1,130 reads/s on the 46,670-state machine, 5.9k vs
     // 3.6k on watermark64.1*l4); a single CTA loses 5 % (331k vs 349k reads/s on dnastore-l4: its levels are short and dense)
-    a.asyncClosure = d->asyncClosure == 2 ? (bp.T > 1 ? 1u : 0u) : d->asyncClosure;
+    a.asyncClosure = d->asyncClosure == 2 ? 1u : d->asyncClosure;
     a.idleNs = d->batchIdleNs;
     a.packed = dPacked;
     a.byteOff = dByteOff;

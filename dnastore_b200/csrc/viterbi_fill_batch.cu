@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(W * 32, 1)
       }
       if (tid < 8) ctl[tid] = 0;
       if (tid == 0) {
-        ctl[kCtlPending] = M;  // asynchronous closure: every state is scheduled for its first relaxation
+        ctl[kCtlPending] = 0u;  // asynchronous closure: number of warps that found nothing to do
         ctl[kCtlPhase] = 0u;
       }
       teamBarrier();
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(W * 32, 1)
 
       // ---- (2) closure (src/viterbi.cpp:97-99,110-159), owner-computes edge relaxation ----
       const bool asyncClosure = args.asyncClosure != 0;
-      uint32_t* const pendingS = const_cast<uint32_t*>(reinterpret_cast<volatile uint32_t*>(ctl) + kCtlPending);
+      uint32_t* const idleS = const_cast<uint32_t*>(reinterpret_cast<volatile uint32_t*>(ctl) + kCtlPending);
       uint32_t remotePending = 0;  // slots of this warp that grew and have successors in other CTAs
       // relaxes the flagged in-transitions of state d (all of them when `allIn` or when there are few); when a lane
       // grew: stores the row, publishes it if some successor lives in another CTA, flags the local successors' masks.
@@ -320,23 +320,11 @@ __global__ void __launch_bounds__(W * 32, 1)
           remotePending |= 1u << sl;
         }
         const uint32_t nLoc = bhNOutLocal(h), outOff = bhOutOff(h);
-        if (!asyncClosure) {
+        uint32_t* const flagTo = asyncClosure ? maskCur : maskNext;
 #pragma unroll 1
-          for (uint32_t o = lane; o < nLoc; o += 32) {
-            const uint32_t w = outS[outOff + o];
-            atomicOr(maskNext + boLocal(w), 1u << boBit(w));
-          }
-        } else if (nLoc) {
-          // the count of states with work may never be transiently low: add first, give back what was already flagged
-          if (lane == 0) atomicAdd(pendingS, nLoc);
-          uint32_t already = 0;
-#pragma unroll 1
-          for (uint32_t o = lane; o < nLoc; o += 32) {
-            const uint32_t w = outS[outOff + o];
-            already += atomicOr(maskCur + boLocal(w), 1u << boBit(w)) != 0u;
-          }
-          already = __reduce_add_sync(0xFFFFFFFFu, already);
-          if (lane == 0 && already) atomicSub(pendingS, already);
+        for (uint32_t o = lane; o < nLoc; o += 32) {
+          const uint32_t w = outS[outOff + o];
+          atomicOr(flagTo + boLocal(w), 1u << boBit(w));
         }
         return true;
       };
@@ -365,57 +353,61 @@ __global__ void __launch_bounds__(W * 32, 1)
 
       if (asyncClosure) {
         // Asynchronous closure: no level barrier.  Every warp keeps relaxing whichever of its own states are flagged
-        // (one mask array; the owner takes a mask with an exchange), ctl[kCtlPending] counts the states that are flagged,
-        // scheduled or being relaxed (notifications included: a visit is released only after its notifications are out),
-        // and the CTA is quiet exactly when that count is zero.
+        // (one mask array; the owner clears the bits it has read, flags are fire-and-forget ORs).  A warp that finds
+        // nothing counts itself idle (ctl[kCtlPending]) and backs off; it leaves the count BEFORE it clears a mask, and
+        // only after its notifications are out does it return to it.  The CTA is quiet exactly when all W warps are idle
+        // and every mask is zero: flags are only set by warps that are not idle, so once that holds nothing can change it.
         const uint32_t iMine = lane * W + warp;
         const bool mineValid = lane < nSlots && iMine < M;
-        // first relaxation of every state: all transitions; flags that arrived earlier are covered by it
-        {
-          uint32_t release = 0;
-          for (uint32_t sl = 0; sl < nSlots; ++sl) {
-            const uint32_t d = sl * W + warp;
-            if (d >= M) break;
-            uint32_t old = 0;
-            if (lane == 0) old = atomicExch(maskCur + d, 0u);
-            old = __shfl_sync(0xFFFFFFFFu, old, 0);
-            relax(sl, 0, true);
-            release += 1u + (old != 0u);
-          }
-          flushRemote();
-          if (lane == 0 && release) atomicSub(pendingS, release);
+        bool idle = false;
+        // first relaxation of every state: all transitions (flags that arrived earlier are covered: cleared first)
+        for (uint32_t sl = 0; sl < nSlots; ++sl) {
+          const uint32_t d = sl * W + warp;
+          if (d >= M) break;
+          if (lane == 0) maskCur[d] = 0u;  // (a flag set after this store is kept; one set before it is served by this relaxation)
+          __syncwarp();
+          relax(sl, 0, true);
         }
+        flushRemote();
         for (;;) {
           uint32_t mym = 0;
           if (mineValid) mym = reinterpret_cast<volatile uint32_t*>(maskCur)[iMine];
           uint32_t work = __ballot_sync(0xFFFFFFFFu, mym != 0);
           if (work) {
-            uint32_t release = 0;
+            if (idle) {
+              if (lane == 0) atomicSub(idleS, 1u);
+              idle = false;
+              __syncwarp();
+            }
+            if (mym) atomicAnd(maskCur + iMine, ~mym);  // the bits read; later ones stay for the next round
             while (work) {
               const uint32_t sl = (uint32_t)__ffs((int)work) - 1u;
               work &= work - 1u;
-              uint32_t m = 0;
-              if (lane == 0) m = atomicExch(maskCur + sl * W + warp, 0u);
-              m = __shfl_sync(0xFFFFFFFFu, m, 0);
-              if (m) {
-                if (kDebug) ++dbgVisits;
-                relax(sl, m, false);
-                ++release;
-              }
+              const uint32_t m = __shfl_sync(0xFFFFFFFFu, mym, sl);
+              if (kDebug) ++dbgVisits;
+              relax(sl, m, false);
             }
             flushRemote();
-            if (lane == 0 && release) atomicSub(pendingS, release);
             continue;
+          }
+          if (!idle) {
+            if (lane == 0) atomicAdd(idleS, 1u);
+            idle = true;
           }
           if (ctl[kCtlPhase] != 0u) break;
           if (warp != 0) {
             if (args.idleNs) __nanosleep(args.idleNs);
             continue;
           }
-          // warp 0, idle: termination / notifications
+          // warp 0, idle: is the CTA quiet?  (all warps idle, then every mask zero, then still all idle)
+          bool quiet = false;
+          if (ctl[kCtlPending] == W) {
+            bool any = false;
+            for (uint32_t i = lane; i < M; i += 32) any |= reinterpret_cast<volatile uint32_t*>(maskCur)[i] != 0u;
+            quiet = !__any_sync(0xFFFFFFFFu, any) && ctl[kCtlPending] == W;
+          }
           uint32_t action = 0;  // 1: a neighbour CTA published new rows, 2: the column's closure is complete
           if (lane == 0) {
-            const bool quiet = ctl[kCtlPending] == 0u;
             if (!kTeam) {
               if (quiet) action = 2;
             } else {
@@ -450,13 +442,13 @@ __global__ void __launch_bounds__(W * 32, 1)
             if (lane == 0) ctl[kCtlPhase] = 1u;
           } else if (action == 1) {
             if (kDebug) ++dbgWakes;
-            // every state with transitions from other CTAs relaxes them again
+            // every state with transitions from other CTAs relaxes them again; the flagging warp is not idle meanwhile
+            if (lane == 0) atomicSub(idleS, 1u);
+            idle = false;
+            __syncwarp();
             for (uint32_t i = lane; i < M; i += 32) {
               const uint32_t rm = remInS[i];
-              if (rm) {
-                atomicAdd(pendingS, 1u);
-                if (atomicOr(maskCur + i, rm) != 0u) atomicSub(pendingS, 1u);
-              }
+              if (rm) atomicOr(maskCur + i, rm);
             }
           } else if (args.idleNs)
             __nanosleep(args.idleNs / 2);
