@@ -121,7 +121,7 @@ struct dnab_decoder {
   uint32_t batchIdleNs = 100;   // option "batch_idle_ns"
   uint32_t asyncClosure = 2;    // read-batched kernel: closure without level barriers: 0 off, 1 on, 2 automatic = in a team (option "async_closure")
   uint32_t teamSlackPct = 8;    // states per CTA above the balanced share that the partitioner may use (option "team_slack_pct")
-  uint32_t wantPersist = 1;     // carried rows in the persisting part of L2 (option "persist_l2")
+  uint32_t wantPersist = 0;     // carried rows in the persisting part of L2 (option "persist_l2")
   size_t persistBytes = 0;
   BatchTables btab{};
   BatchTraceTables btrace{};

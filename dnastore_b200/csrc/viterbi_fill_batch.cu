@@ -81,6 +81,21 @@ constexpr uint32_t kKeepRecord = 0x100u;  // "the S record written by the previo
 
 __device__ __forceinline__ void fenceRelease() { asm volatile("fence.release.gpu;" ::: "memory"); }
 __device__ __forceinline__ void stRecordEarly(uint8_t* p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// rows carried from one column to the next: rewritten in place every column, so they should stay in L2 (evict-last)
+// while the record stream passes through (evict-first)
+__device__ __forceinline__ unsigned long long policyEvictLast() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double ldCarried(const double* p, unsigned long long pol) {
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stCarried(double* p, double v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void redAdd32(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -150,6 +165,7 @@ __global__ void __launch_bounds__(W * 32, 1)
   // per-state rows private to the owning lane, interleaved: [state][s0 | best emit candidate | k parked T cells][32]
   const uint32_t privKinds = 2 + k;
   double* const privT = args.priv + (size_t)team * Np * privKinds * 32 + lane;
+  const unsigned long long polLast = policyEvictLast();
   double2* const sdPubT = args.sdPub + (size_t)team * 2 * Np * 32;  // two parities of the column
   // Team protocol (no returning atomic, no flag to clear): notifyT[c] counts the notifications ever sent to CTA c;
   // passiveT[parity] = (CTAs of this column that are passive) - (notifications sent and not yet consumed).  A sender
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(W * 32, 1)
             s0 = (!bhPad(h) && (tb.local || (rank == tb.startRank && d == tb.startLocal))) ? 0.0 : NEG;
             if (kTeam && bhRemoteOut(h)) stPub2(sdPubCol + (size_t)(rank * M + d) * 32 + lane, s0, NEG);
           } else
-            s0 = privT[(size_t)(rank * M + d) * privKinds * 32];
+            s0 = ldCarried(privT + (size_t)(rank * M + d) * privKinds * 32, polLast);
           stsRow(aSD + d * 512u + lane16, s0, NEG);
         }
       }
@@ -553,10 +569,10 @@ __global__ void __launch_bounds__(W * 32, 1)
           const uint32_t d = sl * W + warp;
           if (d < M && pos > 0) {
             const double* row = privT + (size_t)(rank * M + d) * privKinds * 32;
-            pfB = row[32];
+            pfB = ldCarried(row + 32, polLast);
 #pragma unroll
             for (uint32_t t = 0; t < (uint32_t)KMAX; ++t)
-              if (t < k) pfT[t] = row[64 + 32 * t];
+              if (t < k) pfT[t] = ldCarried(row + 64 + 32 * t, polLast);
           }
         };
 #pragma unroll
@@ -680,11 +696,11 @@ __global__ void __launch_bounds__(W * 32, 1)
               if (t < mdl) {
                 const double v = tNow[t] + subS[bhCtx(h, t) * 4 + xNext];
                 if (t == 0) s0n = dmax(s0n, v);
-                row[64 + 32 * t] = v;
+                stCarried(row + 64 + 32 * t, v, polLast);
               }
           }
-          row[0] = s0n;
-          row[32] = bEn;
+          stCarried(row, s0n, polLast);
+          stCarried(row + 32, bEn, polLast);
           if (pos < L) stRecordEarly(pr + (size_t)N * K2 * 32, idxEn);  // the emit part of S(state,pos+1)'s record
           if (kTeam && bhRemoteOut(h)) stPub2(sdPubNext + (size_t)(rank * M + d) * 32 + lane, s0n, NEG);
           if (!tb.local) {

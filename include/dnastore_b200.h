@@ -137,7 +137,8 @@ int dnab_decoder_configure_ex(dnab_decoder* d, uint32_t block_table_mode, uint32
  *   "thin_n", "t_recompute", "queue_cap", "deal_chunks", "idle_sleep_ns": schedule knobs of the push kernel (tests)
  *   "async_closure"   read-batched kernel: 0 breadth-first levels with a CTA barrier each, 1 no level barriers (work counter), 2 (default)
  *                     automatic = 1 in a team, 0 in a single CTA; "batch_idle_ns" back-off of an idle warp; "team_slack_pct"
- *   "persist_l2"      read-batched kernel: 1 (default) keeps the rows carried between columns in the persisting part of L2
+ *   "persist_l2"      read-batched kernel: 1 gives the rows carried between columns a persisting L2 access-policy window (default 0:
+ *                     measured on B200 it DOUBLES the DRAM writes; the rows carry an evict-last cache hint instead)
  *   "pred_budget_mb"  device memory the predecessor records of one launch may take
  * Unknown keys return DNAB_EINVAL. */
 int dnab_decoder_set_option(dnab_decoder* d, const char* key, int64_t value);
