@@ -27,14 +27,16 @@ constexpr uint32_t kBatchAllEdges = 0xFFFFFFFFu;
 //
 //   header  uint4   x: inOff | outOff << 16        (entry offsets inside the rank's edge arrays)
 //                   y: nEmit | nNull << 8 | nOut << 16 | mdl << 24
-//                   z: ctx (2 bits per duplication index) | hasRemoteOut << 16 | pad << 17 | nOutLocal << 18
+//                   z: ctx (2 bits per duplication index) | hasRemoteOut << 16 | pad << 17 | nOutLocal << 18 | nOutRemoteEdges << 26
 //                      (successors in this CTA come first in the out-edge list)
 //                   w: reference state index (0xFFFFFFFF for padding)
 //   in-edge uint2   x: padded index g of the source
 //                   y: symbol id | base << 5 | remote << 7      (emit edges first, reference list order)
 //   out-edge u32    successors in this CTA: bits 0..15 destination's local index | 16..20 bit of the destination's
 //                   work mask (= index of this transition in the destination's in-edge list, 31 = "31 or later");
-//                   then one entry per OTHER CTA that owns a successor: its rank (the CTA is notified, not the state)
+//                   then the successors in other CTAs (same fields plus bits 21..30 = the owner's rank): their bit is set
+//                   in the owner's INBOX word of that state; then one entry per OTHER CTA that owns a successor: its
+//                   rank (the CTA whose notification counter is incremented)
 //   remoteIn u32    per state: the bits of its work mask whose transitions come from other CTAs
 //   The closure reads its own copy of the in-transitions, grouped so that its loops have no per-edge branch:
 //   hdr2    uint2   x: offset of the state's relax entries inside the rank's array
@@ -52,6 +54,7 @@ __host__ __device__ inline uint32_t bhCtx(const uint4& h, uint32_t i) { return (
 __host__ __device__ inline uint32_t bhRemoteOut(const uint4& h) { return (h.z >> 16) & 1u; }
 __host__ __device__ inline uint32_t bhPad(const uint4& h) { return (h.z >> 17) & 1u; }
 __host__ __device__ inline uint32_t bhNOutLocal(const uint4& h) { return (h.z >> 18) & 0xFFu; }
+__host__ __device__ inline uint32_t bhNOutRemote(const uint4& h) { return h.z >> 26; }
 __host__ __device__ inline uint32_t beSym(const uint2& e) { return e.y & 31u; }
 __host__ __device__ inline uint32_t beBase(const uint2& e) { return (e.y >> 5) & 3u; }
 __host__ __device__ inline uint32_t beRemote(const uint2& e) { return (e.y >> 7) & 1u; }
@@ -100,6 +103,8 @@ struct BatchArgs {
                                  //   its S record (traceback association), the k parked duplication cells
   double2* sdPub;                // [nTeams][2][Np][32] (S,D) rows of states with successors in other CTAs (T > 1), by column parity
   uint32_t* teamState;           // [nTeams][T] per CTA: 1 passive | 2 notified (T > 1), zeroed before every launch
+  uint32_t* inbox;               // [nTeams][Np] per state: work-mask bits flagged by other CTAs (T > 1), zeroed before every launch
+  uint32_t preciseWake;          // 1: a notified CTA takes its inbox words; 0: it re-relaxes every transition that crosses CTAs
   uint32_t* teamPassive;         // [nTeams][2] passive CTAs of the current column, by column parity, zeroed before every launch
   unsigned long long* barrier;   // [nTeams] team barrier counters (monotonic), zeroed before every launch
   double* loglike;               // [nReads] global mode

@@ -99,6 +99,9 @@ __device__ __forceinline__ void stCarried(double* p, double v, unsigned long lon
 __device__ __forceinline__ void redAdd32(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void redOr32(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void stRelaxed32(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -173,6 +176,7 @@ __global__ void __launch_bounds__(W * 32, 1)
   // so the count can only reach T when every CTA is passive and nothing is undelivered.
   uint32_t* const notifyT = args.teamState + (size_t)team * T;
   uint32_t* const passiveT = args.teamPassive + (size_t)team * 2;
+  uint32_t* const inboxT = args.inbox + (size_t)team * Np;
   uint32_t notifySeen = 0;  // (thread 0) notifications consumed so far; the counters are zeroed before the launch
   unsigned long long* const bar = args.barrier + team;
   unsigned long long barTarget = 0;
@@ -353,17 +357,32 @@ __global__ void __launch_bounds__(W * 32, 1)
         uint32_t nNotes = 0;
         for (uint32_t rp = remotePending; rp; rp &= rp - 1u) {
           const uint4 h = hdrS[((uint32_t)__ffs((int)rp) - 1u) * W + warp];
-          nNotes += bhNOut(h) - bhNOutLocal(h);
+          nNotes += bhNOut(h) - bhNOutLocal(h) - bhNOutRemote(h);
         }
         if (lane == 0) redAdd32(passiveCol, 0u - nNotes);
         fenceRelease();
         __syncwarp();
+        if (args.preciseWake) {
+          // which transitions of which states: bits in the owners' inbox words.  They must not be visible before the rows
+          // (an owner that takes a bit early would relax against the old row and the bit would be gone), nor after the
+          // notification (it would find nothing and go passive): a fence on either side.
+          for (uint32_t rp = remotePending; rp; rp &= rp - 1u) {
+            const uint4 h = hdrS[((uint32_t)__ffs((int)rp) - 1u) * W + warp];
+            const uint32_t first = bhOutOff(h) + bhNOutLocal(h), nRem = bhNOutRemote(h);
+            for (uint32_t o = lane; o < nRem; o += 32) {
+              const uint32_t w = outS[first + o];
+              redOr32(inboxT + boRank(w) * M + boLocal(w), 1u << boBit(w));
+            }
+          }
+          fenceRelease();
+          __syncwarp();
+        }
         while (remotePending) {
           const uint32_t sl = (uint32_t)__ffs((int)remotePending) - 1u;
           remotePending &= remotePending - 1u;
           const uint4 h = hdrS[sl * W + warp];
-          const uint32_t nLoc = bhNOutLocal(h), nOut = bhNOut(h), outOff = bhOutOff(h);
-          for (uint32_t o = nLoc + lane; o < nOut; o += 32) redAdd32(notifyT + outS[outOff + o], 1u);  // the CTAs that own successors
+          const uint32_t first = bhOutOff(h) + bhNOutLocal(h) + bhNOutRemote(h), last = bhOutOff(h) + bhNOut(h);
+          for (uint32_t o = first + lane; o < last; o += 32) redAdd32(notifyT + outS[o], 1u);  // the CTAs that own successors
         }
       };
 
@@ -463,7 +482,12 @@ __global__ void __launch_bounds__(W * 32, 1)
             idle = false;
             __syncwarp();
             for (uint32_t i = lane; i < M; i += 32) {
-              const uint32_t rm = remInS[i];
+              uint32_t rm = remInS[i];
+              if (rm && args.preciseWake) {  // only the transitions whose sources were published (the bits were set before the notification)
+                uint32_t* box = inboxT + rank * M + i;
+                rm = ldVolatileGlobal32(box);
+                if (rm) rm = atomicExch(box, 0u);
+              }
               if (rm) atomicOr(maskCur + i, rm);
             }
           } else if (args.idleNs)
@@ -535,7 +559,15 @@ __global__ void __launch_bounds__(W * 32, 1)
               mym = maskCur[iMine];
               if (mym) maskCur[iMine] = 0;
             }
-            if (wake) mym |= remInS[iMine];  // a neighbour CTA published new rows: relax every transition that crosses CTAs
+            if (wake) {  // a neighbour CTA published new rows
+              uint32_t rm = remInS[iMine];
+              if (rm && args.preciseWake) {
+                uint32_t* box = inboxT + rank * M + iMine;
+                rm = ldVolatileGlobal32(box);
+                if (rm) rm = atomicExch(box, 0u);
+              }
+              mym |= rm;
+            }
           }
           uint32_t work = __ballot_sync(0xFFFFFFFFu, mym != 0);
           while (work) {

@@ -259,6 +259,17 @@ def test_gpu_batch_kernel_every_team_size(d, name, team, warps, async_closure):
     _check_reads(d, dec, case, (name, team, warps))
 
 
+@pytest.mark.parametrize("name", ["mr2l4c4_local", "cfg4_global_dels", "cfg5_l8_local", "cfg2_global_subs"])
+def test_gpu_batch_kernel_precise_wake_same_bits(d, name):
+    """Teams: a notified CTA either re-relaxes every transition that crosses CTAs (default) or only the ones flagged in its
+    inbox words (option precise_wake): a schedule choice, no bit may change."""
+    case = util.golden_case(name)
+    dec = d.Decoder(util.compiled_for_case(case), device=0)
+    dec.set_option("kernel", 1)
+    dec.set_option("precise_wake", 1)
+    _check_reads(d, dec, case, name)
+
+
 @pytest.mark.parametrize("kernel", [0, 1])
 def test_gpu_cfg2_cells_hash(d, kernel):
     """Every DP cell of a short read on the 46,670-state machine (global and local mode) hashes to the reference's
