@@ -121,6 +121,7 @@ struct dnab_decoder {
   uint32_t preciseWake = 0;     // 1: a notification re-relaxes only the transitions flagged in the inbox (option "precise_wake": half the
                                 // visits on watermark64.1*l4 but a second release fence on every hop: 5.6k vs 6.3k reads/s, 1,086 vs 1,282 on
                                 // the 46,670-state machine); 0: every transition that crosses CTAs
+  uint32_t eagerNotify = 0;     // option "eager_notify"
   uint32_t batchIdleNs = 100;   // option "batch_idle_ns"
   uint32_t asyncClosure = 2;    // read-batched kernel: closure without level barriers: 0 off, 1 on, 2 automatic = in a team (option "async_closure")
   uint32_t teamSlackPct = 8;    // states per CTA above the balanced share that the partitioner may use (option "team_slack_pct")
@@ -1150,6 +1151,7 @@ static int runDeviceBatch(dnab_decoder* d, int64_t nReads, int32_t maxLen, const
     a.teamState = d->dbTeamState.p;
     a.inbox = d->dbInbox.p;
     a.preciseWake = d->preciseWake;
+    a.eagerNotify = d->eagerNotify;
     a.teamPassive = d->dbTeamPassive.p;
     a.barrier = d->dbBarrier.p;
     a.loglike = dLoglike;
@@ -1501,6 +1503,8 @@ int dnab_decoder_set_option(dnab_decoder* d, const char* key, int64_t value) {
     d->dealChunks = v;
   else if (k == "idle_sleep_ns")
     d->idleSleepNs = v;
+  else if (k == "eager_notify")
+    d->eagerNotify = v;
   else if (k == "precise_wake")
     d->preciseWake = v;
   else if (k == "batch_idle_ns")

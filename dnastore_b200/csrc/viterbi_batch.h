@@ -104,6 +104,7 @@ struct BatchArgs {
   double2* sdPub;                // [nTeams][2][Np][32] (S,D) rows of states with successors in other CTAs (T > 1), by column parity
   uint32_t* teamState;           // [nTeams][T] per CTA: 1 passive | 2 notified (T > 1), zeroed before every launch
   uint32_t* inbox;               // [nTeams][Np] per state: work-mask bits flagged by other CTAs (T > 1), zeroed before every launch
+  uint32_t eagerNotify;          // 1: every notification is also sent once before the release fence (see flushRemote)
   uint32_t preciseWake;          // 1: a notified CTA takes its inbox words; 0: it re-relaxes every transition that crosses CTAs
   uint32_t* teamPassive;         // [nTeams][2] passive CTAs of the current column, by column parity, zeroed before every launch
   unsigned long long* barrier;   // [nTeams] team barrier counters (monotonic), zeroed before every launch

@@ -359,7 +359,19 @@ __global__ void __launch_bounds__(W * 32, 1)
           const uint4 h = hdrS[((uint32_t)__ffs((int)rp) - 1u) * W + warp];
           nNotes += bhNOut(h) - bhNOutLocal(h) - bhNOutRemote(h);
         }
-        if (lane == 0) redAdd32(passiveCol, 0u - nNotes);
+        const bool eager = args.eagerNotify != 0 && !args.preciseWake;
+        if (lane == 0) redAdd32(passiveCol, 0u - (eager ? 2u * nNotes : nNotes));
+        if (eager) {
+          // Eager notification: sent at once, WITHOUT waiting for the fence.  The rows were stored a few hundred cycles ago
+          // and usually are visible when the target reads them; if not, the target relaxes against the old rows, finds
+          // nothing, and the second notification below -- after the fence -- wakes it again.  Both are counted.
+          __syncwarp();
+          for (uint32_t rp = remotePending; rp; rp &= rp - 1u) {
+            const uint4 h = hdrS[((uint32_t)__ffs((int)rp) - 1u) * W + warp];
+            const uint32_t first = bhOutOff(h) + bhNOutLocal(h) + bhNOutRemote(h), last = bhOutOff(h) + bhNOut(h);
+            for (uint32_t o = first + lane; o < last; o += 32) redAdd32(notifyT + outS[o], 1u);
+          }
+        }
         fenceRelease();
         __syncwarp();
         if (args.preciseWake) {
