@@ -417,10 +417,11 @@ def short_fwdback(d, util, n_reads=296):
                 max_abs_loglike_back_minus_forward=float(np.abs(out["loglike_back"] - out["loglike"]).max()))
 
 
-def short_pairhmm(d, n_distinct=1024, copies=32, seed=77):
+def short_pairhmm(d, n_distinct=8192, copies=16, seed=77):
     """Batched pair-HMM forward + backward + expected counts on synthetic alignments:
     reference-encoded ~200-nt strands mutated by the errdecode.pl simulator with the alignment kept
-    (benchdata/synth.mutate_aligned), n_distinct alignments repeated `copies` times. DP cells = envelope cells x (2 + k);
+    (benchdata/synth.mutate_aligned), n_distinct alignments repeated `copies` times (the kernel deals alignments to warps in
+    order of length, so a warp of 32 holds at least 32 / copies different alignments). DP cells = envelope cells x (2 + k);
     16 algorithmic bytes per DP cell (the forward cell is written once and read once by the counts pass)."""
     from benchdata import synth
     rng = np.random.default_rng(seed)
@@ -445,7 +446,7 @@ def short_pairhmm(d, n_distinct=1024, copies=32, seed=77):
     d.pairhmm_fb_batch(params, base, strict=False)  # warm-up
     fwd, back, _counts, ms = d.pairhmm_fb_batch(params, aligns, strict=False)
     peak, _ = measured_peak()
-    return dict(workload=f"pair-HMM forward + backward + expected counts, {len(aligns)} alignments of ~200-nt strands, k = {k}, banded envelope",
+    return dict(workload=f"pair-HMM forward + backward + expected counts, {len(aligns)} alignments ({len(base)} distinct) of ~200-nt strands, k = {k}, banded envelope",
                 alignments=len(aligns), dp_cells=cells, kernel_ms=ms, alignments_per_sec=len(aligns) / (ms * 1e-3),
                 cells_per_sec=cells / (ms * 1e-3), roofline_frac=16.0 * cells / (ms * 1e-3) / 1e9 / peak, kernel="pairHmmFwdBackKernel",
                 max_abs_back_minus_fwd=float(np.abs(np.asarray(fwd) - np.asarray(back)).max()))
@@ -488,7 +489,7 @@ def main():
     if args.mode == "pairhmm":
         if rank == 0:
             import dnastore_b200 as d
-            print(json.dumps(short_pairhmm(d, copies=max(1, args.reads_per_step // 1024) if args.reads_per_step else 32)), flush=True)
+            print(json.dumps(short_pairhmm(d, copies=max(1, args.reads_per_step // 8192) if args.reads_per_step else 16)), flush=True)
         return
     import torch
     import torch.distributed as dist

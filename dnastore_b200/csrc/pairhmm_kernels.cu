@@ -32,17 +32,27 @@ struct PairScores {
   int k;
 };
 
+// Layout of a batch.  32 consecutive alignments form a warp (lane = alignment); everything a warp touches in one step is
+// lane-interleaved, so the lanes read and write whole lines:
+//   * the warp walks the UNION of its lanes' envelopes: row ip covers op in [loW[ip], hiW[ip]] (min / max over the lanes), a
+//     lane takes part in a cell when the cell is inside its own envelope [lo, hi];
+//   * component m of the warp's cell c (counted over the union rows) of lane l sits at ((cellBase + c) * (2+k) + m) * 32 + l;
+//   * tokens, per-lane lo / hi: [warp base + position][32].
 struct PairBatch {
   int64_t n;
-  const uint8_t* in;        // concatenated tokens
-  const uint8_t* out;
-  const int64_t* inOff;     // [n+1]
-  const int64_t* outOff;    // [n+1]
-  const int32_t* lo;        // concatenated per-row ranges, row r of alignment i at rowBase[i]+r
+  const uint8_t* in;        // [inBase[w] + p][32] tokens of the original strands
+  const uint8_t* out;       // [outBase[w] + p][32]
+  const int32_t* inLen;     // [n]
+  const int32_t* outLen;    // [n]
+  const int32_t* lo;        // [rowBase[w] + ip][32] the lane's own envelope row (lo > hi: no cell)
   const int32_t* hi;
-  const int64_t* rowOff;    // cell offset of each row (same indexing as lo/hi), relative to cellBase[i]
-  const int64_t* rowBase;   // [n+1]
-  const int64_t* cellBase;  // [n+1] first cell of each alignment in F / B
+  const int32_t* loW;       // [rowBase[w] + ip] union over the warp
+  const int32_t* hiW;
+  const int64_t* rowOff;    // [rowBase[w] + ip] first cell of the union row, relative to cellBase[w]
+  const int64_t* rowBase;   // [nWarps + 1]
+  const int64_t* cellBase;  // [nWarps]
+  const int64_t* inBase;    // [nWarps]
+  const int64_t* outBase;   // [nWarps]
   double* F;
   double* B;
   const double* lseTable;
@@ -53,108 +63,192 @@ struct PairBatch {
 
 __device__ __forceinline__ double ninf() { return __longlong_as_double(0xFFF0000000000000LL); }
 
-__global__ void pairHmmFwdBackKernel(const PairScores sc, const PairBatch pb) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= pb.n) return;
+// K = compile-time bound on the duplication depth k (the cell's components live in registers); every cell is computed in
+// registers and written ONCE (no -inf fill of the two matrices), and the neighbour in the same row -- F(ip,op-1) on the way
+// forward, B(ip,op+1) on the way back -- is the cell the lane has just computed, so only the other row is read from memory.
+// Operand order of every log_sum_exp is the reference's (src/fwdback.cpp:46-76, :84-114, :154-188); every lane visits its
+// own cells in the reference's order, so the expected counts are accumulated in the reference's order too.
+// PHASE 0: blocks [0, gridDim/2) fill F, blocks [gridDim/2, gridDim) fill B (the two recursions are independent);
+// PHASE 1: the expected counts from both.  Separate launches keep each phase's register count -- and with it the number of
+// resident warps that hide the latency of the log_sum_exp table look-ups (800 KB: L2, not L1) -- small.
+template <int K, int PHASE>
+__global__ void __launch_bounds__(64) pairHmmFwdBackKernel(const PairScores sc, const PairBatch pb) {
+  const int halfGrid = PHASE == 0 ? (int)(gridDim.x >> 1) : 0;
+  const bool backward = PHASE == 0 && (int)blockIdx.x >= halfGrid;
+  const int64_t i = (int64_t)(blockIdx.x - (backward ? halfGrid : 0)) * blockDim.x + threadIdx.x;
+  const int64_t w = i >> 5;
+  if (w * 32 >= pb.n) return;  // whole warp past the end (a partial last warp keeps its idle lanes: the loops are warp-uniform)
+  const bool live = i < pb.n;
+  const int lane = threadIdx.x & 31;
   const int k = sc.k, W = 2 + k;
-  const uint8_t* in = pb.in + pb.inOff[i];
-  const uint8_t* out = pb.out + pb.outOff[i];
-  const int inLen = (int)(pb.inOff[i + 1] - pb.inOff[i]), outLen = (int)(pb.outOff[i + 1] - pb.outOff[i]);
-  const int32_t* lo = pb.lo + pb.rowBase[i];
-  const int32_t* hi = pb.hi + pb.rowBase[i];
-  const int64_t* rowOff = pb.rowOff + pb.rowBase[i];
-  double* F = pb.F + pb.cellBase[i] * W;
-  double* B = pb.B + pb.cellBase[i] * W;
+  const int inLen = live ? pb.inLen[i] : -1, outLen = live ? pb.outLen[i] : -1;
+  const int64_t rowBase = pb.rowBase[w];
+  const int rows = (int)(pb.rowBase[w + 1] - rowBase);
+  const uint8_t* in = pb.in + pb.inBase[w] * 32 + lane;
+  const uint8_t* out = pb.out + pb.outBase[w] * 32 + lane;
+  const int32_t* loL = pb.lo + rowBase * 32 + lane;
+  const int32_t* hiL = pb.hi + rowBase * 32 + lane;
+  const int32_t* loW = pb.loW + rowBase;
+  const int32_t* hiW = pb.hiW + rowBase;
+  const int64_t* rowOff = pb.rowOff + rowBase;
+  double* F = pb.F + pb.cellBase[w] * W * 32 + lane;
+  double* B = pb.B + pb.cellBase[w] * W * 32 + lane;
   const double* T = pb.lseTable;
   const double NEG = ninf();
-  const int64_t nCells = pb.cellBase[i + 1] - pb.cellBase[i];
-  for (int64_t c = 0; c < nCells * W; ++c) {
-    F[c] = NEG;
-    B[c] = NEG;
-  }
-  auto inr = [&](int ip, int op) { return ip >= 0 && ip <= inLen && op >= lo[ip] && op <= hi[ip]; };
-  auto at = [&](double* M, int ip, int op) { return M + (rowOff[ip] + (op - lo[ip])) * W; };
+  auto lo = [&](int ip) { return loL[ip * 32]; };
+  auto hi = [&](int ip) { return hiL[ip * 32]; };
+  auto inr = [&](int ip, int op) { return ip >= 0 && ip <= inLen && op >= lo(ip) && op <= hi(ip); };
+  auto at = [&](double* M, int ip, int op) { return M + (rowOff[ip] + (op - loW[ip])) * W * 32; };
   auto mdl = [&](int ip) { return k < ip ? k : ip; };
-  auto sub = [&](int ip, int op) { return sc.sub[in[ip - 1] * 4 + out[op - 1]]; };
-  auto tsub = [&](int ip, int op, int d) { return sc.sub[in[ip - 1 - d] * 4 + out[op - 1]]; };
+  auto inTok = [&](int p) { return (int)in[p * 32]; };
+  auto outTok = [&](int p) { return (int)out[p * 32]; };
+  auto sub = [&](int ip, int op) { return sc.sub[inTok(ip - 1) * 4 + outTok(op - 1)]; };
+  auto tsub = [&](int ip, int op, int d) { return sc.sub[inTok(ip - 1 - d) * 4 + outTok(op - 1)]; };
 
-  // ---- forward (src/fwdback.cpp:46-76)
-  if (inr(0, 0)) at(F, 0, 0)[0] = 0;
-  for (int ip = 0; ip <= inLen; ++ip)
-    for (int op = lo[ip]; op <= hi[ip]; ++op) {
-      double* cell = at(F, ip, op);
-      if (ip > 0 && op > 0) {
-        if (inr(ip - 1, op - 1)) cell[0] = at(F, ip - 1, op - 1)[0] + sc.noGap + sub(ip, op);
-        if (inr(ip, op - 1)) {
-          const double* ins = at(F, ip, op - 1);
-          for (int d = 0; d < mdl(ip) - 1; ++d) cell[2 + d] = ins[2 + d + 1] + tsub(ip, op, d + 1);
-          cell[0] = lse(T, cell[0], ins[2] + tsub(ip, op, 0));
+  if (PHASE == 0 && !backward) {
+    // ---- forward (src/fwdback.cpp:46-76)
+    for (int ip = 0; ip < rows; ++ip) {
+      double prev[K + 2];  // F(ip, op-1)
+      const int m = mdl(ip), myLo = ip <= inLen ? lo(ip) : 1, myHi = ip <= inLen ? hi(ip) : 0;
+      for (int op = loW[ip]; op <= hiW[ip]; ++op) {
+        if (op < myLo || op > myHi) continue;
+        double c[K + 2];
+#pragma unroll
+        for (int d = 0; d < K + 2; ++d) c[d] = NEG;
+        if (ip == 0 && op == 0) c[0] = 0;
+        if (ip > 0 && op > 0) {
+          if (inr(ip - 1, op - 1)) c[0] = at(F, ip - 1, op - 1)[0] + sc.noGap + sub(ip, op);
+          if (op > myLo) {
+#pragma unroll
+            for (int d = 0; d < K - 1; ++d)
+              if (d < m - 1) c[2 + d] = prev[2 + d + 1] + tsub(ip, op, d + 1);
+            c[0] = lse(T, c[0], prev[2] + tsub(ip, op, 0));
+          }
+        }
+        if (ip > 0 && inr(ip - 1, op)) {
+          const double* del = at(F, ip - 1, op);
+          c[1] = lse(T, del[0] + sc.delOpen, del[32] + sc.delExtend);
+        }
+        c[0] = lse(T, c[0], c[1] + sc.delEnd);
+#pragma unroll
+        for (int d = 0; d < K; ++d)
+          if (d < m) c[2 + d] = lse(T, c[2 + d], c[0] + sc.tanDup + sc.len[d]);
+        double* cell = at(F, ip, op);
+#pragma unroll
+        for (int d = 0; d < K + 2; ++d) {
+          if (d < W) cell[d * 32] = c[d];
+          prev[d] = c[d];
         }
       }
-      if (ip > 0 && inr(ip - 1, op)) {
-        const double* del = at(F, ip - 1, op);
-        cell[1] = lse(T, del[0] + sc.delOpen, del[1] + sc.delExtend);
-      }
-      cell[0] = lse(T, cell[0], cell[1] + sc.delEnd);
-      for (int d = 0; d < mdl(ip); ++d) cell[2 + d] = lse(T, cell[2 + d], cell[0] + sc.tanDup + sc.len[d]);
     }
-  const double ll = inr(inLen, outLen) ? at(F, inLen, outLen)[0] : NEG;
-  pb.fwdLL[i] = ll;
+    if (live) pb.fwdLL[i] = inr(inLen, outLen) ? at(F, inLen, outLen)[0] : NEG;
+  }
 
-  // ---- backward (src/fwdback.cpp:84-114)
-  if (inr(inLen, outLen)) at(B, inLen, outLen)[0] = 0;
-  for (int ip = inLen; ip >= 0; --ip)
-    for (int op = hi[ip]; op >= lo[ip]; --op) {
-      double* cell = at(B, ip, op);
-      if (op < outLen) {
-        if (ip < inLen && inr(ip + 1, op + 1)) cell[0] = sc.noGap + sub(ip + 1, op + 1) + at(B, ip + 1, op + 1)[0];
-        if (ip > 0 && inr(ip, op + 1)) {
-          const double* ins = at(B, ip, op + 1);
-          for (int d = 1; d < mdl(ip); ++d) cell[2 + d] = tsub(ip, op + 1, d) + ins[2 + d - 1];
-          cell[2] = tsub(ip, op + 1, 0) + ins[0];
+  if (PHASE == 0 && backward) {
+    // ---- backward (src/fwdback.cpp:84-114)
+    for (int ip = rows - 1; ip >= 0; --ip) {
+      double prev[K + 2];  // B(ip, op+1)
+      const int m = mdl(ip), myLo = ip <= inLen ? lo(ip) : 1, myHi = ip <= inLen ? hi(ip) : 0;
+      for (int op = hiW[ip]; op >= loW[ip]; --op) {
+        if (op < myLo || op > myHi) continue;
+        double c[K + 2];
+#pragma unroll
+        for (int d = 0; d < K + 2; ++d) c[d] = NEG;
+        if (ip == inLen && op == outLen) c[0] = 0;
+        if (op < outLen) {
+          if (ip < inLen && inr(ip + 1, op + 1)) c[0] = sc.noGap + sub(ip + 1, op + 1) + at(B, ip + 1, op + 1)[0];
+          if (ip > 0 && op < myHi) {
+#pragma unroll
+            for (int d = 1; d < K; ++d)
+              if (d < m) c[2 + d] = tsub(ip, op + 1, d) + prev[2 + d - 1];
+            c[2] = tsub(ip, op + 1, 0) + prev[0];
+          }
+        }
+        if (ip < inLen && inr(ip + 1, op)) {
+          const double* del = at(B, ip + 1, op);
+          c[0] = lse(T, c[0], sc.delOpen + del[32]);
+          c[1] = sc.delExtend + del[32];
+        }
+#pragma unroll
+        for (int d = 0; d < K; ++d)
+          if (d < m) c[0] = lse(T, c[0], c[2 + d] + sc.tanDup + sc.len[d]);
+        c[1] = lse(T, c[1], c[0] + sc.delEnd);
+        double* cell = at(B, ip, op);
+#pragma unroll
+        for (int d = 0; d < K + 2; ++d) {
+          if (d < W) cell[d * 32] = c[d];
+          prev[d] = c[d];
         }
       }
-      if (ip < inLen && inr(ip + 1, op)) {
-        const double* del = at(B, ip + 1, op);
-        cell[0] = lse(T, cell[0], sc.delOpen + del[1]);
-        cell[1] = sc.delExtend + del[1];
-      }
-      for (int d = 0; d < mdl(ip); ++d) cell[0] = lse(T, cell[0], cell[2 + d] + sc.tanDup + sc.len[d]);
-      cell[1] = lse(T, cell[1], cell[0] + sc.delEnd);
     }
-  pb.backLL[i] = inr(0, 0) ? at(B, 0, 0)[0] : NEG;
+    if (live) pb.backLL[i] = inr(0, 0) ? at(B, 0, 0)[0] : NEG;
+  }
 
+  if (PHASE != 1) return;
   // ---- expected counts (src/fwdback.cpp:154-188); cells outside the envelope read as -inf
-  double* cnt = pb.counts + i * (5 + k + 16);
-  for (int c = 0; c < 5 + k + 16; ++c) cnt[c] = 0;
-  double *nLen = cnt + 5, *nSub = cnt + 5 + k;
-  auto fget = [&](int ip, int op, int m) { return inr(ip, op) ? at(F, ip, op)[m] : NEG; };
-  for (int ip = 0; ip <= inLen; ++ip)
-    for (int op = lo[ip]; op <= hi[ip]; ++op) {
+  const double ll = live ? pb.fwdLL[i] : NEG;
+  // the 16 substitution counts live in shared memory (one column per thread): a dynamically indexed register array would
+  // cost a 16-way select per update
+  __shared__ double nSubS[16][64];
+  double acc[5], nLen[K];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) acc[c] = 0;
+#pragma unroll
+  for (int c = 0; c < K; ++c) nLen[c] = 0;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) nSubS[c][threadIdx.x] = 0;
+  auto addSub = [&](int idx, double v) { nSubS[idx][threadIdx.x] += v; };
+  auto fget = [&](int ip, int op, int mm) { return inr(ip, op) ? at(F, ip, op)[mm * 32] : NEG; };
+  for (int ip = 0; ip < rows; ++ip) {
+    const int myLo = ip <= inLen ? lo(ip) : 1, myHi = ip <= inLen ? hi(ip) : 0;
+    for (int op = loW[ip]; op <= hiW[ip]; ++op) {
+      if (op < myLo || op > myHi) continue;
       const double* bc = at(B, ip, op);
       if (ip > 0 && op > 0) {
         const double c = exp(fget(ip - 1, op - 1, 0) + sc.noGap + sub(ip, op) + bc[0] - ll);
-        cnt[2] += c;
-        nSub[in[ip - 1] * 4 + out[op - 1]] += c;
+        acc[2] += c;
+        addSub(inTok(ip - 1) * 4 + outTok(op - 1), c);
         for (int d = 0; d < mdl(ip) - 1; ++d) {
-          const double ci = exp(fget(ip, op - 1, 2 + d + 1) + tsub(ip, op, d + 1) + bc[2 + d] - ll);
-          nSub[in[ip - 1 - (d + 1)] * 4 + out[op - 1]] += ci;
+          const double ci = exp(fget(ip, op - 1, 2 + d + 1) + tsub(ip, op, d + 1) + bc[(2 + d) * 32] - ll);
+          addSub(inTok(ip - 1 - (d + 1)) * 4 + outTok(op - 1), ci);
         }
         const double c0 = exp(fget(ip, op - 1, 2) + tsub(ip, op, 0) + bc[0] - ll);
-        nSub[in[ip - 1] * 4 + out[op - 1]] += c0;
+        addSub(inTok(ip - 1) * 4 + outTok(op - 1), c0);
       }
       if (ip > 0) {
-        cnt[0] += exp(fget(ip - 1, op, 0) + sc.delOpen + bc[1] - ll);
-        cnt[3] += exp(fget(ip - 1, op, 1) + sc.delExtend + bc[1] - ll);
+        acc[0] += exp(fget(ip - 1, op, 0) + sc.delOpen + bc[32] - ll);
+        acc[3] += exp(fget(ip - 1, op, 1) + sc.delExtend + bc[32] - ll);
       }
       const double* fc = at(F, ip, op);
-      cnt[4] += exp(fc[1] + sc.delEnd + bc[0] - ll);
-      for (int d = 0; d < mdl(ip); ++d) {
-        const double c = exp(fc[0] + sc.tanDup + sc.len[d] + bc[2 + d] - ll);
-        cnt[1] += c;
-        nLen[d] += c;
-      }
+      acc[4] += exp(fc[32] + sc.delEnd + bc[0] - ll);
+#pragma unroll
+      for (int d = 0; d < K; ++d)
+        if (d < mdl(ip)) {
+          const double c = exp(fc[0] + sc.tanDup + sc.len[d] + bc[(2 + d) * 32] - ll);
+          acc[1] += c;
+          nLen[d] += c;
+        }
     }
+  }
+  if (!live) return;
+  double* cnt = pb.counts + i * (5 + k + 16);
+#pragma unroll
+  for (int c = 0; c < 5; ++c) cnt[c] = acc[c];
+#pragma unroll
+  for (int c = 0; c < K; ++c)
+    if (c < k) cnt[5 + c] = nLen[c];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) cnt[5 + k + c] = nSubS[c][threadIdx.x];
+}
+
+typedef void (*PairKernelPtr)(const PairScores, const PairBatch);
+template <int PHASE>
+static PairKernelPtr pickPairKernel(int k) {
+  if (k <= 2) return pairHmmFwdBackKernel<2, PHASE>;
+  if (k <= 4) return pairHmmFwdBackKernel<4, PHASE>;
+  if (k <= 6) return pairHmmFwdBackKernel<6, PHASE>;
+  if (k <= 8) return pairHmmFwdBackKernel<8, PHASE>;
+  return pairHmmFwdBackKernel<kMaxDup, PHASE>;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -202,63 +296,104 @@ bool pairHmmFwdBackBatch(int device, const MutatorParams& params, bool strict, c
                           nullScore;
   for (int l = 0; l < k; ++l) sc.len[l] = std::log(params.pLen[l]);
 
-  // envelope rows: inRange(ip,op) <=> |a[ip]-b[op]| <= maxDistance, a contiguous run of op per ip
+  // envelope rows: inRange(ip,op) <=> |a[ip]-b[op]| <= maxDistance, a contiguous run of op per ip.
+  // Alignments are independent, so they are dealt to the warps in order of length (slot s = rank in that order): the lanes
+  // of a warp then walk envelopes of nearly the same shape and the union rows hold few idle cells.
   const int maxDist = strict ? 0 : k;
+  std::vector<int64_t> order((size_t)n);
+  for (int64_t i = 0; i < n; ++i) order[(size_t)i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+    return aligns[(size_t)x].a.size() != aligns[(size_t)y].a.size() ? aligns[(size_t)x].a.size() < aligns[(size_t)y].a.size()
+                                                                     : aligns[(size_t)x].out.size() < aligns[(size_t)y].out.size();
+  });
+  const int64_t nWarps = (n + 31) / 32;
   std::vector<uint8_t> in, out;
-  std::vector<int64_t> inOff{0}, outOff{0}, rowOff, rowBase{0}, cellBase{0};
-  std::vector<int32_t> lo, hi;
-  for (const auto& al : aligns) {
-    in.insert(in.end(), al.in.begin(), al.in.end());
-    out.insert(out.end(), al.out.begin(), al.out.end());
-    inOff.push_back((int64_t)in.size());
-    outOff.push_back((int64_t)out.size());
-    int64_t cells = 0;
-    const int outLen = (int)al.out.size();
-    for (size_t ip = 0; ip < al.a.size(); ++ip) {
-      int l = outLen + 1, h = -1;
-      for (int op = 0; op <= outLen; ++op)
-        if (std::abs(al.a[ip] - al.b[op]) <= maxDist) {
-          l = std::min(l, op);
-          h = std::max(h, op);
-        }
-      lo.push_back(l);
-      hi.push_back(h);
-      rowOff.push_back(cells);
-      if (h >= l) cells += h - l + 1;
+  std::vector<int32_t> inLen((size_t)n), outLen((size_t)n), lo, hi, loW, hiW;
+  std::vector<int64_t> rowOff, rowBase{0}, cellBase, inBase, outBase;
+  int64_t totalCells = 0;
+  for (int64_t w = 0; w < nWarps; ++w) {
+    const int64_t first = w * 32, lanes = std::min<int64_t>(32, n - first);
+    size_t rows = 0, maxIn = 0, maxOut = 0;
+    for (int64_t l = 0; l < lanes; ++l) {
+      const PairAlignment& al = aligns[(size_t)order[(size_t)(first + l)]];
+      rows = std::max(rows, al.a.size());
+      maxIn = std::max(maxIn, al.in.size());
+      maxOut = std::max(maxOut, al.out.size());
+      inLen[(size_t)(first + l)] = (int32_t)al.in.size();
+      outLen[(size_t)(first + l)] = (int32_t)al.out.size();
     }
-    rowBase.push_back((int64_t)lo.size());
-    cellBase.push_back(cellBase.back() + cells);
+    inBase.push_back((int64_t)in.size() / 32);
+    outBase.push_back((int64_t)out.size() / 32);
+    in.resize(in.size() + maxIn * 32, 0);
+    out.resize(out.size() + maxOut * 32, 0);
+    const size_t r0 = loW.size();
+    lo.resize((r0 + rows) * 32, 1);  // lo > hi: the lane has no cell in this row
+    hi.resize((r0 + rows) * 32, 0);
+    loW.resize(r0 + rows, INT32_MAX);
+    hiW.resize(r0 + rows, -1);
+    for (int64_t l = 0; l < lanes; ++l) {
+      const PairAlignment& al = aligns[(size_t)order[(size_t)(first + l)]];
+      for (size_t p = 0; p < al.in.size(); ++p) in[((size_t)inBase.back() + p) * 32 + (size_t)l] = al.in[p];
+      for (size_t p = 0; p < al.out.size(); ++p) out[((size_t)outBase.back() + p) * 32 + (size_t)l] = al.out[p];
+      const int oLen = (int)al.out.size();
+      int from = 0;  // b[] is non-decreasing: the run of row ip starts no earlier than the run of row ip-1
+      for (size_t ip = 0; ip < al.a.size(); ++ip) {
+        if (ip > 0 && al.a[ip] < al.a[ip - 1]) from = 0;
+        while (from <= oLen && al.b[(size_t)from] < al.a[ip] - maxDist) ++from;
+        int to = from;
+        while (to <= oLen && al.b[(size_t)to] <= al.a[ip] + maxDist) ++to;
+        const int lcur = from, hcur = to - 1;
+        if (hcur >= lcur) {
+          lo[(r0 + ip) * 32 + (size_t)l] = lcur;
+          hi[(r0 + ip) * 32 + (size_t)l] = hcur;
+          loW[r0 + ip] = std::min(loW[r0 + ip], lcur);
+          hiW[r0 + ip] = std::max(hiW[r0 + ip], hcur);
+        }
+      }
+    }
+    cellBase.push_back(totalCells);
+    int64_t cells = 0;
+    for (size_t ip = 0; ip < rows; ++ip) {
+      if (hiW[r0 + ip] < 0) loW[r0 + ip] = 0;  // nobody has a cell here: an empty union row
+      rowOff.push_back(cells);
+      if (hiW[r0 + ip] >= loW[r0 + ip]) cells += hiW[r0 + ip] - loW[r0 + ip] + 1;
+    }
+    totalCells += cells;
+    rowBase.push_back((int64_t)loW.size());
   }
   const int W = 2 + k, nc = 5 + k + 16;
   PairBatch pb{};
   pb.n = n;
   uint8_t *dIn = nullptr, *dOut = nullptr;
-  int64_t *dInOff = nullptr, *dOutOff = nullptr, *dRowOff = nullptr, *dRowBase = nullptr, *dCellBase = nullptr;
-  int32_t *dLo = nullptr, *dHi = nullptr;
+  int64_t *dRowOff = nullptr, *dRowBase = nullptr, *dCellBase = nullptr, *dInBase = nullptr, *dOutBase = nullptr;
+  int32_t *dLo = nullptr, *dHi = nullptr, *dLoW = nullptr, *dHiW = nullptr, *dInLen = nullptr, *dOutLen = nullptr;
   double *dF = nullptr, *dB = nullptr, *dTable = nullptr, *dFwd = nullptr, *dBack = nullptr, *dCounts = nullptr;
-  const size_t cellDoubles = (size_t)std::max<int64_t>(cellBase.back(), 1) * W;
-  bool ok = upload(dIn, in) && upload(dOut, out) && upload(dInOff, inOff) && upload(dOutOff, outOff) &&
-            upload(dRowOff, rowOff) && upload(dRowBase, rowBase) && upload(dCellBase, cellBase) && upload(dLo, lo) &&
-            upload(dHi, hi) && upload(dTable, logSumExpLookupTable()) &&
-            cudaMalloc(&dF, cellDoubles * sizeof(double)) == cudaSuccess &&
+  const size_t cellDoubles = (size_t)std::max<int64_t>(totalCells, 1) * W * 32;
+  if (in.empty()) in.resize(32, 0);
+  if (out.empty()) out.resize(32, 0);
+  bool ok = upload(dIn, in) && upload(dOut, out) && upload(dInLen, inLen) && upload(dOutLen, outLen) &&
+            upload(dRowOff, rowOff) && upload(dRowBase, rowBase) && upload(dCellBase, cellBase) && upload(dInBase, inBase) &&
+            upload(dOutBase, outBase) && upload(dLo, lo) && upload(dHi, hi) && upload(dLoW, loW) && upload(dHiW, hiW) &&
+            upload(dTable, logSumExpLookupTable()) && cudaMalloc(&dF, cellDoubles * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&dB, cellDoubles * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&dFwd, n * sizeof(double)) == cudaSuccess && cudaMalloc(&dBack, n * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&dCounts, (size_t)n * nc * sizeof(double)) == cudaSuccess;
-  std::vector<double> hc((size_t)n * nc);
+  std::vector<double> hc((size_t)n * nc), hf((size_t)n), hb((size_t)n);
   if (ok) {
-    pb.in = dIn; pb.out = dOut; pb.inOff = dInOff; pb.outOff = dOutOff; pb.lo = dLo; pb.hi = dHi;
-    pb.rowOff = dRowOff; pb.rowBase = dRowBase; pb.cellBase = dCellBase; pb.F = dF; pb.B = dB;
-    pb.lseTable = dTable; pb.fwdLL = dFwd; pb.backLL = dBack; pb.counts = dCounts;
+    pb.in = dIn; pb.out = dOut; pb.inLen = dInLen; pb.outLen = dOutLen; pb.lo = dLo; pb.hi = dHi; pb.loW = dLoW; pb.hiW = dHiW;
+    pb.rowOff = dRowOff; pb.rowBase = dRowBase; pb.cellBase = dCellBase; pb.inBase = dInBase; pb.outBase = dOutBase;
+    pb.F = dF; pb.B = dB; pb.lseTable = dTable; pb.fwdLL = dFwd; pb.backLL = dBack; pb.counts = dCounts;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     const int threads = 64, blocks = (int)((n + threads - 1) / threads);
     cudaEventRecord(e0);
-    pairHmmFwdBackKernel<<<blocks, threads>>>(sc, pb);
+    pickPairKernel<0>(k)<<<2 * blocks, threads>>>(sc, pb);
+    pickPairKernel<1>(k)<<<blocks, threads>>>(sc, pb);
     cudaEventRecord(e1);
     ok = cudaGetLastError() == cudaSuccess &&
-         cudaMemcpy(fwdLL.data(), dFwd, n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&
-         cudaMemcpy(backLL.data(), dBack, n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&
+         cudaMemcpy(hf.data(), dFwd, n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&
+         cudaMemcpy(hb.data(), dBack, n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&
          cudaMemcpy(hc.data(), dCounts, hc.size() * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
     float ms = 0;
     if (ok && kernelMs && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *kernelMs = ms;
@@ -266,12 +401,16 @@ bool pairHmmFwdBackBatch(int device, const MutatorParams& params, bool strict, c
     cudaEventDestroy(e1);
   }
   if (!ok) setLastError(std::string("pair-HMM forward/backward: CUDA error: ") + cudaGetErrorString(cudaGetLastError()));
-  for (void* p : {(void*)dIn, (void*)dOut, (void*)dInOff, (void*)dOutOff, (void*)dRowOff, (void*)dRowBase, (void*)dCellBase,
-                  (void*)dLo, (void*)dHi, (void*)dF, (void*)dB, (void*)dTable, (void*)dFwd, (void*)dBack, (void*)dCounts})
+  for (void* p : {(void*)dIn, (void*)dOut, (void*)dInLen, (void*)dOutLen, (void*)dRowOff, (void*)dRowBase, (void*)dCellBase,
+                  (void*)dInBase, (void*)dOutBase, (void*)dLo, (void*)dHi, (void*)dLoW, (void*)dHiW, (void*)dF, (void*)dB,
+                  (void*)dTable, (void*)dFwd, (void*)dBack, (void*)dCounts})
     if (p) cudaFree(p);
   if (!ok) return false;
-  for (int64_t i = 0; i < n; ++i) {
-    const double* c = hc.data() + (size_t)i * nc;
+  for (int64_t slot = 0; slot < n; ++slot) {
+    const size_t i = (size_t)order[(size_t)slot];
+    fwdLL[i] = hf[(size_t)slot];
+    backLL[i] = hb[(size_t)slot];
+    const double* c = hc.data() + (size_t)slot * nc;
     MutatorCounts& m = counts[i];
     m.nDelOpen = c[0];
     m.nTanDup = c[1];

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(W * 32, 1)
     __syncthreads();
   };
 
-  unsigned long long dbgLevels = 0, dbgVisits = 0, dbgEdges = 0, dbgWakes = 0, dbgClosure = 0, dbgRecord = 0, dbgPassive = 0;
+  unsigned long long dbgLevels = 0, dbgVisits = 0, dbgEdges = 0, dbgWakes = 0, dbgClosure = 0, dbgRecord = 0, dbgPassive = 0, dbgInit = 0, dbgBarrier = 0, dbgRelaxCyc = 0, dbgFlushCyc = 0;
 
   for (int64_t group = team; group < args.nGroups; group += args.nTeams) {
     const int64_t slotIdx = group * 32 + lane;
@@ -221,6 +221,8 @@ __global__ void __launch_bounds__(W * 32, 1)
       }
       const uint32_t par = col & 1u;  // columns are numbered across groups: the parity alternates without a break
       ++col;
+      unsigned long long stamp = 0;
+      if (kDebug) stamp = clock64();
       double2* const sdPubCol = sdPubT + (size_t)par * Np * 32;
       double2* const sdPubNext = sdPubT + (size_t)(par ^ 1u) * Np * 32;
       uint32_t* const passiveCol = passiveT + par;
@@ -246,10 +248,18 @@ __global__ void __launch_bounds__(W * 32, 1)
         ctl[kCtlPending] = 0u;  // asynchronous closure: number of warps that found nothing to do
         ctl[kCtlPhase] = 0u;
       }
+      if (kDebug) {
+        const unsigned long long t = clock64();
+        dbgInit += t - stamp;
+        stamp = t;
+      }
       teamBarrier();
       if (kTeam && rank == 0 && tid == 0) stRelaxed32(passiveT + (par ^ 1u), 0u);  // the other parity's count is dead: reset it for the next column
-      unsigned long long stamp = 0;
-      if (kDebug) stamp = clock64();
+      if (kDebug) {
+        const unsigned long long t = clock64();
+        dbgBarrier += t - stamp;
+        stamp = t;
+      }
 
       // ---- (2) closure (src/viterbi.cpp:97-99,110-159), owner-computes edge relaxation ----
       const bool asyncClosure = args.asyncClosure != 0;
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(W * 32, 1)
           const uint4 h = hdrS[((uint32_t)__ffs((int)rp) - 1u) * W + warp];
           nNotes += bhNOut(h) - bhNOutLocal(h) - bhNOutRemote(h);
         }
-        const bool eager = args.eagerNotify != 0 && !args.preciseWake;
+        const bool eager = (args.eagerNotify & 1u) != 0 && !args.preciseWake;
         if (lane == 0) redAdd32(passiveCol, 0u - (eager ? 2u * nNotes : nNotes));
         if (eager) {
           // Eager notification: sent at once, WITHOUT waiting for the fence.  The rows were stored a few hundred cycles ago
@@ -413,9 +423,17 @@ __global__ void __launch_bounds__(W * 32, 1)
           if (d >= M) break;
           if (lane == 0) maskCur[d] = 0u;  // (a flag set after this store is kept; one set before it is served by this relaxation)
           __syncwarp();
+          unsigned long long tr = 0;
+          if (kDebug) tr = clock64();
           relax(sl, 0, true);
+          if (kDebug) dbgRelaxCyc += clock64() - tr;
         }
-        flushRemote();
+        {
+          unsigned long long tr = 0;
+          if (kDebug) tr = clock64();
+          flushRemote();
+          if (kDebug) dbgFlushCyc += clock64() - tr;
+        }
         for (;;) {
           uint32_t mym = 0;
           if (mineValid) mym = reinterpret_cast<volatile uint32_t*>(maskCur)[iMine];
@@ -432,9 +450,18 @@ __global__ void __launch_bounds__(W * 32, 1)
               work &= work - 1u;
               const uint32_t m = __shfl_sync(0xFFFFFFFFu, mym, sl);
               if (kDebug) ++dbgVisits;
+              unsigned long long tr = 0;
+              if (kDebug) tr = clock64();
               relax(sl, m, false);
+              if (kDebug) dbgRelaxCyc += clock64() - tr;
+              if (kTeam && (args.eagerNotify & 2u) && work) flushRemote();  // do not let the other flagged states delay this one's news
             }
-            flushRemote();
+            {
+              unsigned long long tr = 0;
+              if (kDebug) tr = clock64();
+              flushRemote();
+              if (kDebug) dbgFlushCyc += clock64() - tr;
+            }
             continue;
           }
           if (!idle) {
@@ -493,14 +520,27 @@ __global__ void __launch_bounds__(W * 32, 1)
             if (lane == 0) atomicSub(idleS, 1u);
             idle = false;
             __syncwarp();
-            for (uint32_t i = lane; i < M; i += 32) {
-              uint32_t rm = remInS[i];
-              if (rm && args.preciseWake) {  // only the transitions whose sources were published (the bits were set before the notification)
-                uint32_t* box = inboxT + rank * M + i;
-                rm = ldVolatileGlobal32(box);
-                if (rm) rm = atomicExch(box, 0u);
+            if (args.preciseWake) {
+              // only the transitions whose sources were published (the bits were set before the notification); the inbox
+              // words are read side by side (one L2 round trip for all of them), then taken, then flagged
+              constexpr uint32_t kBox = 16;  // 32 * 16 >= the largest M that fits shared memory
+              uint32_t bx[kBox];
+#pragma unroll
+              for (uint32_t u = 0; u < kBox; ++u) {
+                const uint32_t i = lane + 32u * u;
+                bx[u] = (i < M && remInS[i]) ? ldVolatileGlobal32(inboxT + rank * M + i) : 0u;
               }
-              if (rm) atomicOr(maskCur + i, rm);
+#pragma unroll
+              for (uint32_t u = 0; u < kBox; ++u)
+                if (bx[u]) bx[u] = atomicExch(inboxT + rank * M + lane + 32u * u, 0u);
+#pragma unroll
+              for (uint32_t u = 0; u < kBox; ++u)
+                if (bx[u]) atomicOr(maskCur + lane + 32u * u, bx[u]);
+            } else {
+              for (uint32_t i = lane; i < M; i += 32) {
+                const uint32_t rm = remInS[i];
+                if (rm) atomicOr(maskCur + i, rm);
+              }
             }
           } else if (args.idleNs)
             __nanosleep(args.idleNs / 2);
@@ -772,6 +812,10 @@ __global__ void __launch_bounds__(W * 32, 1)
     if (warp == 0) atomicAdd(&args.dbg[5], dbgRecord);
     if (warp == 0) atomicAdd(&args.dbg[6], dbgWakes);
     if (warp == 0) atomicAdd(&args.dbg[7], dbgPassive);
+    if (warp == 0) atomicAdd(&args.dbg[8], dbgInit);
+    if (warp == 0) atomicAdd(&args.dbg[9], dbgBarrier);
+    atomicAdd(&args.dbg[10], dbgRelaxCyc);
+    atomicAdd(&args.dbg[11], dbgFlushCyc);
   }
 }
 
