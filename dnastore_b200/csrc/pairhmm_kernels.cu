@@ -95,77 +95,99 @@ __global__ void __launch_bounds__(64) pairHmmFwdBackKernel(const PairScores sc, 
   double* B = pb.B + pb.cellBase[w] * W * 32 + lane;
   const double* T = pb.lseTable;
   const double NEG = ninf();
-  auto lo = [&](int ip) { return loL[ip * 32]; };
-  auto hi = [&](int ip) { return hiL[ip * 32]; };
-  auto inr = [&](int ip, int op) { return ip >= 0 && ip <= inLen && op >= lo(ip) && op <= hi(ip); };
-  auto at = [&](double* M, int ip, int op) { return M + (rowOff[ip] + (op - loW[ip])) * W * 32; };
+  const int64_t WS = (int64_t)W * 32;  // doubles from one cell to the next
+  // Everything that depends on the row only is fetched once per row: the lane's own range, the range of the neighbouring
+  // row (rows are walked in order, so it is the previous iteration's), the row's first cell (cell (ip, op) of matrix M is
+  // rowPtr(M, ip) + op * WS) and the input tokens the row's transitions look at.
+  auto ownLo = [&](int ip) { return ip <= inLen ? loL[ip * 32] : 1; };
+  auto ownHi = [&](int ip) { return ip <= inLen ? hiL[ip * 32] : 0; };
+  auto rowPtr = [&](double* M, int ip) { return M + (rowOff[ip] - loW[ip]) * WS; };
   auto mdl = [&](int ip) { return k < ip ? k : ip; };
-  auto inTok = [&](int p) { return (int)in[p * 32]; };
   auto outTok = [&](int p) { return (int)out[p * 32]; };
-  auto sub = [&](int ip, int op) { return sc.sub[inTok(ip - 1) * 4 + outTok(op - 1)]; };
-  auto tsub = [&](int ip, int op, int d) { return sc.sub[inTok(ip - 1 - d) * 4 + outTok(op - 1)]; };
+  auto rowTokens = [&](int ip, int (&tok)[K]) {  // tok[d] = in[ip-1-d]: the token under the transition that copies (d = 0) or re-reads it
+#pragma unroll
+    for (int d = 0; d < K; ++d) tok[d] = d < ip ? (int)in[(ip - 1 - d) * 32] : 0;
+  };
 
   if (PHASE == 0 && !backward) {
     // ---- forward (src/fwdback.cpp:46-76)
+    int pLo = 1, pHi = 0;  // the lane's range in row ip-1
     for (int ip = 0; ip < rows; ++ip) {
+      const int m = mdl(ip), myLo = ownLo(ip), myHi = ownHi(ip), uLo = loW[ip], uHi = hiW[ip];
+      double* const cur = rowPtr(F, ip);
+      const double* const prv = rowPtr(F, ip > 0 ? ip - 1 : 0);
+      int tok[K];
+      rowTokens(ip, tok);
       double prev[K + 2];  // F(ip, op-1)
-      const int m = mdl(ip), myLo = ip <= inLen ? lo(ip) : 1, myHi = ip <= inLen ? hi(ip) : 0;
-      for (int op = loW[ip]; op <= hiW[ip]; ++op) {
+      for (int op = uLo; op <= uHi; ++op) {
         if (op < myLo || op > myHi) continue;
         double c[K + 2];
 #pragma unroll
         for (int d = 0; d < K + 2; ++d) c[d] = NEG;
         if (ip == 0 && op == 0) c[0] = 0;
         if (ip > 0 && op > 0) {
-          if (inr(ip - 1, op - 1)) c[0] = at(F, ip - 1, op - 1)[0] + sc.noGap + sub(ip, op);
+          const int ot = outTok(op - 1);
+          if (op - 1 >= pLo && op - 1 <= pHi) c[0] = prv[(op - 1) * WS] + sc.noGap + sc.sub[tok[0] * 4 + ot];
           if (op > myLo) {
 #pragma unroll
             for (int d = 0; d < K - 1; ++d)
-              if (d < m - 1) c[2 + d] = prev[2 + d + 1] + tsub(ip, op, d + 1);
-            c[0] = lse(T, c[0], prev[2] + tsub(ip, op, 0));
+              if (d < m - 1) c[2 + d] = prev[2 + d + 1] + sc.sub[tok[d + 1] * 4 + ot];
+            c[0] = lse(T, c[0], prev[2] + sc.sub[tok[0] * 4 + ot]);
           }
         }
-        if (ip > 0 && inr(ip - 1, op)) {
-          const double* del = at(F, ip - 1, op);
+        if (ip > 0 && op >= pLo && op <= pHi) {
+          const double* del = prv + op * WS;
           c[1] = lse(T, del[0] + sc.delOpen, del[32] + sc.delExtend);
         }
         c[0] = lse(T, c[0], c[1] + sc.delEnd);
 #pragma unroll
         for (int d = 0; d < K; ++d)
           if (d < m) c[2 + d] = lse(T, c[2 + d], c[0] + sc.tanDup + sc.len[d]);
-        double* cell = at(F, ip, op);
+        double* cell = cur + op * WS;
 #pragma unroll
         for (int d = 0; d < K + 2; ++d) {
           if (d < W) cell[d * 32] = c[d];
           prev[d] = c[d];
         }
       }
+      pLo = myLo;
+      pHi = myHi;
     }
-    if (live) pb.fwdLL[i] = inr(inLen, outLen) ? at(F, inLen, outLen)[0] : NEG;
+    if (live) {
+      const int eLo = ownLo(inLen), eHi = ownHi(inLen);
+      pb.fwdLL[i] = (outLen >= eLo && outLen <= eHi) ? rowPtr(F, inLen)[outLen * WS] : NEG;
+    }
   }
 
   if (PHASE == 0 && backward) {
     // ---- backward (src/fwdback.cpp:84-114)
+    int nLo = 1, nHi = 0;  // the lane's range in row ip+1
     for (int ip = rows - 1; ip >= 0; --ip) {
+      const int m = mdl(ip), myLo = ownLo(ip), myHi = ownHi(ip), uLo = loW[ip], uHi = hiW[ip];
+      double* const cur = rowPtr(B, ip);
+      const double* const nxt = rowPtr(B, ip + 1 < rows ? ip + 1 : ip);
+      int tok[K];
+      rowTokens(ip, tok);
+      const int tokNext = ip < inLen ? (int)in[ip * 32] : 0;  // in[ip]: the token row ip+1 copies
       double prev[K + 2];  // B(ip, op+1)
-      const int m = mdl(ip), myLo = ip <= inLen ? lo(ip) : 1, myHi = ip <= inLen ? hi(ip) : 0;
-      for (int op = hiW[ip]; op >= loW[ip]; --op) {
+      for (int op = uHi; op >= uLo; --op) {
         if (op < myLo || op > myHi) continue;
         double c[K + 2];
 #pragma unroll
         for (int d = 0; d < K + 2; ++d) c[d] = NEG;
         if (ip == inLen && op == outLen) c[0] = 0;
         if (op < outLen) {
-          if (ip < inLen && inr(ip + 1, op + 1)) c[0] = sc.noGap + sub(ip + 1, op + 1) + at(B, ip + 1, op + 1)[0];
+          const int ot = outTok(op);  // out[op]: the token under every move into column op+1
+          if (ip < inLen && op + 1 >= nLo && op + 1 <= nHi) c[0] = sc.noGap + sc.sub[tokNext * 4 + ot] + nxt[(op + 1) * WS];
           if (ip > 0 && op < myHi) {
 #pragma unroll
             for (int d = 1; d < K; ++d)
-              if (d < m) c[2 + d] = tsub(ip, op + 1, d) + prev[2 + d - 1];
-            c[2] = tsub(ip, op + 1, 0) + prev[0];
+              if (d < m) c[2 + d] = sc.sub[tok[d] * 4 + ot] + prev[2 + d - 1];
+            c[2] = sc.sub[tok[0] * 4 + ot] + prev[0];
           }
         }
-        if (ip < inLen && inr(ip + 1, op)) {
-          const double* del = at(B, ip + 1, op);
+        if (ip < inLen && op >= nLo && op <= nHi) {
+          const double* del = nxt + op * WS;
           c[0] = lse(T, c[0], sc.delOpen + del[32]);
           c[1] = sc.delExtend + del[32];
         }
@@ -173,15 +195,17 @@ __global__ void __launch_bounds__(64) pairHmmFwdBackKernel(const PairScores sc, 
         for (int d = 0; d < K; ++d)
           if (d < m) c[0] = lse(T, c[0], c[2 + d] + sc.tanDup + sc.len[d]);
         c[1] = lse(T, c[1], c[0] + sc.delEnd);
-        double* cell = at(B, ip, op);
+        double* cell = cur + op * WS;
 #pragma unroll
         for (int d = 0; d < K + 2; ++d) {
           if (d < W) cell[d * 32] = c[d];
           prev[d] = c[d];
         }
       }
+      nLo = myLo;
+      nHi = myHi;
     }
-    if (live) pb.backLL[i] = inr(0, 0) ? at(B, 0, 0)[0] : NEG;
+    if (live) pb.backLL[i] = (0 >= ownLo(0) && 0 <= ownHi(0)) ? rowPtr(B, 0)[0] : NEG;
   }
 
   if (PHASE != 1) return;
@@ -198,37 +222,49 @@ __global__ void __launch_bounds__(64) pairHmmFwdBackKernel(const PairScores sc, 
 #pragma unroll
   for (int c = 0; c < 16; ++c) nSubS[c][threadIdx.x] = 0;
   auto addSub = [&](int idx, double v) { nSubS[idx][threadIdx.x] += v; };
-  auto fget = [&](int ip, int op, int mm) { return inr(ip, op) ? at(F, ip, op)[mm * 32] : NEG; };
+  int pLo = 1, pHi = 0;
   for (int ip = 0; ip < rows; ++ip) {
-    const int myLo = ip <= inLen ? lo(ip) : 1, myHi = ip <= inLen ? hi(ip) : 0;
-    for (int op = loW[ip]; op <= hiW[ip]; ++op) {
+    const int m = mdl(ip), myLo = ownLo(ip), myHi = ownHi(ip), uLo = loW[ip], uHi = hiW[ip];
+    const double* const fcur = rowPtr(F, ip);
+    const double* const fprv = rowPtr(F, ip > 0 ? ip - 1 : 0);
+    const double* const bcur = rowPtr(B, ip);
+    int tok[K];
+    rowTokens(ip, tok);
+    for (int op = uLo; op <= uHi; ++op) {
       if (op < myLo || op > myHi) continue;
-      const double* bc = at(B, ip, op);
+      const double* bc = bcur + op * WS;
+      const double* fc = fcur + op * WS;
       if (ip > 0 && op > 0) {
-        const double c = exp(fget(ip - 1, op - 1, 0) + sc.noGap + sub(ip, op) + bc[0] - ll);
+        const int ot = outTok(op - 1);
+        const bool diag = op - 1 >= pLo && op - 1 <= pHi, left = op > myLo;
+        const double c = exp((diag ? fprv[(op - 1) * WS] : NEG) + sc.noGap + sc.sub[tok[0] * 4 + ot] + bc[0] - ll);
         acc[2] += c;
-        addSub(inTok(ip - 1) * 4 + outTok(op - 1), c);
-        for (int d = 0; d < mdl(ip) - 1; ++d) {
-          const double ci = exp(fget(ip, op - 1, 2 + d + 1) + tsub(ip, op, d + 1) + bc[(2 + d) * 32] - ll);
-          addSub(inTok(ip - 1 - (d + 1)) * 4 + outTok(op - 1), ci);
-        }
-        const double c0 = exp(fget(ip, op - 1, 2) + tsub(ip, op, 0) + bc[0] - ll);
-        addSub(inTok(ip - 1) * 4 + outTok(op - 1), c0);
+        addSub(tok[0] * 4 + ot, c);
+#pragma unroll
+        for (int d = 0; d < K - 1; ++d)
+          if (d < m - 1) {
+            const double ci = exp((left ? fc[(2 + d + 1) * 32 - WS] : NEG) + sc.sub[tok[d + 1] * 4 + ot] + bc[(2 + d) * 32] - ll);
+            addSub(tok[d + 1] * 4 + ot, ci);
+          }
+        const double c0 = exp((left ? fc[2 * 32 - WS] : NEG) + sc.sub[tok[0] * 4 + ot] + bc[0] - ll);
+        addSub(tok[0] * 4 + ot, c0);
       }
       if (ip > 0) {
-        acc[0] += exp(fget(ip - 1, op, 0) + sc.delOpen + bc[32] - ll);
-        acc[3] += exp(fget(ip - 1, op, 1) + sc.delExtend + bc[32] - ll);
+        const bool up = op >= pLo && op <= pHi;
+        acc[0] += exp((up ? fprv[op * WS] : NEG) + sc.delOpen + bc[32] - ll);
+        acc[3] += exp((up ? fprv[op * WS + 32] : NEG) + sc.delExtend + bc[32] - ll);
       }
-      const double* fc = at(F, ip, op);
       acc[4] += exp(fc[32] + sc.delEnd + bc[0] - ll);
 #pragma unroll
       for (int d = 0; d < K; ++d)
-        if (d < mdl(ip)) {
+        if (d < m) {
           const double c = exp(fc[0] + sc.tanDup + sc.len[d] + bc[(2 + d) * 32] - ll);
           acc[1] += c;
           nLen[d] += c;
         }
     }
+    pLo = myLo;
+    pHi = myHi;
   }
   if (!live) return;
   double* cnt = pb.counts + i * (5 + k + 16);
