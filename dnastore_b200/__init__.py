@@ -21,6 +21,7 @@ from ._capi import (  # noqa: F401
     MutatorCounts,
     PairDb,
     pairhmm_fb_batch,
+    pairhmm_set_chunk_cells,
     expected_counts,
     baum_welch,
     ExactDecoder,
@@ -36,7 +37,7 @@ from ._capi import (  # noqa: F401
 
 __all__ = [
     "DnabError", "Machine", "ErrorFlags", "Compiled", "Decoder", "MultiDecoder", "Tables", "lib", "lib_path", "pack_reads", "MutatorParams", "MutatorCounts", "PairDb",
-    "pairhmm_fb_batch", "expected_counts", "baum_welch",
+    "pairhmm_fb_batch", "pairhmm_set_chunk_cells", "expected_counts", "baum_welch",
     "ExactDecoder", "exact_decode_bits", "exact_decode_string", "exact_decode_fasta", "pack_decoded_symbols",
     "READ_OK", "READ_NO_DECODING", "READ_OVERFLOW", "READ_TRACEBACK_FAILED",
 ]

@@ -177,6 +177,7 @@ _sig("dnab_pair_db_out", C.POINTER(C.c_uint8), _vp, C.c_int64)
 _sig("dnab_pair_db_env_a", C.POINTER(C.c_int32), _vp, C.c_int64)
 _sig("dnab_pair_db_env_b", C.POINTER(C.c_int32), _vp, C.c_int64)
 _sig("dnab_pair_db_free", None, _vp)
+_sig("dnab_pairhmm_set_chunk_cells", C.c_int, C.c_int64)
 _sig("dnab_pairhmm_fb_batch", C.c_int, C.c_int, C.POINTER(MutatorParams), C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp,
      _vp, _vp, _vp, C.POINTER(C.c_double))
 _sig("dnab_expected_counts", C.c_int, C.c_int, C.POINTER(MutatorParams), _vp, C.c_int, C.POINTER(MutatorCounts),
@@ -441,6 +442,11 @@ class PairDb:
         if getattr(self, "_h", None):
             lib.dnab_pair_db_free(self._h)
             self._h = None
+
+
+def pairhmm_set_chunk_cells(cells):
+    """Cap on the envelope cells one pair-HMM launch keeps on the device (0 = automatic); results do not depend on it."""
+    lib.dnab_pairhmm_set_chunk_cells(int(cells))
 
 
 def pairhmm_fb_batch(params, aligns, strict=False, device=0):

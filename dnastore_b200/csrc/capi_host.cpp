@@ -247,6 +247,11 @@ const int32_t* dnab_pair_db_env_a(const dnab_pair_db* db, int64_t i) { return db
 const int32_t* dnab_pair_db_env_b(const dnab_pair_db* db, int64_t i) { return db->aligns[i].b.data(); }
 void dnab_pair_db_free(dnab_pair_db* db) { delete db; }
 
+int dnab_pairhmm_set_chunk_cells(int64_t cells) {
+  dnab::setPairHmmChunkCells(cells);
+  return DNAB_OK;
+}
+
 int dnab_pairhmm_fb_batch(int device, const dnab_mutator_params* p, int strict, int64_t n_align, const uint8_t* in_tok,
                           const int64_t* in_off, const uint8_t* out_tok, const int64_t* out_off, const int32_t* env_a,
                           const int32_t* env_b, double* fwd_ll, double* back_ll, dnab_mutator_counts* counts,

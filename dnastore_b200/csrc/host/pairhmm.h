@@ -53,6 +53,10 @@ bool pairHmmFwdBackBatch(int device, const MutatorParams& params, bool strictAli
                          const std::vector<PairAlignment>& aligns, std::vector<double>& fwdLL,
                          std::vector<double>& backLL, std::vector<MutatorCounts>& counts, double* kernelMs = nullptr);
 
+// Upper bound on the union-envelope cells (per warp of 32 alignments) one launch keeps in F and in B; 0 = as many as fit
+// 40 % of the free device memory each.  Results do not depend on it.
+void setPairHmmChunkCells(int64_t cells);
+
 // expectedCounts (src/fwdback.cpp:190-209) and baumWelchParams (:211-230) over a database.
 bool expectedCounts(int device, const MutatorParams& params, const std::vector<PairAlignment>& db, bool strict,
                     MutatorCounts& total, double& loglike);

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <string>
@@ -40,6 +42,8 @@ struct PairScores {
 //   * tokens, per-lane lo / hi: [warp base + position][32].
 struct PairBatch {
   int64_t n;
+  int64_t firstWarp;        // this launch covers warps [firstWarp, firstWarp + gridDim-many): a chunk that fits F and B
+  int64_t cellOrigin;       // cellBase of firstWarp: F and B hold the chunk's cells only
   const uint8_t* in;        // [inBase[w] + p][32] tokens of the original strands
   const uint8_t* out;       // [outBase[w] + p][32]
   const int32_t* inLen;     // [n]
@@ -75,7 +79,7 @@ template <int K, int PHASE>
 __global__ void __launch_bounds__(64) pairHmmFwdBackKernel(const PairScores sc, const PairBatch pb) {
   const int halfGrid = PHASE == 0 ? (int)(gridDim.x >> 1) : 0;
   const bool backward = PHASE == 0 && (int)blockIdx.x >= halfGrid;
-  const int64_t i = (int64_t)(blockIdx.x - (backward ? halfGrid : 0)) * blockDim.x + threadIdx.x;
+  const int64_t i = pb.firstWarp * 32 + (int64_t)(blockIdx.x - (backward ? halfGrid : 0)) * blockDim.x + threadIdx.x;
   const int64_t w = i >> 5;
   if (w * 32 >= pb.n) return;  // whole warp past the end (a partial last warp keeps its idle lanes: the loops are warp-uniform)
   const bool live = i < pb.n;
@@ -91,8 +95,8 @@ __global__ void __launch_bounds__(64) pairHmmFwdBackKernel(const PairScores sc, 
   const int32_t* loW = pb.loW + rowBase;
   const int32_t* hiW = pb.hiW + rowBase;
   const int64_t* rowOff = pb.rowOff + rowBase;
-  double* F = pb.F + pb.cellBase[w] * W * 32 + lane;
-  double* B = pb.B + pb.cellBase[w] * W * 32 + lane;
+  double* F = pb.F + (pb.cellBase[w] - pb.cellOrigin) * W * 32 + lane;
+  double* B = pb.B + (pb.cellBase[w] - pb.cellOrigin) * W * 32 + lane;
   const double* T = pb.lseTable;
   const double NEG = ninf();
   const int64_t WS = (int64_t)W * 32;  // doubles from one cell to the next
@@ -295,6 +299,9 @@ static bool upload(T*& d, const std::vector<T>& h) {
   return h.empty() || cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
 }
 
+static std::atomic<int64_t> gPairChunkCells{0};
+void setPairHmmChunkCells(int64_t cells) { gPairChunkCells.store(cells < 0 ? 0 : cells); }
+
 bool pairHmmFwdBackBatch(int device, const MutatorParams& params, bool strict, const std::vector<PairAlignment>& aligns,
                          std::vector<double>& fwdLL, std::vector<double>& backLL, std::vector<MutatorCounts>& counts,
                          double* kernelMs) {
@@ -404,7 +411,29 @@ bool pairHmmFwdBackBatch(int device, const MutatorParams& params, bool strict, c
   int64_t *dRowOff = nullptr, *dRowBase = nullptr, *dCellBase = nullptr, *dInBase = nullptr, *dOutBase = nullptr;
   int32_t *dLo = nullptr, *dHi = nullptr, *dLoW = nullptr, *dHiW = nullptr, *dInLen = nullptr, *dOutLen = nullptr;
   double *dF = nullptr, *dB = nullptr, *dTable = nullptr, *dFwd = nullptr, *dBack = nullptr, *dCounts = nullptr;
-  const size_t cellDoubles = (size_t)std::max<int64_t>(totalCells, 1) * W * 32;
+  // F and B of the whole batch may not fit the device (131,072 alignments of 200 nt at k = 6: 43 GB): the warps are run in
+  // chunks of consecutive warps (an even number, a block holds two) whose cells fit a budget of 40 % of the free memory
+  // each for F and B
+  cellBase.push_back(totalCells);
+  size_t freeB = 0, totalB = 0;
+  cudaMemGetInfo(&freeB, &totalB);
+  int64_t budgetCells = std::max<int64_t>((int64_t)((double)freeB * 0.4 / ((double)W * 32 * sizeof(double))), 1);
+  if (gPairChunkCells.load() > 0) budgetCells = std::min(budgetCells, gPairChunkCells.load());
+  std::vector<int64_t> chunkFirst{0};
+  int64_t chunkCells = 0;
+  for (int64_t w = 0; w < nWarps; w += 2) {
+    const int64_t pairCells = cellBase[(size_t)std::min(w + 2, nWarps)] - cellBase[(size_t)w];
+    if (chunkCells > 0 && chunkCells + pairCells > budgetCells) {
+      chunkFirst.push_back(w);
+      chunkCells = 0;
+    }
+    chunkCells += pairCells;
+  }
+  chunkFirst.push_back(nWarps);
+  int64_t maxChunkCells = 1;
+  for (size_t c = 0; c + 1 < chunkFirst.size(); ++c)
+    maxChunkCells = std::max(maxChunkCells, cellBase[(size_t)chunkFirst[c + 1]] - cellBase[(size_t)chunkFirst[c]]);
+  const size_t cellDoubles = (size_t)maxChunkCells * W * 32;
   if (in.empty()) in.resize(32, 0);
   if (out.empty()) out.resize(32, 0);
   bool ok = upload(dIn, in) && upload(dOut, out) && upload(dInLen, inLen) && upload(dOutLen, outLen) &&
@@ -422,10 +451,16 @@ bool pairHmmFwdBackBatch(int device, const MutatorParams& params, bool strict, c
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const int threads = 64, blocks = (int)((n + threads - 1) / threads);
+    const int threads = 64;
     cudaEventRecord(e0);
-    pickPairKernel<0>(k)<<<2 * blocks, threads>>>(sc, pb);
-    pickPairKernel<1>(k)<<<blocks, threads>>>(sc, pb);
+    for (size_t c = 0; c + 1 < chunkFirst.size(); ++c) {
+      pb.firstWarp = chunkFirst[c];
+      pb.cellOrigin = cellBase[(size_t)chunkFirst[c]];
+      const int blocks = (int)((chunkFirst[c + 1] - chunkFirst[c] + 1) / 2);
+      if (blocks <= 0) continue;
+      pickPairKernel<0>(k)<<<2 * blocks, threads>>>(sc, pb);
+      pickPairKernel<1>(k)<<<blocks, threads>>>(sc, pb);
+    }
     cudaEventRecord(e1);
     ok = cudaGetLastError() == cudaSuccess &&
          cudaMemcpy(hf.data(), dFwd, n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&

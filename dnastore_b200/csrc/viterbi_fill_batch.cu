@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(W * 32, 1)
           const uint4 h = hdrS[((uint32_t)__ffs((int)rp) - 1u) * W + warp];
           nNotes += bhNOut(h) - bhNOutLocal(h) - bhNOutRemote(h);
         }
-        const bool eager = (args.eagerNotify & 1u) != 0 && !args.preciseWake;
+        const bool eager = args.eagerNotify != 0 && !args.preciseWake;
         if (lane == 0) redAdd32(passiveCol, 0u - (eager ? 2u * nNotes : nNotes));
         if (eager) {
           // Eager notification: sent at once, WITHOUT waiting for the fence.  The rows were stored a few hundred cycles ago
@@ -454,7 +454,6 @@ __global__ void __launch_bounds__(W * 32, 1)
               if (kDebug) tr = clock64();
               relax(sl, m, false);
               if (kDebug) dbgRelaxCyc += clock64() - tr;
-              if (kTeam && (args.eagerNotify & 2u) && work) flushRemote();  // do not let the other flagged states delay this one's news
             }
             {
               unsigned long long tr = 0;
@@ -520,27 +519,14 @@ __global__ void __launch_bounds__(W * 32, 1)
             if (lane == 0) atomicSub(idleS, 1u);
             idle = false;
             __syncwarp();
-            if (args.preciseWake) {
-              // only the transitions whose sources were published (the bits were set before the notification); the inbox
-              // words are read side by side (one L2 round trip for all of them), then taken, then flagged
-              constexpr uint32_t kBox = 16;  // 32 * 16 >= the largest M that fits shared memory
-              uint32_t bx[kBox];
-#pragma unroll
-              for (uint32_t u = 0; u < kBox; ++u) {
-                const uint32_t i = lane + 32u * u;
-                bx[u] = (i < M && remInS[i]) ? ldVolatileGlobal32(inboxT + rank * M + i) : 0u;
+            for (uint32_t i = lane; i < M; i += 32) {
+              uint32_t rm = remInS[i];
+              if (rm && args.preciseWake) {  // only the transitions whose sources were published (the bits were set before the notification)
+                uint32_t* box = inboxT + rank * M + i;
+                rm = ldVolatileGlobal32(box);
+                if (rm) rm = atomicExch(box, 0u);
               }
-#pragma unroll
-              for (uint32_t u = 0; u < kBox; ++u)
-                if (bx[u]) bx[u] = atomicExch(inboxT + rank * M + lane + 32u * u, 0u);
-#pragma unroll
-              for (uint32_t u = 0; u < kBox; ++u)
-                if (bx[u]) atomicOr(maskCur + lane + 32u * u, bx[u]);
-            } else {
-              for (uint32_t i = lane; i < M; i += 32) {
-                const uint32_t rm = remInS[i];
-                if (rm) atomicOr(maskCur + i, rm);
-              }
+              if (rm) atomicOr(maskCur + i, rm);
             }
           } else if (args.idleNs)
             __nanosleep(args.idleNs / 2);

@@ -398,7 +398,7 @@ const int32_t* dnab_pair_db_env_b(const dnab_pair_db* db, int64_t i);  /* out_le
 void dnab_pair_db_free(dnab_pair_db* db);
 
 /* Forward, backward and expected counts of a batch of alignments on `device` (one GPU thread per
- * alignment).  Alignment i: tokens in_tok[in_off[i]..in_off[i+1]), out_tok[out_off[i]..out_off[i+1]),
+ * alignment, 32 alignments of similar length per warp).  Alignment i: tokens in_tok[in_off[i]..in_off[i+1]), out_tok[out_off[i]..out_off[i+1]),
  * envelope env_a[in_off[i]+i ..] (in_len+1 entries) and env_b[out_off[i]+i ..] (out_len+1 entries).
  * strict != 0 <=> --strict-guides (maxDistance 0, else maxDupLen; src/fwdback.cpp:17).
  * fwd_ll = ForwardMatrix::loglike, back_ll = BackwardMatrix::loglike (bit-identical to the
@@ -407,6 +407,10 @@ int dnab_pairhmm_fb_batch(int device, const dnab_mutator_params* p, int strict, 
                           const int64_t* in_off, const uint8_t* out_tok, const int64_t* out_off, const int32_t* env_a,
                           const int32_t* env_b, double* fwd_ll, double* back_ll, dnab_mutator_counts* counts,
                           double* kernel_ms);
+/* The batch is run in chunks of alignments whose forward and backward cells fit the device: by default 40 % of the free
+ * memory each; `cells` > 0 caps a chunk at that many envelope cells per lane (tuning / testing; 0 = automatic).
+ * Results do not depend on it. */
+int dnab_pairhmm_set_chunk_cells(int64_t cells);
 /* expectedCounts (src/fwdback.cpp:190-209): counts summed and log-likelihoods added in database order. */
 int dnab_expected_counts(int device, const dnab_mutator_params* p, const dnab_pair_db* db, int strict,
                          dnab_mutator_counts* total, double* loglike);

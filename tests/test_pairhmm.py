@@ -166,3 +166,45 @@ def test_gpu_cli_error_counts_and_fit_error(tmp_path):
     out = subprocess.run([exe, "-v0", "--fit-error", str(stk), "--strict-guides"], capture_output=True, text=True, check=True).stdout
     fitted, _it = d.baum_welch(params_for(c), load_db(c, tmp_path), strict=True)
     assert out == fitted.to_json()
+
+
+def _mixed_alignments(tmp_path, n=330, seed=5):
+    """Alignments of very different lengths (3-150 nt) with substitutions, duplications and deletions: a warp of the kernel
+    holds 32 of them and walks the union of their envelopes."""
+    from benchdata import synth
+    rng = np.random.default_rng(seed)
+    pool = synth.load_pool("cfg1_l4c4_200b")
+    rows = []
+    for i in range(n):
+        strand = pool[i % len(pool)][:int(rng.integers(3, 150))]
+        a, b = synth.mutate_aligned(strand, rng, sub_rate=0.03, dup_rate=0.03, max_dup=3, del_rate=0.03, max_del=4)
+        if not a.replace("-", "") or not b.replace("-", ""):
+            continue
+        rows.append(f"# STOCKHOLM 1.0\nin  {a}\nout {b}\n//\n")
+    p = tmp_path / "mixed.stk"
+    p.write_text("".join(rows))
+    db = d.PairDb(p)
+    return [db.alignment(i) for i in range(len(db))]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strict", [False, True])
+def test_gpu_mixed_batch_matches_oracle_whatever_the_chunking(tmp_path, strict):
+    aligns = _mixed_alignments(tmp_path)
+    assert len(aligns) > 300 and len({len(a[0]) for a in aligns}) > 50
+    params = d.MutatorParams.from_flags(d.ErrorFlags(length=8, sub_prob=.03, dup_prob=.02, del_open=.02, del_ext=.3))
+    try:
+        runs = []
+        for cells in (0, 700, 1):  # automatic; a few warps per launch; one block (two warps) per launch
+            d.pairhmm_set_chunk_cells(cells)
+            runs.append(d.pairhmm_fb_batch(params, aligns, strict=strict))
+    finally:
+        d.pairhmm_set_chunk_cells(0)
+    fwd, back, counts, _ms = runs[0]
+    for i, al in enumerate(aligns):
+        of, ob, oc = oracle_fb(params, al, strict)
+        assert util.hexf(fwd[i]) == util.hexf(of) and util.hexf(back[i]) == util.hexf(ob), i
+        np.testing.assert_allclose(counts[i].flat(), oc, rtol=1e-12, atol=1e-300)
+    for f2, b2, c2, _ in runs[1:]:
+        assert np.asarray(f2).tobytes() == np.asarray(fwd).tobytes() and np.asarray(b2).tobytes() == np.asarray(back).tobytes()
+        assert all(np.array_equal(x.flat(), y.flat()) for x, y in zip(c2, counts))
