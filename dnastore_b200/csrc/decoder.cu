@@ -118,9 +118,8 @@ struct dnab_decoder {
   uint32_t wantTeam = 0;        // CTAs per team (0 = smallest that fits)
   uint32_t wantWarps = 0;       // warps per CTA (0 = 32)
   BatchPlan bplan;
-  uint32_t preciseWake = 0;     // 1: a notification re-relaxes only the transitions flagged in the inbox (option "precise_wake": half the
-                                // visits on watermark64.1*l4 but a second release fence on every hop: 5.6k vs 6.3k reads/s, 1,086 vs 1,282 on
-                                // the 46,670-state machine); 0: every transition that crosses CTAs
+  uint32_t notifyClasses = 32;  // option "notify_classes": notification counters per CTA of a team (1 = a notification wakes every
+                                // transition that crosses CTAs; 32 = a 32nd of them, one class per lane of the polling warp)
   uint32_t eagerNotify = 0;     // option "eager_notify"
   uint32_t batchIdleNs = 100;   // option "batch_idle_ns"
   uint32_t asyncClosure = 2;    // read-batched kernel: closure without level barriers: 0 off, 1 on, 2 automatic = in a team (option "async_closure")
@@ -131,7 +130,7 @@ struct dnab_decoder {
   BatchTraceTables btrace{};
   DevBuf<uint4> dbHdr;
   DevBuf<uint2> dbIn, dbRel, dbHdr2;
-  DevBuf<uint32_t> dbOut, dbRankInOff, dbRankOutOff, dbRemoteIn, dbEmitOff, dbEmitSrc, dbNullOff, dbNullSrc, dbTeamState, dbTeamPassive, dbInbox, dbPartOrig;
+  DevBuf<uint32_t> dbOut, dbRankInOff, dbRankOutOff, dbRemoteIn, dbEmitOff, dbEmitSrc, dbNullOff, dbNullSrc, dbTeamState, dbTeamPassive, dbClsOff, dbClsStates, dbPartOrig;
   DevBuf<uint8_t> dbEmitSym, dbNullSym;
   DevBuf<double> dbTsE, dbPriv, dbPartVal;
   DevBuf<double2> dbSdPub;
@@ -827,7 +826,7 @@ static int buildBatchPlan(dnab_decoder* d) {
   uint32_t T0 = std::max<uint32_t>(1, (uint32_t)(((size_t)N * kBatchReads * 16 + d->smemOptin - 1) / d->smemOptin));
   std::vector<uint4> hdr;
   std::vector<uint2> inE, relE, hdr2;
-  std::vector<uint32_t> outE, rankInOff, rankOutOff, newOf(N), origOf, remoteIn;
+  std::vector<uint32_t> outE, rankInOff, rankOutOff, newOf(N), origOf, remoteIn, clsOff, clsStates, clsOf;
   // builds the tables of a team of T CTAs; false when T is infeasible
   auto buildTeam = [&](uint32_t T, uint32_t M) -> bool {
     W = wantW ? wantW : (T > 1 ? 32u : 24u);
@@ -866,6 +865,32 @@ static int buildBatchPlan(dnab_decoder* d) {
       std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
       relPos[dst].resize(nIn);
       for (uint32_t q = 0; q < nIn; ++q) relPos[dst][idx[q]] = q;
+    }
+    // notification classes (T > 1): the states of a CTA that have a transition from another CTA are dealt round-robin into
+    // `notifyClasses` classes (1 = every notification wakes all of them)
+    clsOf.assign(Np, 0);
+    clsOff.assign((size_t)T * (kNotifyClasses + 1), 0);
+    clsStates.assign(Np, 0);
+    for (uint32_t r = 0; r < T; ++r) {
+      std::vector<std::vector<uint32_t>> byClass(kNotifyClasses);
+      uint32_t ord = 0;
+      for (uint32_t i = 0; i < M; ++i) {
+        const uint32_t s = origOf[r * M + i];
+        if (s == 0xFFFFFFFFu) continue;
+        bool remoteIn = false;
+        for (uint32_t e = d->emitOff[s]; e < d->emitOff[s + 1]; ++e) remoteIn |= newOf[d->emitSrc[e]] / M != r;
+        for (uint32_t e = d->nullOff[s]; e < d->nullOff[s + 1]; ++e) remoteIn |= newOf[d->nullSrc[e]] / M != r;
+        if (!remoteIn) continue;
+        const uint32_t c = (ord++) % std::max(1u, std::min(d->notifyClasses, kNotifyClasses));
+        clsOf[r * M + i] = c;
+        byClass[c].push_back(i);
+      }
+      uint32_t at = 0;
+      for (uint32_t c = 0; c < kNotifyClasses; ++c) {
+        clsOff[(size_t)r * (kNotifyClasses + 1) + c] = at;
+        for (uint32_t i : byClass[c]) clsStates[r * M + at++] = i;
+      }
+      clsOff[(size_t)r * (kNotifyClasses + 1) + kNotifyClasses] = at;
     }
     inE.clear();
     relE.clear();
@@ -913,31 +938,27 @@ static int buildBatchPlan(dnab_decoder* d) {
         }
         bool remoteOut = (d->local && s == 0 && T > 1);  // local mode: every CTA reads S(start,0) for the (0,0) escape
         uint32_t nLocal = 0;
-        std::vector<uint32_t> remoteCtas, remoteEdges;
-        for (const auto& o : outs[s]) {  // successors in this CTA first, then those in other CTAs, then the CTAs that own them
+        std::vector<uint32_t> remoteNotes;
+        for (const auto& o : outs[s]) {  // successors in this CTA first, then the (CTA, class) pairs that own the others
           const uint32_t dg = newOf[o.first];
           const uint32_t bit = std::min(relPos[o.first][o.second], 31u);
           if (dg / M != r) {
             remoteOut = true;
-            remoteCtas.push_back(dg / M);
-            remoteEdges.push_back((dg % M) | (bit << 16) | ((dg / M) << 21));
+            remoteNotes.push_back((dg / M) * kNotifyClasses + clsOf[dg]);
             continue;
           }
           ++nLocal;
           outE.push_back((dg % M) | (bit << 16));
         }
-        std::sort(remoteCtas.begin(), remoteCtas.end());
-        remoteCtas.erase(std::unique(remoteCtas.begin(), remoteCtas.end()), remoteCtas.end());
-        std::sort(remoteEdges.begin(), remoteEdges.end());
-        remoteEdges.erase(std::unique(remoteEdges.begin(), remoteEdges.end()), remoteEdges.end());
-        if (remoteEdges.size() > 63) return false;
-        outE.insert(outE.end(), remoteEdges.begin(), remoteEdges.end());
-        outE.insert(outE.end(), remoteCtas.begin(), remoteCtas.end());
-        const uint32_t nOutEntries = nLocal + (uint32_t)remoteEdges.size() + (uint32_t)remoteCtas.size();
+        std::sort(remoteNotes.begin(), remoteNotes.end());
+        remoteNotes.erase(std::unique(remoteNotes.begin(), remoteNotes.end()), remoteNotes.end());
+        outE.insert(outE.end(), remoteNotes.begin(), remoteNotes.end());
+        const uint32_t nOutEntries = nLocal + (uint32_t)remoteNotes.size();
+        if (nOutEntries > 255) return false;
         uint32_t ctxBits = 0;
         for (uint32_t t = 0; t < d->mdl[s]; ++t) ctxBits |= (uint32_t)(d->ctx[(size_t)s * k + t] & 3u) << (2 * t);
         hdr[r * M + i] = make_uint4(inOff | (outOff << 16), nE | (nN << 8) | (nOutEntries << 16) | ((uint32_t)d->mdl[s] << 24),
-                                    ctxBits | (remoteOut ? 1u << 16 : 0u) | (nLocal << 18) | ((uint32_t)remoteEdges.size() << 26), s);
+                                    ctxBits | (remoteOut ? 1u << 16 : 0u) | (nLocal << 18), s);
       }
       maxIn = std::max(maxIn, (uint32_t)inE.size() - rankInOff[r]);
       maxOut = std::max(maxOut, (uint32_t)outE.size() - rankOutOff[r]);
@@ -1011,6 +1032,8 @@ static int buildBatchPlan(dnab_decoder* d) {
   CUDA_TRY(d->dbRankInOff.upload(rankInOff));
   CUDA_TRY(d->dbRankOutOff.upload(rankOutOff));
   CUDA_TRY(d->dbRemoteIn.upload(remoteIn));
+  CUDA_TRY(d->dbClsOff.upload(clsOff));
+  CUDA_TRY(d->dbClsStates.upload(clsStates));
   // score tables with the traceback's association, formed once on the host in IEEE fp64 (-ffp-contract=off)
   std::vector<double> tsE((size_t)kMaxSyms * 16, 0.);
   for (uint32_t sym = 0; sym < d->symScore.size(); ++sym)
@@ -1026,6 +1049,8 @@ static int buildBatchPlan(dnab_decoder* d) {
   t.rankInOff = d->dbRankInOff.p;
   t.rankOutOff = d->dbRankOutOff.p;
   t.remoteIn = d->dbRemoteIn.p;
+  t.clsOff = d->dbClsOff.p;
+  t.clsStates = d->dbClsStates.p;
   t.hdr2 = d->dbHdr2.p;
   t.relEdges = d->dbRel.p;
   t.tsE = d->dbTsE.p;
@@ -1095,8 +1120,7 @@ static int buildBatchPlan(dnab_decoder* d) {
     }
   }
   CUDA_TRY(d->dbSdPub.ensure(bp.T > 1 ? (size_t)bp.nTeams * 2 * Np * 32 : 1));
-  CUDA_TRY(d->dbTeamState.ensure((size_t)bp.nTeams * bp.T));
-  CUDA_TRY(d->dbInbox.ensure(bp.T > 1 ? (size_t)bp.nTeams * Np : 1));
+  CUDA_TRY(d->dbTeamState.ensure((size_t)bp.nTeams * bp.T * kNotifyClasses));
   CUDA_TRY(d->dbTeamPassive.ensure((size_t)bp.nTeams * 2));
   CUDA_TRY(d->dbBarrier.ensure((size_t)bp.nTeams));
   return DNAB_OK;
@@ -1149,8 +1173,6 @@ static int runDeviceBatch(dnab_decoder* d, int64_t nReads, int32_t maxLen, const
     a.priv = d->dbPriv.p;
     a.sdPub = d->dbSdPub.p;
     a.teamState = d->dbTeamState.p;
-    a.inbox = d->dbInbox.p;
-    a.preciseWake = d->preciseWake;
     a.eagerNotify = d->eagerNotify;
     a.teamPassive = d->dbTeamPassive.p;
     a.barrier = d->dbBarrier.p;
@@ -1175,7 +1197,6 @@ static int runDeviceBatch(dnab_decoder* d, int64_t nReads, int32_t maxLen, const
     const bool rec = timeIt || pooled;
     if (bp.T > 1) {
       CUDA_TRY(cudaMemsetAsync(d->dbTeamState.p, 0, d->dbTeamState.n * sizeof(uint32_t), stream));
-      CUDA_TRY(cudaMemsetAsync(d->dbInbox.p, 0, d->dbInbox.n * sizeof(uint32_t), stream));
       CUDA_TRY(cudaMemsetAsync(d->dbTeamPassive.p, 0, d->dbTeamPassive.n * sizeof(uint32_t), stream));
       CUDA_TRY(cudaMemsetAsync(d->dbBarrier.p, 0, d->dbBarrier.n * sizeof(unsigned long long), stream));
     }
@@ -1505,8 +1526,8 @@ int dnab_decoder_set_option(dnab_decoder* d, const char* key, int64_t value) {
     d->idleSleepNs = v;
   else if (k == "eager_notify")
     d->eagerNotify = v;
-  else if (k == "precise_wake")
-    d->preciseWake = v;
+  else if (k == "notify_classes")
+    d->notifyClasses = v;
   else if (k == "batch_idle_ns")
     d->batchIdleNs = v;
   else if (k == "async_closure")

@@ -27,17 +27,18 @@ constexpr uint32_t kBatchAllEdges = 0xFFFFFFFFu;
 //
 //   header  uint4   x: inOff | outOff << 16        (entry offsets inside the rank's edge arrays)
 //                   y: nEmit | nNull << 8 | nOut << 16 | mdl << 24
-//                   z: ctx (2 bits per duplication index) | hasRemoteOut << 16 | pad << 17 | nOutLocal << 18 | nOutRemoteEdges << 26
+//                   z: ctx (2 bits per duplication index) | hasRemoteOut << 16 | pad << 17 | nOutLocal << 18
 //                      (successors in this CTA come first in the out-edge list)
 //                   w: reference state index (0xFFFFFFFF for padding)
 //   in-edge uint2   x: padded index g of the source
 //                   y: symbol id | base << 5 | remote << 7      (emit edges first, reference list order)
 //   out-edge u32    successors in this CTA: bits 0..15 destination's local index | 16..20 bit of the destination's
 //                   work mask (= index of this transition in the destination's in-edge list, 31 = "31 or later");
-//                   then the successors in other CTAs (same fields plus bits 21..30 = the owner's rank): their bit is set
-//                   in the owner's INBOX word of that state; then one entry per OTHER CTA that owns a successor: its
-//                   rank (the CTA whose notification counter is incremented)
+//                   then one entry per (OTHER CTA, class) that owns a successor: rank * kNotifyClasses + class, the index
+//                   of the notification counter that is incremented when this state publishes a new row
 //   remoteIn u32    per state: the bits of its work mask whose transitions come from other CTAs
+//   clsOff  u32     [T][kNotifyClasses + 1], clsStates u32 [T*M]: the CTA's states that have transitions from other CTAs,
+//                   grouped by notification class (local indices; class q = entries clsOff[q] .. clsOff[q+1])
 //   The closure reads its own copy of the in-transitions, grouped so that its loops have no per-edge branch:
 //   hdr2    uint2   x: offset of the state's relax entries inside the rank's array
 //                   y: local emit | local null << 8 | remote emit << 16 | remote null << 24   (counts, in this order)
@@ -54,7 +55,6 @@ __host__ __device__ inline uint32_t bhCtx(const uint4& h, uint32_t i) { return (
 __host__ __device__ inline uint32_t bhRemoteOut(const uint4& h) { return (h.z >> 16) & 1u; }
 __host__ __device__ inline uint32_t bhPad(const uint4& h) { return (h.z >> 17) & 1u; }
 __host__ __device__ inline uint32_t bhNOutLocal(const uint4& h) { return (h.z >> 18) & 0xFFu; }
-__host__ __device__ inline uint32_t bhNOutRemote(const uint4& h) { return h.z >> 26; }
 __host__ __device__ inline uint32_t beSym(const uint2& e) { return e.y & 31u; }
 __host__ __device__ inline uint32_t beBase(const uint2& e) { return (e.y >> 5) & 3u; }
 __host__ __device__ inline uint32_t beRemote(const uint2& e) { return (e.y >> 7) & 1u; }
@@ -62,6 +62,9 @@ __host__ __device__ inline uint32_t boLocal(uint32_t w) { return w & 0xFFFFu; }
 __host__ __device__ inline uint32_t boBit(uint32_t w) { return (w >> 16) & 31u; }
 __host__ __device__ inline uint32_t boRank(uint32_t w) { return (w >> 21) & 0x3FFu; }
 __host__ __device__ inline uint32_t boRemote(uint32_t w) { return w >> 31; }
+
+// classes of notification counters per CTA = lanes of the polling warp
+constexpr uint32_t kNotifyClasses = 32;
 
 struct BatchTables {
   uint32_t nStates, M, T, k, local, nSyms;
@@ -73,6 +76,8 @@ struct BatchTables {
   const uint32_t* rankInOff;     // [T+1]
   const uint32_t* rankOutOff;    // [T+1]
   const uint32_t* remoteIn;      // [T*M]
+  const uint32_t* clsOff;        // [T][kNotifyClasses + 1]
+  const uint32_t* clsStates;     // [T*M]
   const uint2* hdr2;             // [T*M]
   const uint2* relEdges;         // all ranks, rank r at rankInOff[r] (as many relax entries as in-edges)
   const double* tsE;             // [32 syms][4 bases][4 observed] (score+noGap)+sub: traceback association (src/viterbi.cpp:255)
@@ -102,10 +107,8 @@ struct BatchArgs {
                                  //   S0 of the next column (emission step fused into the record pass), the best emit candidate of
                                  //   its S record (traceback association), the k parked duplication cells
   double2* sdPub;                // [nTeams][2][Np][32] (S,D) rows of states with successors in other CTAs (T > 1), by column parity
-  uint32_t* teamState;           // [nTeams][T] per CTA: 1 passive | 2 notified (T > 1), zeroed before every launch
-  uint32_t* inbox;               // [nTeams][Np] per state: work-mask bits flagged by other CTAs (T > 1), zeroed before every launch
-  uint32_t eagerNotify;          // 1: every notification is also sent once before the release fence (see flushRemote)
-  uint32_t preciseWake;          // 1: a notified CTA takes its inbox words; 0: it re-relaxes every transition that crosses CTAs
+  uint32_t* teamState;           // [nTeams][T][kNotifyClasses] notification counters (T > 1), zeroed before every launch
+  uint32_t eagerNotify;          // 1: every notification is also sent once BEFORE the release fence (see flushRemote)
   uint32_t* teamPassive;         // [nTeams][2] passive CTAs of the current column, by column parity, zeroed before every launch
   unsigned long long* barrier;   // [nTeams] team barrier counters (monotonic), zeroed before every launch
   double* loglike;               // [nReads] global mode
@@ -116,7 +119,7 @@ struct BatchArgs {
 };
 
 struct BatchLayout {
-  uint32_t sd, maskA, maskB, remIn, hdr, hdr2, inE, relE, outE, tsE, sub, ctl, total;
+  uint32_t sd, maskA, maskB, remIn, cls, hdr, hdr2, inE, relE, outE, tsE, sub, ctl, total;
 };
 
 __host__ __device__ inline BatchLayout makeBatchLayout(uint32_t M, uint32_t maxIn, uint32_t maxOut, uint32_t nSyms, bool team) {
@@ -131,6 +134,7 @@ __host__ __device__ inline BatchLayout makeBatchLayout(uint32_t M, uint32_t maxI
   L.maskA = take(M * 4);
   L.maskB = take(M * 4);
   L.remIn = team ? take(M * 4) : 0;
+  L.cls = team ? take((kNotifyClasses + 1 + M) * 4) : 0;
   L.hdr = take(M * 16);
   L.hdr2 = take(M * 8);
   L.inE = take((maxIn + 1) * 8);

@@ -19,9 +19,9 @@
 // A TEAM of T CTAs holds the (S,D) columns of one group in shared memory, M = ceil(N/T) states each
 // (M*512 bytes); T = 1 for dnastore-l4, the whole GPU for the 46,670-state BASELINE machine.  Nothing
 // crosses CTAs through shared memory: a state with successors in other CTAs PUBLISHES its (S,D) row to an
-// L2-resident array whenever it grows and then flags the successor's bit in the owner's INBOX mask; the
-// owner drains its inbox when it runs out of local work, and the team meets at a counter barrier in L2
-// that also tells whether anybody flagged a remote bit since the last meeting.  Nothing is limited by the
+// L2-resident array whenever it grows and then adds 1 to a NOTIFICATION COUNTER of the owner CTA (one counter per
+// class of destination states, see the team protocol below); the owner polls its counters when it runs out of
+// local work, and the team meets at a counter barrier in L2 once per column.  Nothing is limited by the
 // 16-CTA cluster size, so machines that do not fit a cluster use the same code path.
 //
 // After the closure one dense pass per column (a) evaluates the predecessor records with the TRACEBACK's
@@ -76,7 +76,7 @@ __device__ __forceinline__ unsigned long long ldAcquire64(const unsigned long lo
   return v;
 }
 
-enum : uint32_t { kCtlFlag = 0, kCtlWake = 4, kCtlDecision = 8, kCtlPending = 16, kCtlPhase = 17 };
+enum : uint32_t { kCtlFlag = 0, kCtlWake = 4, kCtlDecision = 8, kCtlPending = 16, kCtlPhase = 17, kCtlLock = 18, kCtlSeen = 32 };
 constexpr uint32_t kKeepRecord = 0x100u;  // "the S record written by the previous column's pass stands"
 
 __device__ __forceinline__ void fenceRelease() { asm volatile("fence.release.gpu;" ::: "memory"); }
@@ -98,9 +98,6 @@ __device__ __forceinline__ void stCarried(double* p, double v, unsigned long lon
 }
 __device__ __forceinline__ void redAdd32(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void redOr32(uint32_t* p, uint32_t v) {
-  asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void stRelaxed32(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -125,6 +122,8 @@ __global__ void __launch_bounds__(W * 32, 1)
   uint32_t* maskCur = reinterpret_cast<uint32_t*>(smem + lay.maskA);
   uint32_t* maskNext = reinterpret_cast<uint32_t*>(smem + lay.maskB);
   uint32_t* remInS = reinterpret_cast<uint32_t*>(smem + lay.remIn);
+  uint32_t* clsOffS = reinterpret_cast<uint32_t*>(smem + lay.cls);  // [kNotifyClasses + 1] then the states, by class
+  uint32_t* clsStS = clsOffS + kNotifyClasses + 1;
   uint4* hdrS = reinterpret_cast<uint4*>(smem + lay.hdr);
   uint2* hdr2S = reinterpret_cast<uint2*>(smem + lay.hdr2);
   uint2* inS = reinterpret_cast<uint2*>(smem + lay.inE);
@@ -139,7 +138,10 @@ __global__ void __launch_bounds__(W * 32, 1)
     for (uint32_t i = tid; i < M; i += nThreads) {
       hdrS[i] = tb.hdr[rank * M + i];
       hdr2S[i] = tb.hdr2[rank * M + i];
-      if (kTeam) remInS[i] = tb.remoteIn[rank * M + i];
+      if (kTeam) {
+        remInS[i] = tb.remoteIn[rank * M + i];
+        clsStS[i] = tb.clsStates[rank * M + i];
+      }
       maskCur[i] = 0;
       maskNext[i] = 0;
     }
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(W * 32, 1)
     for (uint32_t i = tid; i < tb.nSyms * 16; i += nThreads) tsE[i] = tb.tsE[i];
     if (tid < 16) subS[tid] = tb.sub[tid];
     if (tid < 64) ctl[tid] = 0;
+    if (kTeam && tid <= kNotifyClasses) clsOffS[tid] = tb.clsOff[rank * (kNotifyClasses + 1) + tid];
   }
   __syncthreads();
 
@@ -170,14 +173,17 @@ __global__ void __launch_bounds__(W * 32, 1)
   double* const privT = args.priv + (size_t)team * Np * privKinds * 32 + lane;
   const unsigned long long polLast = policyEvictLast();
   double2* const sdPubT = args.sdPub + (size_t)team * 2 * Np * 32;  // two parities of the column
-  // Team protocol (no returning atomic, no flag to clear): notifyT[c] counts the notifications ever sent to CTA c;
-  // passiveT[parity] = (CTAs of this column that are passive) - (notifications sent and not yet consumed).  A sender
-  // subtracts 1 BEFORE the fence that precedes its notification; a receiver adds what it consumed when it consumes it;
-  // so the count can only reach T when every CTA is passive and nothing is undelivered.
-  uint32_t* const notifyT = args.teamState + (size_t)team * T;
+  // Team protocol (no returning atomic, no flag to clear).  The states of a CTA that have transitions from other CTAs are
+  // dealt into kNotifyClasses classes; notifyT[c * kNotifyClasses + q] counts the notifications ever sent to class q of
+  // CTA c ("a source of some state of that class published a new row").  passiveT[parity] = (CTAs of this column that are
+  // passive) - (notifications sent and not yet consumed): a sender subtracts its notifications BEFORE the fence that
+  // precedes them; the receiver adds what it consumed when it consumes it; so the count can only reach T when every CTA is
+  // passive and nothing is undelivered.  Lane q of warp 0 polls class q (one 128-byte line for the warp) and flags only
+  // that class's states: a wake-up re-relaxes a 32nd of the transitions that cross CTAs instead of all of them.
+  uint32_t* const notifyT = args.teamState + (size_t)team * T * kNotifyClasses;
   uint32_t* const passiveT = args.teamPassive + (size_t)team * 2;
-  uint32_t* const inboxT = args.inbox + (size_t)team * Np;
-  uint32_t notifySeen = 0;  // (thread 0) notifications consumed so far; the counters are zeroed before the launch
+  uint32_t notifySeen = 0;  // (level-synchronous variant, thread 0) notifications consumed so far; the asynchronous closure keeps
+                            // one count per class in ctl[kCtlSeen..]; the counters are zeroed before the launch
   unsigned long long* const bar = args.barrier + team;
   unsigned long long barTarget = 0;
   uint32_t col = 0;
@@ -264,6 +270,7 @@ __global__ void __launch_bounds__(W * 32, 1)
       // ---- (2) closure (src/viterbi.cpp:97-99,110-159), owner-computes edge relaxation ----
       const bool asyncClosure = args.asyncClosure != 0;
       uint32_t* const idleS = const_cast<uint32_t*>(reinterpret_cast<volatile uint32_t*>(ctl) + kCtlPending);
+      uint32_t* const lockS = const_cast<uint32_t*>(reinterpret_cast<volatile uint32_t*>(ctl) + kCtlLock);
       uint32_t remotePending = 0;  // slots of this warp that grew and have successors in other CTAs
       // relaxes the flagged in-transitions of state d (all of them when `allIn` or when there are few); when a lane
       // grew: stores the row, publishes it if some successor lives in another CTA, flags the local successors' masks.
@@ -367,44 +374,29 @@ __global__ void __launch_bounds__(W * 32, 1)
         uint32_t nNotes = 0;
         for (uint32_t rp = remotePending; rp; rp &= rp - 1u) {
           const uint4 h = hdrS[((uint32_t)__ffs((int)rp) - 1u) * W + warp];
-          nNotes += bhNOut(h) - bhNOutLocal(h) - bhNOutRemote(h);
+          nNotes += bhNOut(h) - bhNOutLocal(h);
         }
-        const bool eager = args.eagerNotify != 0 && !args.preciseWake;
+        const bool eager = args.eagerNotify != 0;
         if (lane == 0) redAdd32(passiveCol, 0u - (eager ? 2u * nNotes : nNotes));
         if (eager) {
-          // Eager notification: sent at once, WITHOUT waiting for the fence.  The rows were stored a few hundred cycles ago
-          // and usually are visible when the target reads them; if not, the target relaxes against the old rows, finds
-          // nothing, and the second notification below -- after the fence -- wakes it again.  Both are counted.
+          // Eager notification (option, off): sent at once, WITHOUT waiting for the fence.  The rows were stored a few
+          // hundred cycles ago and usually are visible when the target reads them; if not, the target relaxes against the
+          // old rows, finds nothing, and the second notification below -- after the fence -- wakes it again.  Both count.
           __syncwarp();
           for (uint32_t rp = remotePending; rp; rp &= rp - 1u) {
             const uint4 h = hdrS[((uint32_t)__ffs((int)rp) - 1u) * W + warp];
-            const uint32_t first = bhOutOff(h) + bhNOutLocal(h) + bhNOutRemote(h), last = bhOutOff(h) + bhNOut(h);
+            const uint32_t first = bhOutOff(h) + bhNOutLocal(h), last = bhOutOff(h) + bhNOut(h);
             for (uint32_t o = first + lane; o < last; o += 32) redAdd32(notifyT + outS[o], 1u);
           }
         }
         fenceRelease();
         __syncwarp();
-        if (args.preciseWake) {
-          // which transitions of which states: bits in the owners' inbox words.  They must not be visible before the rows
-          // (an owner that takes a bit early would relax against the old row and the bit would be gone), nor after the
-          // notification (it would find nothing and go passive): a fence on either side.
-          for (uint32_t rp = remotePending; rp; rp &= rp - 1u) {
-            const uint4 h = hdrS[((uint32_t)__ffs((int)rp) - 1u) * W + warp];
-            const uint32_t first = bhOutOff(h) + bhNOutLocal(h), nRem = bhNOutRemote(h);
-            for (uint32_t o = lane; o < nRem; o += 32) {
-              const uint32_t w = outS[first + o];
-              redOr32(inboxT + boRank(w) * M + boLocal(w), 1u << boBit(w));
-            }
-          }
-          fenceRelease();
-          __syncwarp();
-        }
         while (remotePending) {
           const uint32_t sl = (uint32_t)__ffs((int)remotePending) - 1u;
           remotePending &= remotePending - 1u;
           const uint4 h = hdrS[sl * W + warp];
-          const uint32_t first = bhOutOff(h) + bhNOutLocal(h) + bhNOutRemote(h), last = bhOutOff(h) + bhNOut(h);
-          for (uint32_t o = first + lane; o < last; o += 32) redAdd32(notifyT + outS[o], 1u);  // the CTAs that own successors
+          const uint32_t first = bhOutOff(h) + bhNOutLocal(h), last = bhOutOff(h) + bhNOut(h);
+          for (uint32_t o = first + lane; o < last; o += 32) redAdd32(notifyT + outS[o], 1u);  // (owner CTA, class) of the successors
         }
       };
 
@@ -468,11 +460,26 @@ __global__ void __launch_bounds__(W * 32, 1)
             idle = true;
           }
           if (ctl[kCtlPhase] != 0u) break;
-          if (warp != 0) {
+          // ONE idle warp at a time looks after the CTA -- notifications from other CTAs, the quiet check, the team's
+          // termination -- whichever gets the lock: a notification does not wait for a particular warp to run out of work
+          uint32_t mine = 0;
+          if (lane == 0) mine = atomicCAS(lockS, 0u, 1u) == 0u;
+          if (!__shfl_sync(0xFFFFFFFFu, mine, 0)) {
             if (args.idleNs) __nanosleep(args.idleNs);
             continue;
           }
-          // warp 0, idle: is the CTA quiet?  (all warps idle, then every mask zero, then still all idle)
+          auto unlock = [&]() {
+            __syncwarp();
+            if (lane == 0) {
+              __threadfence_block();
+              atomicExch(lockS, 0u);
+            }
+          };
+          if (ctl[kCtlPhase] != 0u) {  // the column ended between the test above and the lock
+            unlock();
+            break;
+          }
+          // is the CTA quiet?  (all warps idle, then every mask zero, then still all idle)
           bool quiet = false;
           if (ctl[kCtlPending] == W) {
             bool any = false;
@@ -480,60 +487,77 @@ __global__ void __launch_bounds__(W * 32, 1)
             quiet = !__any_sync(0xFFFFFFFFu, any) && ctl[kCtlPending] == W;
           }
           uint32_t action = 0;  // 1: a neighbour CTA published new rows, 2: the column's closure is complete
-          if (lane == 0) {
-            if (!kTeam) {
-              if (quiet) action = 2;
-            } else {
-              uint32_t c = ldVolatileGlobal32(notifyT + rank);
-              if (c != notifySeen) {  // new rows published by neighbours: consume (this CTA is not counted passive now)
-                redAdd32(passiveCol, c - notifySeen);
-                notifySeen = c;
-                action = 1;
-              } else if (quiet) {
-                unsigned long long t0 = 0;
-                if (kDebug) t0 = clock64();
-                redAdd32(passiveCol, 1u);  // passive
-                for (;;) {
-                  c = ldVolatileGlobal32(notifyT + rank);
-                  if (c != notifySeen) {
-                    redAdd32(passiveCol, c - notifySeen - 1u);  // active again, and these notifications are consumed
-                    notifySeen = c;
-                    action = 1;
-                    break;
-                  }
-                  if (ldVolatileGlobal32(passiveCol) == T) {
-                    action = 2;
-                    break;
-                  }
+          uint32_t delta = 0;   // lane q: new notifications of class q
+          if (!kTeam) {
+            if (quiet) action = 2;
+          } else {
+            uint32_t seen = ctl[kCtlSeen + lane];  // notifications of class `lane` consumed so far (kept by the lock holder)
+            // lane q reads the counter of class q (one line for the warp); returns the warp's total of new notifications
+            auto pollClasses = [&]() -> uint32_t {
+              const uint32_t c = ldVolatileGlobal32(notifyT + rank * kNotifyClasses + lane);
+              delta = c - seen;
+              seen = c;
+              return __any_sync(0xFFFFFFFFu, delta != 0u) ? __reduce_add_sync(0xFFFFFFFFu, delta) : 0u;
+            };
+            uint32_t tot = pollClasses();
+            if (tot) {  // new rows published by neighbours: consumed (this CTA is not counted passive now)
+              if (lane == 0) redAdd32(passiveCol, tot);
+              action = 1;
+            } else if (quiet) {
+              unsigned long long t0 = 0;
+              if (kDebug) t0 = clock64();
+              if (lane == 0) redAdd32(passiveCol, 1u);  // passive
+              for (;;) {
+                tot = pollClasses();
+                if (tot) {
+                  if (lane == 0) redAdd32(passiveCol, tot - 1u);  // active again, and these notifications are consumed
+                  action = 1;
+                  break;
                 }
-                if (kDebug) dbgPassive += clock64() - t0;
+                uint32_t p = lane == 0 ? ldVolatileGlobal32(passiveCol) : 0u;
+                p = __shfl_sync(0xFFFFFFFFu, p, 0);
+                if (p == T) {
+                  action = 2;
+                  break;
+                }
               }
+              if (kDebug) dbgPassive += clock64() - t0;
             }
+            ctl[kCtlSeen + lane] = seen;
           }
-          action = __shfl_sync(0xFFFFFFFFu, action, 0);
           if (action == 2) {
             if (lane == 0) ctl[kCtlPhase] = 1u;
+            unlock();
           } else if (action == 1) {
             if (kDebug) ++dbgWakes;
-            // every state with transitions from other CTAs relaxes them again; the flagging warp is not idle meanwhile
+            // the states of the notified classes relax their transitions from other CTAs again; the flagging warp is not
+            // idle meanwhile
             if (lane == 0) atomicSub(idleS, 1u);
             idle = false;
             __syncwarp();
-            for (uint32_t i = lane; i < M; i += 32) {
-              uint32_t rm = remInS[i];
-              if (rm && args.preciseWake) {  // only the transitions whose sources were published (the bits were set before the notification)
-                uint32_t* box = inboxT + rank * M + i;
-                rm = ldVolatileGlobal32(box);
-                if (rm) rm = atomicExch(box, 0u);
+            for (uint32_t notified = __ballot_sync(0xFFFFFFFFu, delta != 0u); notified; notified &= notified - 1u) {
+              const uint32_t c = (uint32_t)__ffs((int)notified) - 1u;
+              for (uint32_t q = clsOffS[c] + lane; q < clsOffS[c + 1]; q += 32) {
+                const uint32_t i = clsStS[q];
+                atomicOr(maskCur + i, remInS[i]);
               }
-              if (rm) atomicOr(maskCur + i, rm);
             }
-          } else if (args.idleNs)
-            __nanosleep(args.idleNs / 2);
+            unlock();
+          } else {
+            unlock();
+            if (args.idleNs) __nanosleep(args.idleNs / 2);
+          }
         }
         __syncthreads();
       } else
       {
+        // (level-synchronous variant, async_closure = 0: thread 0 keeps the TOTAL over the classes in notifySeen and a
+        // wake-up flags every transition that crosses CTAs)
+        auto notifyTotal = [&]() -> uint32_t {
+          uint32_t t = 0;
+          for (uint32_t q = 0; q < kNotifyClasses; ++q) t += ldVolatileGlobal32(notifyT + rank * kNotifyClasses + q);
+          return t;
+        };
         uint32_t lvl = 0;
         bool activated = false;
         // level 0: every transition of every state
@@ -566,7 +590,7 @@ __global__ void __launch_bounds__(W * 32, 1)
               uint32_t decision;
               redAdd32(passiveCol, 1u);  // passive
               for (;;) {
-                const uint32_t c = ldVolatileGlobal32(notifyT + rank);
+                const uint32_t c = notifyTotal();
                 if (c != notifySeen) {
                   redAdd32(passiveCol, c - notifySeen - 1u);  // active again, and these notifications are consumed
                   notifySeen = c;
@@ -589,7 +613,7 @@ __global__ void __launch_bounds__(W * 32, 1)
           if (kDebug && wake) ++dbgWakes;
           activated = false;
           uint32_t st = 0;
-          if (kTeam && tid == 0) st = ldVolatileGlobal32(notifyT + rank);  // consumed after this level's work
+          if (kTeam && tid == 0) st = notifyTotal();  // consumed after this level's work
           const uint32_t iMine = lane * W + warp;
           uint32_t mym = 0;
           if (lane < nSlots && iMine < M) {
@@ -597,15 +621,7 @@ __global__ void __launch_bounds__(W * 32, 1)
               mym = maskCur[iMine];
               if (mym) maskCur[iMine] = 0;
             }
-            if (wake) {  // a neighbour CTA published new rows
-              uint32_t rm = remInS[iMine];
-              if (rm && args.preciseWake) {
-                uint32_t* box = inboxT + rank * M + iMine;
-                rm = ldVolatileGlobal32(box);
-                if (rm) rm = atomicExch(box, 0u);
-              }
-              mym |= rm;
-            }
+            if (wake) mym |= remInS[iMine];  // a neighbour CTA published new rows
           }
           uint32_t work = __ballot_sync(0xFFFFFFFFu, mym != 0);
           while (work) {
@@ -796,8 +812,8 @@ __global__ void __launch_bounds__(W * 32, 1)
     atomicAdd(&args.dbg[3], dbgEdges);
     if (warp == 0) atomicAdd(&args.dbg[4], dbgClosure);
     if (warp == 0) atomicAdd(&args.dbg[5], dbgRecord);
-    if (warp == 0) atomicAdd(&args.dbg[6], dbgWakes);
-    if (warp == 0) atomicAdd(&args.dbg[7], dbgPassive);
+    atomicAdd(&args.dbg[6], dbgWakes);    // (asynchronous closure: whichever warp held the CTA's lock)
+    atomicAdd(&args.dbg[7], dbgPassive);
     if (warp == 0) atomicAdd(&args.dbg[8], dbgInit);
     if (warp == 0) atomicAdd(&args.dbg[9], dbgBarrier);
     atomicAdd(&args.dbg[10], dbgRelaxCyc);

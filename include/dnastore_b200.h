@@ -137,8 +137,11 @@ int dnab_decoder_configure_ex(dnab_decoder* d, uint32_t block_table_mode, uint32
  *   "thin_n", "t_recompute", "queue_cap", "deal_chunks", "idle_sleep_ns": schedule knobs of the push kernel (tests)
  *   "async_closure"   read-batched kernel: 0 breadth-first levels with a CTA barrier each, 1 no level barriers (work counter), 2 (default)
  *                     automatic = 1 in a team, 0 in a single CTA; "batch_idle_ns" back-off of an idle warp; "team_slack_pct"
- *   "precise_wake"    read-batched kernel, teams: 1 = a notified CTA re-relaxes only the transitions flagged in its inbox words (costs a
- *                     second release fence per notification; measured slower), 0 (default) = every transition that crosses CTAs
+ *   "notify_classes"  read-batched kernel, teams: notification counters per CTA, 1..32 (default 32).  The states of a CTA that have
+ *                     transitions from other CTAs are dealt into that many classes; a publishing state notifies the classes of its
+ *                     successors and the owner re-relaxes only the notified classes (1 = every transition that crosses CTAs)
+ *   "eager_notify"    read-batched kernel, teams: 1 = every notification is also sent once before the release fence (measured slower:
+ *                     the extra wake-ups cost more than the fence latency they save), 0 (default)
  *   "persist_l2"      read-batched kernel: 1 gives the rows carried between columns a persisting L2 access-policy window (default 0:
  *                     measured on B200 it DOUBLES the DRAM writes; the rows carry an evict-last cache hint instead)
  *   "pred_budget_mb"  device memory the predecessor records of one launch may take

@@ -259,14 +259,15 @@ def test_gpu_batch_kernel_every_team_size(d, name, team, warps, async_closure):
     _check_reads(d, dec, case, (name, team, warps))
 
 
+@pytest.mark.parametrize("classes", [1, 5, 32])
 @pytest.mark.parametrize("name", ["mr2l4c4_local", "cfg4_global_dels", "cfg5_l8_local", "cfg2_global_subs"])
-def test_gpu_batch_kernel_precise_wake_same_bits(d, name):
-    """Teams: a notified CTA either re-relaxes every transition that crosses CTAs (default) or only the ones flagged in its
-    inbox words (option precise_wake): a schedule choice, no bit may change."""
+def test_gpu_batch_kernel_notification_classes_same_bits(d, name, classes):
+    """Teams: a notified CTA re-relaxes the transitions from other CTAs of the notified classes of its states only (32
+    classes by default; 1 = every such transition): a schedule choice, no bit may change."""
     case = util.golden_case(name)
     dec = d.Decoder(util.compiled_for_case(case), device=0)
     dec.set_option("kernel", 1)
-    dec.set_option("precise_wake", 1)
+    dec.set_option("notify_classes", classes)
     _check_reads(d, dec, case, name)
 
 
