@@ -12,8 +12,10 @@
 // has a 32-bit work mask, bit j = "in-transition j's source grew (for some read of the group)".  The warp
 // that owns a state relaxes exactly the flagged transitions (reading the source's row, writing only its own
 // row: no atomics on DP cells, no lost updates), and if any lane grew it flags the corresponding bit of
-// each successor's mask.  Levels are breadth first (level 0 relaxes every transition of every state), one
-// CTA barrier per level.  tools/union_frontier.py measured what sharing one frontier among 32 reads costs:
+// each successor's mask.  By default there are no levels and no barriers inside a column: every warp keeps
+// relaxing whichever of its states are flagged until the CTA (the team) is quiet; the first version's
+// breadth-first levels with one CTA barrier each are still selectable (async_closure = 0).
+// tools/union_frontier.py measured what sharing one frontier among 32 reads costs:
 // 2.9-7.6 state visits per column instead of 2.0-2.9 per read, i.e. 0.09-0.24 warp-level visits per read.
 //
 // A TEAM of T CTAs holds the (S,D) columns of one group in shared memory, M = ceil(N/T) states each
