@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(W * 32, 1)
           // ONE idle warp at a time looks after the CTA -- notifications from other CTAs, the quiet check, the team's
           // termination -- whichever gets the lock: a notification does not wait for a particular warp to run out of work
           uint32_t mine = 0;
-          if (lane == 0) mine = atomicCAS(lockS, 0u, 1u) == 0u;
+          if (lane == 0) mine = ctl[kCtlLock] == 0u && atomicCAS(lockS, 0u, 1u) == 0u;  // (peek first: 31 warps may be idle)
           if (!__shfl_sync(0xFFFFFFFFu, mine, 0)) {
             if (args.idleNs) __nanosleep(args.idleNs);
             continue;
