@@ -165,3 +165,19 @@ def test_fasta_ingest_forms_through_the_exact_decoder(tmp_path):
     assert d.exact_decode_fasta(m, gz)[0] == b"HELLO"
     with pytest.raises(d.DnabError):
         d.exact_decode_fasta(m, tmp_path / "missing.fa")
+
+
+def test_every_option_key_is_documented_in_the_header():
+    """dnab_decoder_set_option / dnab_multi_decoder_set_option: a key the library accepts is a key the ABI header explains."""
+    import re
+    root = util.ROOT
+    header = open(os.path.join(root, "include", "dnastore_b200.h")).read()
+    dec = open(os.path.join(root, "dnastore_b200", "csrc", "decoder.cu")).read()
+    body = dec[dec.index("int dnab_decoder_set_option("):]
+    body = body[:body.index("\n}\n")]
+    keys = re.findall(r'k == "([a-z_0-9]+)"', body)
+    pipe = open(os.path.join(root, "dnastore_b200", "csrc", "pipeline.cpp")).read()
+    keys += re.findall(r'== "([a-z_0-9]+)"', pipe[pipe.index("dnab_multi_decoder_set_option("):])
+    assert len(keys) >= 20
+    missing = [k for k in keys if f'"{k}"' not in header]
+    assert not missing, missing
