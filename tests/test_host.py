@@ -181,3 +181,16 @@ def test_every_option_key_is_documented_in_the_header():
     assert len(keys) >= 20
     missing = [k for k in keys if f'"{k}"' not in header]
     assert not missing, missing
+
+
+def test_profile_files_named_in_the_docs_exist():
+    """profiles/README.md and DESIGN.md cite ncu summaries by file name: every cited file is committed, and every
+    round-2 summary is described in the README."""
+    root = util.ROOT
+    have = set(os.listdir(os.path.join(root, "profiles")))
+    readme = open(os.path.join(root, "profiles", "README.md")).read()
+    design = open(os.path.join(root, "DESIGN.md")).read()
+    cited = set(re.findall(r"(r0[12]_[a-z0-9_]+\.(?:txt|json|csv))", readme + design))
+    assert cited and not (cited - have), sorted(cited - have)
+    undocumented = {f for f in have if f.startswith("r02_") and f not in readme}
+    assert not undocumented, sorted(undocumented)
